@@ -1,0 +1,149 @@
+/* nans_b200.h — C ABI of libnans_b200.so: the B200 (sm_100a) rigid-body step.
+ *
+ * This is the thin extern "C" CUDA layer behind the reference's game-layer plugin entry
+ *     extern "C" void SimUpdateAndRender(memory*, sdl_input*, sdl_render*, real32 dt)
+ * (reference: code/nans.h:396-397, code/nans.cpp:1719).  Each entry point below replaces one
+ * reference function or data structure on that path (cited per declaration).  Signatures are
+ * plain C: opaque handle, plain pointers and sizes; no torch / C++ types.
+ *
+ * Memory model: the reference places its whole world (`sdl_state`, code/nans.h:374-386) at
+ * offset 0 of one host-owned mmap block (code/sdl_nans.cpp:541-555) and keeps contact lists and
+ * GJK/EPA scratch in std::vector.  Here the world lives in ONE device arena (a single cudaMalloc,
+ * or caller-provided device memory) carved once into SoA body / shape / pair / contact / scratch
+ * regions; nothing is allocated during stepping.
+ *
+ * Error behaviour: the reference path returns void and reports nothing.  Every call here returns
+ * 0 on success or a negative nans_status; nans_last_error() gives the text.  There is NO CPU
+ * fallback: without a usable CUDA device every call fails with NANS_ERR_CUDA.
+ */
+#ifndef NANS_B200_H
+#define NANS_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+    NANS_OK = 0,
+    NANS_ERR_CUDA = -1,      /* CUDA runtime error / no device */
+    NANS_ERR_ARG = -2,       /* bad argument */
+    NANS_ERR_CAPACITY = -3,  /* pair / contact / EPA-arena capacity exceeded (results truncated) */
+    NANS_ERR_STATE = -4      /* call order (e.g. solve before detect) */
+} nans_status;
+
+/* collision_type, code/nans.h:71-87 */
+enum { NANS_CC = 0, NANS_CS = 1, NANS_CF = 2, NANS_SS = 3, NANS_SF = 4 };
+
+typedef struct nans_world nans_world; /* opaque; replaces sdl_state (code/nans.h:374-386) */
+
+/* World capacities; replaces MAX_CUBE_COUNT / MAX_SPHERE_COUNT (code/nans.h:52-53). */
+typedef struct {
+    int32_t n_cubes;        /* dynamic boxes, body rows [0, n_cubes) */
+    int32_t n_spheres;      /* dynamic spheres, body rows [n_cubes, n_cubes+n_spheres) */
+    int32_t n_statics;      /* floor-type slabs (reference: exactly one, the Floor) */
+    int32_t max_pairs;      /* broadphase candidate capacity (0 = default 24 * bodies) */
+    int32_t max_contacts;   /* contact capacity            (0 = default 12 * bodies) */
+    int32_t device;         /* CUDA device ordinal */
+    void *arena;            /* optional caller-provided device arena (e.g. a torch tensor) */
+    uint64_t arena_bytes;   /* its size; ignored when arena == NULL */
+    void *stream;           /* cudaStream_t to run on (NULL = library-owned stream) */
+} nans_world_desc;
+
+/* Host-side view of the world state: the same fields as struct cube / sphere
+ * (code/nans.h:303-336), as arrays.  Any pointer may be NULL (field skipped).
+ * Rows: cubes first, then spheres ("nb" = n_cubes + n_spheres). */
+typedef struct {
+    float *pos, *vel, *force;       /* [nb][3]  Position, V, Forces */
+    float *ang, *angvel, *torque;   /* [nb][3]  Angles, W, Torque */
+    float *mass, *moi;              /* [nb]     Mass, MOI */
+    float *scale;                   /* [nb][3]  model scale (Size, or (.5,1,.5)*Size for the debug box) */
+    float *radius;                  /* [nb]     Radius (spheres) */
+    float *verts;                   /* [n_cubes][8][3] Vertices (world space, reference order) */
+    float *st_pos, *st_ang, *st_scale; /* [n_statics][3] */
+    float *st_mass, *st_moi;        /* [n_statics] */
+    float *st_verts;                /* [n_statics][8][3] */
+    int32_t *world_id;              /* [nb] optional independent-world id (batched worlds); NULL = one world */
+} nans_scene_view;
+
+/* The meaningful fields of contact_pair (code/nans.h:339-372), reference index conventions:
+ * a/b index cubes for CC; cube,sphere for CS; cube,static for CF; spheres for SS; sphere,static
+ * for SF. */
+typedef struct {
+    int32_t type, a, b;
+    float point_a[3], point_b[3], n[3];
+} nans_contact;
+
+/* Per-step counters (device -> host on request). */
+typedef struct {
+    int32_t n_pairs;          /* broadphase candidates */
+    int32_t n_contacts;       /* contacts after GJK+EPA (reference-order list length) */
+    int32_t n_gjk_found;      /* pairs whose GJK reported FoundIntersection */
+    int32_t solver_levels;    /* dependency levels the exact-order solver ran */
+    int32_t overflow;         /* bit0 pairs, bit1 contacts, bit2 EPA faces, bit3 EPA edges, bit4 cell list */
+    int32_t max_epa_faces;    /* high-water mark of the per-thread polytope arena */
+    int32_t reserved[2];
+} nans_step_stats;
+
+/* ---- lifecycle ------------------------------------------------------------------------- */
+/* replaces the host's mmap + `sdl_state at PermanentStorage+0` (code/sdl_nans.cpp:541-555,
+ * code/nans.cpp:1721); desc->arena NULL => one cudaMalloc. */
+int nans_world_create(const nans_world_desc *desc, nans_world **out);
+void nans_world_destroy(nans_world *w);
+uint64_t nans_world_arena_bytes(const nans_world_desc *desc); /* bytes create() will carve */
+const char *nans_last_error(void);
+int nans_device_count(void);
+
+/* ---- state transfer (host buffers; copies are on the world's stream, synchronous on return) */
+/* replaces Init's field-by-field scene set-up (code/nans.cpp:1598-1678) */
+int nans_world_upload(nans_world *w, const nans_scene_view *scene);
+int nans_world_download(nans_world *w, nans_scene_view *scene);
+/* CubeAddForce/CubeAddTorque/SphereAddForce (code/nans.cpp:81-110): += on one body row */
+int nans_world_add_force(nans_world *w, int32_t body_row, const float force[3], const float torque[3]);
+/* overwrite a body's pose/velocities (ShootSphere teleport, code/nans.cpp:113-120; debug pokes :149-186) */
+int nans_world_set_body(nans_world *w, int32_t body_row, const float pos[3], const float vel[3],
+                        const float angvel[3]);
+
+/* ---- the four stages, one entry per reference function (asynchronous on the world's stream) */
+int nans_integrate_forces(nans_world *w, float dt);     /* IntegrateForces     code/nans.cpp:975  */
+int nans_detect_collisions(nans_world *w);              /* DetectCollisions    code/nans.cpp:1352 */
+int nans_solve_constraints(nans_world *w, float dt);    /* SolveConstraints    code/nans.cpp:1539 */
+int nans_integrate_velocities(nans_world *w, float dt); /* IntegrateVelocities code/nans.cpp:1332
+                                                           + model/vertex rebuild :1870-1881,1913-1941 */
+/* the draw section's model rebuild on its own (code/nans.cpp:1870-1881,1913-1941 + UpdateVertices
+ * :395-407): Model = T*Rx*Ry*Rz*S -> 8 world vertices for every cube and static, from the pose */
+int nans_rebuild_vertices(nans_world *w);
+/* the step as SimUpdateAndRender runs it (code/nans.cpp:1758-1762) */
+int nans_step(nans_world *w, float dt);
+int nans_synchronize(nans_world *w);
+
+/* results of the last detect/step */
+int nans_get_stats(nans_world *w, nans_step_stats *out);                 /* synchronises */
+int nans_get_contacts(nans_world *w, nans_contact *out, int32_t cap, int32_t *count); /* Pairs vector, code/nans.h:385 */
+int nans_get_pairs(nans_world *w, int32_t *pair_a, int32_t *pair_b, int32_t cap, int32_t *count); /* body rows; statics as -(k+1) */
+/* replace the contact list (tests: solve from the oracle's contacts) */
+int nans_set_contacts(nans_world *w, const nans_contact *in, int32_t count);
+
+/* ---- stand-alone narrowphase, CheckCollision (code/nans.cpp:907-966) over n pairs (config C3)
+ * Inputs are world-space shapes: box = 8 vertices, sphere = centre + radius.  Host buffers;
+ * outputs: hit (bool32 result), gjk (evolve_result), N / PointA / PointB. */
+int nans_check_collision_batch(int32_t n, const int32_t *type,
+                               const float *pos_a, const float *verts_a, const float *rad_a,
+                               const float *pos_b, const float *verts_b, const float *rad_b,
+                               int32_t *hit, int32_t *gjk, float *out_n, float *out_pa, float *out_pb,
+                               int32_t device);
+
+/* device-resident variant for throughput measurement: buffers are DEVICE pointers
+ * (pos/rad: [n][4] float4 = xyz+radius; verts: [n][8][3]; out_contact: [n][3] float4) */
+int nans_check_collision_device(int32_t n, const int32_t *d_type,
+                                const float *d_posrad_a, const float *d_verts_a,
+                                const float *d_posrad_b, const float *d_verts_b,
+                                int32_t *d_hit, float *d_out, void *stream);
+
+/* kernel-launch counter (all launches issued by this library in this process) */
+uint64_t nans_kernel_launches(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,381 @@
+// broadphase.cu — candidate-pair generation.  The reference has NO broadphase: DetectCollisions
+// (code/nans.cpp:1352-1536) runs GJK on every pair of the world, O(N^2).  This stage produces a
+// superset of the pairs whose GJK can report a hit (AABB overlap, inclusive, inflated), emitted
+// ALREADY IN THE REFERENCE'S LIST ORDER — CC (i<j lexicographic), CF (by cube), SF (by sphere),
+// CS (cube-major), SS (i<j) — so that compaction of the narrowphase hits yields the reference's
+// contact list with no sort of the contacts.
+//
+//   aabb_key_kernel      AABB per body (8 vertices / centre +- radius) + 30-bit Morton cell key
+//   radix sort           4 x 8-bit LSD passes (histogram -> scan -> stable scatter), key+row payload
+//   gather_sorted_kernel AABBs permuted into Morton order (neighbour scans read contiguous ranges)
+//   cell_table_kernel    open-addressing hash: cell key -> [start, end) in the sorted order
+//   pair_count_kernel    per body, 27-cell scan, counts per (type, body)
+//   (exclusive scan)     offsets in reference order
+//   pair_emit_kernel     same scan, writes partners, sorts each short run ascending
+//
+// All kernels are HBM/L2-bound integer + compare work; see DESIGN.md §4 for bytes per body.
+#include "world.cuh"
+
+namespace nans {
+
+constexpr uint32_t kEmptyKey = 0xffffffffu;
+
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t expand_bits10(uint32_t v)
+{
+    v &= 0x3ffu;
+    v = (v | (v << 16)) & 0x030000ffu;
+    v = (v | (v << 8)) & 0x0300f00fu;
+    v = (v | (v << 4)) & 0x030c30c3u;
+    v = (v | (v << 2)) & 0x09249249u;
+    return v;
+}
+__device__ __forceinline__ uint32_t morton30(uint32_t x, uint32_t y, uint32_t z)
+{
+    return (expand_bits10(x) << 2) | (expand_bits10(y) << 1) | expand_bits10(z);
+}
+__device__ __forceinline__ uint32_t compact_bits10(uint32_t v)
+{
+    v &= 0x09249249u;
+    v = (v | (v >> 2)) & 0x030c30c3u;
+    v = (v | (v >> 4)) & 0x0300f00fu;
+    v = (v | (v >> 8)) & 0x030000ffu;
+    v = (v | (v >> 16)) & 0x3ffu;
+    return v;
+}
+
+// Conservative inflation: GJK accepts touching shapes (AddSupport uses >=, code/nans.cpp:528) and a
+// sphere support Radius*normalize(d) can exceed Radius by rounding, so boxes are grown by an
+// absolute + relative margin.  Only a superset is required; the final arbiter is GJK itself.
+__device__ __forceinline__ void inflate(float &lo, float &hi)
+{
+    const float m = 1e-3f + 1e-5f * fmaxf(fabsf(lo), fabsf(hi));
+    lo -= m;
+    hi += m;
+}
+
+__device__ __forceinline__ void box_aabb(const float4 *v6, float lo[3], float hi[3])
+{
+    float f[24];
+#pragma unroll
+    for (int q = 0; q < 6; ++q) {
+        const float4 t = v6[q];
+        f[4 * q] = t.x; f[4 * q + 1] = t.y; f[4 * q + 2] = t.z; f[4 * q + 3] = t.w;
+    }
+#pragma unroll
+    for (int r = 0; r < 3; ++r) { lo[r] = f[r]; hi[r] = f[r]; }
+#pragma unroll
+    for (int k = 1; k < 8; ++k)
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+            lo[r] = fminf(lo[r], f[3 * k + r]);
+            hi[r] = fmaxf(hi[r], f[3 * k + r]);
+        }
+#pragma unroll
+    for (int r = 0; r < 3; ++r) inflate(lo[r], hi[r]);
+}
+
+__device__ __forceinline__ int cell_coord(float c, float inv_cell)
+{
+    // floor(c / cell) biased to [0, 1023]; clamping is monotone, so AABB-overlapping bodies stay in
+    // adjacent cells even outside the addressable volume (only performance degrades there)
+    float f = floorf(c * inv_cell);
+    f = fminf(fmaxf(f, -512.0f), 511.0f);
+    return (int)f + 512;   // NaN -> (int)NaN = 0 -> 512
+}
+
+__global__ void __launch_bounds__(256) aabb_key_kernel(DeviceWorld w, float inv_cell)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < w.n_statics) {   // statics: AABB only (tested against every body, never sorted)
+        float lo[3], hi[3];
+        box_aabb(w.st_verts + 6 * i, lo, hi);
+        w.st_aabb[2 * i] = make_float4(lo[0], lo[1], lo[2], 0.f);
+        w.st_aabb[2 * i + 1] = make_float4(hi[0], hi[1], hi[2], 0.f);
+    }
+    if (i >= w.nb) return;
+    float lo[3], hi[3];
+    if (i < w.n_cubes) {
+        box_aabb(w.verts + 6 * (size_t)i, lo, hi);
+    } else {
+        const float4 p = w.pos[i];
+        const float r = w.scale[i].w;
+        lo[0] = p.x - r; lo[1] = p.y - r; lo[2] = p.z - r;
+        hi[0] = p.x + r; hi[1] = p.y + r; hi[2] = p.z + r;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) inflate(lo[k], hi[k]);
+    }
+    w.aabb_lo[i] = make_float4(lo[0], lo[1], lo[2], 0.f);
+    w.aabb_hi[i] = make_float4(hi[0], hi[1], hi[2], 0.f);
+    int cx = cell_coord(0.5f * (lo[0] + hi[0]), inv_cell);
+    int cy = cell_coord(0.5f * (lo[1] + hi[1]), inv_cell);
+    int cz = cell_coord(0.5f * (lo[2] + hi[2]), inv_cell);
+    if (w.world_id) {
+        // batched independent worlds: each world owns a 16x16 column of cells in x,z
+        const int wid = w.world_id[i];
+        cx = min(max(cx - 512 + 8, 0), 15) + 16 * (wid & 63);
+        cz = min(max(cz - 512 + 8, 0), 15) + 16 * ((wid >> 6) & 63);
+    }
+    w.key[0][i] = morton30((uint32_t)cx, (uint32_t)cy, (uint32_t)cz);
+    w.val[0][i] = (uint32_t)i;
+}
+
+// ---------------------------------------------------------------------------------------------
+// LSD radix sort, 8 bits per pass.
+constexpr int kRadixThreads = 256;
+constexpr int kRadixItems = 16;
+constexpr int kRadixTile = kRadixThreads * kRadixItems;  // 4096 keys per block
+
+__global__ void __launch_bounds__(kRadixThreads) radix_hist_kernel(const uint32_t *__restrict__ keys, int n,
+                                                                   int shift, uint32_t *__restrict__ hist,
+                                                                   int n_blocks)
+{
+    __shared__ uint32_t h[256];
+    h[threadIdx.x] = 0;
+    __syncthreads();
+    const int base = blockIdx.x * kRadixTile;
+#pragma unroll 4
+    for (int k = 0; k < kRadixItems; ++k) {
+        const int i = base + k * kRadixThreads + threadIdx.x;
+        if (i < n) atomicAdd(&h[(keys[i] >> shift) & 255u], 1u);
+    }
+    __syncthreads();
+    hist[threadIdx.x * n_blocks + blockIdx.x] = h[threadIdx.x];  // digit-major: one scan gives offsets
+}
+
+__global__ void __launch_bounds__(kRadixThreads) radix_scatter_kernel(
+    const uint32_t *__restrict__ keys_in, const uint32_t *__restrict__ vals_in,
+    uint32_t *__restrict__ keys_out, uint32_t *__restrict__ vals_out, int n, int shift,
+    const uint32_t *__restrict__ hist_scanned, int n_blocks)
+{
+    __shared__ uint32_t base_off[256];            // running global offset per digit for this block
+    __shared__ uint32_t warp_cnt[kRadixThreads / 32][256];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    base_off[threadIdx.x] = hist_scanned[threadIdx.x * n_blocks + blockIdx.x];
+    const int tile = blockIdx.x * kRadixTile;
+    for (int k = 0; k < kRadixItems; ++k) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) warp_cnt[wid][q * 32 + lane] = 0;
+        __syncthreads();
+        const int i = tile + k * kRadixThreads + threadIdx.x;   // chunk k is contiguous: stable order
+        const bool valid = i < n;
+        uint32_t key = 0, val = 0, digit = 0;
+        if (valid) { key = keys_in[i]; val = vals_in[i]; digit = (key >> shift) & 255u; }
+        // rank among same-digit lanes of this warp (invalid lanes use a private pseudo-digit)
+        const uint32_t peers = __match_any_sync(0xffffffffu, valid ? digit : 0x100u + lane);
+        const uint32_t rank = __popc(peers & ((1u << lane) - 1u));
+        if (valid && rank == 0) warp_cnt[wid][digit] = __popc(peers);
+        __syncthreads();
+        // thread d: exclusive prefix of digit d over the warps, then advance the block base
+        {
+            const int d = threadIdx.x;
+            uint32_t run = base_off[d];
+#pragma unroll
+            for (int q = 0; q < kRadixThreads / 32; ++q) {
+                const uint32_t c = warp_cnt[q][d];
+                warp_cnt[q][d] = run;
+                run += c;
+            }
+            base_off[d] = run;
+        }
+        __syncthreads();
+        if (valid) {
+            const uint32_t dst = warp_cnt[wid][digit] + rank;
+            keys_out[dst] = key;
+            vals_out[dst] = val;
+        }
+        __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// After the sort: AABBs in Morton order, w lanes carry body row / world id; hash table of cells.
+__global__ void __launch_bounds__(256) gather_sorted_kernel(DeviceWorld w, const uint32_t *__restrict__ keys,
+                                                            const uint32_t *__restrict__ vals,
+                                                            float4 *__restrict__ s_lo, float4 *__restrict__ s_hi)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= w.nb) return;
+    const uint32_t row = vals[t];
+    float4 lo = w.aabb_lo[row], hi = w.aabb_hi[row];
+    lo.w = __int_as_float((int)row);
+    hi.w = __int_as_float(w.world_id ? w.world_id[row] : 0);
+    s_lo[t] = lo;
+    s_hi[t] = hi;
+    // cell table: heads write start, tails write end (both find-or-insert, so no ordering race)
+    const uint32_t key = keys[t];
+    const bool head = (t == 0) || (keys[t - 1] != key);
+    const bool tail = (t == w.nb - 1) || (keys[t + 1] != key);
+    if (head || tail) {
+        uint32_t h = key * 0x9E3779B1u;
+        uint32_t slot = (h ^ (h >> 15)) & w.cell_mask;
+        while (true) {
+            const uint32_t prev = atomicCAS(&w.cell_keys[slot], kEmptyKey, key);
+            if (prev == kEmptyKey || prev == key) break;
+            slot = (slot + 1) & w.cell_mask;
+        }
+        if (head) w.cell_start[slot] = (uint32_t)t;
+        if (tail) w.cell_end[slot] = (uint32_t)t + 1u;
+    }
+}
+
+__device__ __forceinline__ bool cell_lookup(const DeviceWorld &w, uint32_t key, uint32_t &start, uint32_t &end)
+{
+    uint32_t h = key * 0x9E3779B1u;
+    uint32_t slot = (h ^ (h >> 15)) & w.cell_mask;
+    while (true) {
+        const uint32_t k = __ldg(&w.cell_keys[slot]);
+        if (k == key) { start = __ldg(&w.cell_start[slot]); end = __ldg(&w.cell_end[slot]); return true; }
+        if (k == kEmptyKey) return false;
+        slot = (slot + 1) & w.cell_mask;
+    }
+}
+
+__device__ __forceinline__ bool overlap(const float4 &alo, const float4 &ahi, const float4 &blo, const float4 &bhi)
+{
+    return alo.x <= bhi.x && blo.x <= ahi.x && alo.y <= bhi.y && blo.y <= ahi.y && alo.z <= bhi.z && blo.z <= ahi.z;
+}
+
+// segment order = reference list order (code/nans.cpp:1355-1535)
+enum { SEG_CC = 0, SEG_CF = 1, SEG_SF = 2, SEG_CS = 3, SEG_SS = 4 };
+
+// Visit every dynamic partner of sorted entry t that the reference would list under body `row`.
+// F(seg, partner_row)
+template <typename F>
+__device__ __forceinline__ void for_each_partner(const DeviceWorld &w, const uint32_t *__restrict__ keys,
+                                                 const float4 *__restrict__ s_lo, const float4 *__restrict__ s_hi,
+                                                 int t, F f)
+{
+    const float4 alo = s_lo[t], ahi = s_hi[t];
+    const int row = __float_as_int(alo.w);
+    const int wid = __float_as_int(ahi.w);
+    const bool a_cube = row < w.n_cubes;
+    const uint32_t key = keys[t];
+    const int cx = (int)compact_bits10(key >> 2), cy = (int)compact_bits10(key >> 1), cz = (int)compact_bits10(key);
+    for (int dz = -1; dz <= 1; ++dz)
+        for (int dy = -1; dy <= 1; ++dy)
+            for (int dx = -1; dx <= 1; ++dx) {
+                const int nx = cx + dx, ny = cy + dy, nz = cz + dz;
+                if ((unsigned)nx > 1023u || (unsigned)ny > 1023u || (unsigned)nz > 1023u) continue;
+                uint32_t s, e;
+                if (!cell_lookup(w, morton30((uint32_t)nx, (uint32_t)ny, (uint32_t)nz), s, e)) continue;
+                for (uint32_t u = s; u < e; ++u) {
+                    const float4 blo = s_lo[u], bhi = s_hi[u];
+                    const int brow = __float_as_int(blo.w);
+                    if (__float_as_int(bhi.w) != wid) continue;
+                    const bool b_cube = brow < w.n_cubes;
+                    int seg;
+                    if (a_cube) {
+                        if (b_cube) { if (brow <= row) continue; seg = SEG_CC; }
+                        else seg = SEG_CS;                       // cube-major: listed under the cube
+                    } else {
+                        if (b_cube || brow <= row) continue;     // CS is emitted by the cube
+                        seg = SEG_SS;
+                    }
+                    if (!overlap(alo, ahi, blo, bhi)) continue;
+                    f(seg, brow);
+                }
+            }
+}
+
+__global__ void __launch_bounds__(128) pair_count_kernel(DeviceWorld w, const uint32_t *__restrict__ keys,
+                                                         const float4 *__restrict__ s_lo,
+                                                         const float4 *__restrict__ s_hi)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= w.nb) return;
+    const float4 alo = s_lo[t], ahi = s_hi[t];
+    const int row = __float_as_int(alo.w);
+    uint32_t cnt[5] = {0, 0, 0, 0, 0};
+    for_each_partner(w, keys, s_lo, s_hi, t, [&](int seg, int) { cnt[seg]++; });
+    // statics: CF for cubes, SF for spheres, static index ascending
+    uint32_t ns = 0;
+    for (int k = 0; k < w.n_statics; ++k)
+        if (overlap(alo, ahi, w.st_aabb[2 * k], w.st_aabb[2 * k + 1])) ++ns;
+    cnt[row < w.n_cubes ? SEG_CF : SEG_SF] = ns;
+#pragma unroll
+    for (int s = 0; s < 5; ++s) w.pair_count[(size_t)s * w.nb + row] = cnt[s];
+}
+
+__global__ void __launch_bounds__(128) pair_emit_kernel(DeviceWorld w, const uint32_t *__restrict__ keys,
+                                                        const float4 *__restrict__ s_lo,
+                                                        const float4 *__restrict__ s_hi)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= w.nb) return;
+    const float4 alo = s_lo[t], ahi = s_hi[t];
+    const int row = __float_as_int(alo.w);
+    uint32_t off[5], fill[5] = {0, 0, 0, 0, 0};
+#pragma unroll
+    for (int s = 0; s < 5; ++s) off[s] = w.pair_count[(size_t)s * w.nb + row];   // scanned: offsets
+    const uint32_t cap = (uint32_t)w.max_pairs;
+    for_each_partner(w, keys, s_lo, s_hi, t, [&](int seg, int brow) {
+        const uint32_t p = off[seg] + fill[seg]++;
+        if (p < cap) { w.pair_a[p] = row; w.pair_b[p] = brow; }
+    });
+    const int sseg = row < w.n_cubes ? SEG_CF : SEG_SF;
+    for (int k = 0; k < w.n_statics; ++k)
+        if (overlap(alo, ahi, w.st_aabb[2 * k], w.st_aabb[2 * k + 1])) {
+            const uint32_t p = off[sseg] + fill[sseg]++;
+            if (p < cap) { w.pair_a[p] = row; w.pair_b[p] = -(k + 1); }
+        }
+    // each (body, type) run in ascending partner order = the reference's inner loop order
+    // (insertion sort in place; runs are a handful of entries)
+#pragma unroll
+    for (int s = 0; s < 5; ++s) {
+        if (s == SEG_CF || s == SEG_SF) continue;
+        const uint32_t b = off[s], n = fill[s];
+        if (b + n > cap) continue;
+        for (uint32_t i = 1; i < n; ++i) {
+            const int v = w.pair_b[b + i];
+            uint32_t j = i;
+            while (j > 0 && w.pair_b[b + j - 1] > v) { w.pair_b[b + j] = w.pair_b[b + j - 1]; --j; }
+            w.pair_b[b + j] = v;
+        }
+    }
+    if (t == 0) {
+        const uint32_t total = w.pair_count[(size_t)5 * w.nb];
+        w.counters->n_pairs = (int32_t)min(total, cap);
+        if (total > cap) atomicOr(&w.counters->overflow, OVF_PAIRS);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+int launch_broadphase(World *w)
+{
+    DeviceWorld &d = w->d;
+    cudaStream_t s = w->stream;
+    const int nb = d.nb;
+    NANS_CUDA(cudaMemsetAsync(d.counters, 0, sizeof(Counters), s));
+    if (nb == 0) return NANS_OK;
+    aabb_key_kernel<<<div_up(max(nb, d.n_statics), 256), 256, 0, s>>>(d, 1.0f / d.cell_size);
+    NANS_LAUNCH_CHECK();
+
+    // radix sort on key[0]/val[0] <-> key[1]/val[1]; 30-bit keys = 4 passes, ends in buffer 0
+    const int n_blocks = div_up(nb, kRadixTile);
+    for (int pass = 0; pass < 4; ++pass) {
+        const int src = pass & 1, dst = src ^ 1;
+        radix_hist_kernel<<<n_blocks, kRadixThreads, 0, s>>>(d.key[src], nb, pass * 8, d.radix_hist, n_blocks);
+        NANS_LAUNCH_CHECK();
+        int rc = exclusive_scan_u32(d.radix_hist, d.radix_hist, 256 * n_blocks, d.scan_block, s);
+        if (rc) return rc;
+        radix_scatter_kernel<<<n_blocks, kRadixThreads, 0, s>>>(d.key[src], d.val[src], d.key[dst], d.val[dst],
+                                                                nb, pass * 8, d.radix_hist, n_blocks);
+        NANS_LAUNCH_CHECK();
+    }
+    // sorted AABBs reuse key[1]/val[1]'s neighbours: dedicated arrays carved as aabb_lo+nb.. (see api.cu)
+    float4 *s_lo = d.aabb_lo + nb, *s_hi = d.aabb_hi + nb;
+    NANS_CUDA(cudaMemsetAsync(d.cell_keys, 0xff, sizeof(uint32_t) * ((size_t)d.cell_mask + 1), s));
+    gather_sorted_kernel<<<div_up(nb, 256), 256, 0, s>>>(d, d.key[0], d.val[0], s_lo, s_hi);
+    NANS_LAUNCH_CHECK();
+    pair_count_kernel<<<div_up(nb, 128), 128, 0, s>>>(d, d.key[0], s_lo, s_hi);
+    NANS_LAUNCH_CHECK();
+    NANS_CUDA(cudaMemsetAsync(d.pair_count + (size_t)5 * nb, 0, sizeof(uint32_t), s));
+    int rc = exclusive_scan_u32(d.pair_count, d.pair_count, 5 * nb + 1, d.scan_block, s);
+    if (rc) return rc;
+    pair_emit_kernel<<<div_up(nb, 128), 128, 0, s>>>(d, d.key[0], s_lo, s_hi);
+    NANS_LAUNCH_CHECK();
+    return NANS_OK;
+}
+
+}  // namespace nans

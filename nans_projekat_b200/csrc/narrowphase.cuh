@@ -1,0 +1,271 @@
+// narrowphase.cuh — GJK intersection + EPA penetration, one pair per thread.
+//
+// Restructured from the reference's CheckCollision / EvolveSimplex / ResolveCollision
+// (code/nans.cpp:907-966, 572-769, 788-904) with bit-identical arithmetic (nans_math.cuh):
+//   * the GJK simplex (std::vector<vertex>, <= 4 entries while GJK runs) lives in registers;
+//     erase()/swap are predicated register moves;
+//   * the EPA polytope is index-based: vertices P/SupA/SupB in a per-thread arena, faces as three
+//     byte indices plus a CACHED unflipped unit normal n and signed plane offset d = dot(n, A.P).
+//     The reference recomputes normalize(cross(AB,AC)) for every face twice per iteration
+//     (closest-face scan :813-821 and visibility test :873-881); both are pure functions of the
+//     face's vertices, so they are computed once at face creation: |d| is the scan distance, the
+//     flipped normal is (d < 0 ? -n : n) = PushTriangle's stored N (:316-320);
+//   * std::vector<edge>/<triangle> erase/push_back order is preserved exactly (the closest-face
+//     tie-break is "first minimum", so face order is observable).
+#pragma once
+#include "nans_math.cuh"
+#include "world.cuh"
+
+namespace nans {
+
+enum { kNoIntersection = 0, kFoundIntersection = 1, kStillEvolving = 2 };  // evolve_result, code/nans.h:89-94
+
+struct GjkVertex { vec3 P, SupA, SupB; };  // struct vertex, code/nans.h:245-255
+
+struct NpShape {
+    float v[24];   // box: 8 world vertices in reference order
+    vec3 pos;      // body centre (GJK start direction; sphere support)
+    float radius;  // sphere
+};
+
+// GetCubeSupport / GetFloorSupport, code/nans.cpp:410-430,441-461: first vertex with strictly
+// greater dot; vec3(0) if every compare fails (NaN direction)
+__device__ __forceinline__ vec3 box_support(const float (&v)[24], vec3 d)
+{
+    float best = -FLT_MAX;
+    vec3 res = V3(0.f, 0.f, 0.f);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const vec3 c = V3(v[3 * k], v[3 * k + 1], v[3 * k + 2]);
+        const float dist = dot(c, d);
+        if (dist > best) { best = dist; res = c; }
+    }
+    return res;
+}
+// GetSphereSupport, code/nans.cpp:433-438
+__device__ __forceinline__ vec3 sphere_support(vec3 pos, float radius, vec3 d)
+{
+    return pos + radius * normalize(d);
+}
+
+template <bool A_SPHERE, bool B_SPHERE>
+__device__ __forceinline__ GjkVertex calc_support(const NpShape &A, const NpShape &B, vec3 d)
+{
+    GjkVertex r;   // CalculateSupport, code/nans.cpp:464-519
+    r.SupA = A_SPHERE ? sphere_support(A.pos, A.radius, d) : box_support(A.v, d);
+    const vec3 nd = -1.0f * d;
+    r.SupB = B_SPHERE ? sphere_support(B.pos, B.radius, nd) : box_support(B.v, nd);
+    r.P = r.SupA - r.SupB;
+    return r;
+}
+
+__device__ __forceinline__ void simplex_erase(GjkVertex (&s)[4], int &n, int i)
+{
+#pragma unroll
+    for (int k = 0; k < 3; ++k)
+        if (k >= i) s[k] = s[k + 1];
+    --n;
+}
+__device__ __forceinline__ void simplex_push(GjkVertex (&s)[4], int &n, const GjkVertex &v)
+{
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+        if (k == n) s[k] = v;
+    ++n;
+}
+
+// TripleCross, code/nans.cpp:565-569
+__device__ __forceinline__ vec3 triple_cross(vec3 A, vec3 B, vec3 C) { return (B * dot(C, A)) - (A * dot(C, B)); }
+
+// EvolveSimplex, code/nans.cpp:572-769
+template <bool A_SPHERE, bool B_SPHERE>
+__device__ __forceinline__ int evolve_simplex(const NpShape &A, const NpShape &B, GjkVertex (&s)[4], int &n)
+{
+    vec3 dir = normalize(B.pos - A.pos);
+    if (n == 1) {
+        dir = dir * -1.0f;
+    } else if (n == 2) {
+        // ClosestPointOnLine, code/nans.cpp:540-562 (normalised segment: U,V are not barycentrics)
+        const vec3 a = s[0].P, b = s[1].P;
+        const vec3 seg = normalize(b - a);
+        const float len = length(seg);
+        const float V = fdiv(dot(-a, seg), len);
+        const float U = fdiv(dot(b, seg), len);
+        vec3 cp;
+        if (U <= 0.0f) cp = b;
+        else if (V <= 0.0f) cp = a;
+        else cp = (U * a) + (V * b);
+        if (V <= 0.0f) simplex_erase(s, n, 1);
+        else if (U <= 0.0f) simplex_erase(s, n, 0);
+        dir = -cp;
+    } else if (n == 3) {
+        const vec3 ao = -s[0].P;
+        const vec3 e1 = s[1].P - s[0].P;
+        const vec3 e2 = s[2].P - s[0].P;
+        const vec3 tn = cross(e1, e2);
+        const vec3 e1n = cross(e1, tn);
+        const vec3 e2n = cross(tn, e2);
+        if (dot(e2n, ao) > 0.0f) {
+            if (dot(e2, ao) > 0.0f) { dir = triple_cross(e2, ao, e2); simplex_erase(s, n, 1); }
+            else if (dot(e1, ao) > 0.0f) { dir = triple_cross(e1, ao, e1); simplex_erase(s, n, 2); }
+            else { dir = ao; simplex_erase(s, n, 2); simplex_erase(s, n, 1); }
+        } else if (dot(e1n, ao) > 0.0f) {
+            if (dot(e1, ao) > 0.0f) { dir = triple_cross(e1, ao, e1); simplex_erase(s, n, 2); }
+            else { dir = ao; simplex_erase(s, n, 2); simplex_erase(s, n, 1); }
+        } else if (dot(tn, ao) > 0.0f) {
+            dir = tn;
+        } else {
+            dir = -tn;
+            const GjkVertex t = s[1]; s[1] = s[2]; s[2] = t;
+        }
+    } else if (n == 4) {
+        const vec3 da = s[0].P - s[3].P;
+        const vec3 db = s[1].P - s[3].P;
+        const vec3 dc = s[2].P - s[3].P;
+        const vec3 d0 = -1.0f * s[3].P;
+        const vec3 abd = cross(da, db), bcd = cross(db, dc), cad = cross(dc, da);
+        if (dot(abd, d0) > 0.0f) { simplex_erase(s, n, 2); dir = abd; }
+        else if (dot(bcd, d0) > 0.0f) { simplex_erase(s, n, 0); dir = bcd; }
+        else if (dot(cad, d0) > 0.0f) { simplex_erase(s, n, 1); dir = cad; }
+        else return kFoundIntersection;
+    }
+    if (length(dir) <= 0.0001f) return kNoIntersection;
+    // AddSupport, code/nans.cpp:522-537
+    const GjkVertex nv = calc_support<A_SPHERE, B_SPHERE>(A, B, dir);
+    simplex_push(s, n, nv);
+    return dot(dir, nv.P) >= 0.0f ? kStillEvolving : kNoIntersection;
+}
+
+// ---- EPA --------------------------------------------------------------------------------------
+struct EpaArena {                        // per-thread (local memory; touched part stays in L1/L2)
+    vec3 P[kEpaMaxVerts], SA[kEpaMaxVerts], SB[kEpaMaxVerts];
+    float4 fnd[kEpaMaxFaces];            // unflipped unit normal, d = dot(n, A.P)
+    uint32_t fidx[kEpaMaxFaces];         // a | b<<8 | c<<16
+    uint16_t edge[kEpaMaxEdges];         // a | b<<8
+};
+
+__device__ __forceinline__ void epa_push_face(EpaArena &E, int &nf, int a, int b, int c)
+{
+    // PushTriangle, code/nans.cpp:293-322 (flip folded into the sign of d)
+    const vec3 n = normalize(cross(E.P[b] - E.P[a], E.P[c] - E.P[a]));
+    const float d = dot(E.P[a], n);
+    E.fnd[nf] = make_float4(n.x, n.y, n.z, d);
+    E.fidx[nf] = (uint32_t)a | ((uint32_t)b << 8) | ((uint32_t)c << 16);
+    ++nf;
+}
+__device__ __forceinline__ vec3 face_normal_flipped(const float4 &nd)
+{
+    const vec3 n = V3(nd);
+    return nd.w < 0.0f ? n * -1.0f : n;
+}
+
+// PushEdge, code/nans.cpp:233-266: cancel an opposite-winding edge BY VALUE of P (code/nans.h:251-254)
+__device__ __forceinline__ void epa_push_edge(EpaArena &E, int &ne, int a, int b, int &ovf)
+{
+    const vec3 pa = E.P[a], pb = E.P[b];
+    for (int i = 0; i < ne; ++i) {
+        const int ea = E.edge[i] & 255, eb = E.edge[i] >> 8;
+        if (equal(E.P[ea], pb) && equal(E.P[eb], pa)) {
+            for (int k = i; k < ne - 1; ++k) E.edge[k] = E.edge[k + 1];
+            --ne;
+            return;
+        }
+    }
+    if (ne >= kEpaMaxEdges) { ovf |= OVF_EPA_EDGES; return; }
+    E.edge[ne++] = (uint16_t)(a | (b << 8));
+}
+
+// ResolveCollision, code/nans.cpp:788-904.  Returns the bool32 result; fills PointA/PointB/N.
+template <bool A_SPHERE, bool B_SPHERE>
+__device__ __noinline__ int epa_resolve(const NpShape &A, const NpShape &B, const GjkVertex (&s)[4],
+                                        EpaArena &E, vec3 &outPA, vec3 &outPB, vec3 &outN, int &ovf,
+                                        int &max_faces)
+{
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { E.P[k] = s[k].P; E.SA[k] = s[k].SupA; E.SB[k] = s[k].SupB; }
+    int nv = 4, nf = 0, ne = 0;
+    epa_push_face(E, nf, 0, 1, 2);  // ABC
+    epa_push_face(E, nf, 0, 2, 3);  // ACD
+    epa_push_face(E, nf, 0, 3, 1);  // ADB
+    epa_push_face(E, nf, 1, 3, 2);  // BDC
+    int it = 0;
+    while (it++ <= 64) {            // MAX_EPA_ITERATIONS, code/nans.h:56
+        max_faces = max(max_faces, nf);
+        // closest face: first strict minimum of |d| (:807-822)
+        float cur = fabsf(E.fnd[0].w);
+        int ci = 0;
+        for (int i = 1; i < nf; ++i) {
+            const float dist = fabsf(E.fnd[i].w);
+            if (dist < cur) { cur = dist; ci = i; }
+        }
+        const float4 cnd = E.fnd[ci];
+        const vec3 N = face_normal_flipped(cnd);
+        const GjkVertex ns = calc_support<A_SPHERE, B_SPHERE>(A, B, N);
+        if (fsub(dot(N, ns.P), cur) < 0.001f) {   // MAX_EPA_ERROR, code/nans.h:55
+            const uint32_t f = E.fidx[ci];
+            const int a = f & 255, b = (f >> 8) & 255, c = (f >> 16) & 255;
+            // Barycentric, code/nans.cpp:772-785
+            const vec3 Pp = N * cur;
+            const vec3 v0 = E.P[b] - E.P[a], v1 = E.P[c] - E.P[a], v2 = Pp - E.P[a];
+            const float d00 = dot(v0, v0), d01 = dot(v0, v1), d11 = dot(v1, v1);
+            const float d20 = dot(v2, v0), d21 = dot(v2, v1);
+            const float denom = fsub(fmul(d00, d11), fmul(d01, d01));
+            const float bv = fdiv(fsub(fmul(d11, d20), fmul(d01, d21)), denom);
+            const float bw = fdiv(fsub(fmul(d00, d21), fmul(d01, d20)), denom);
+            const float bu = fsub(fsub(1.0f, bv), bw);
+            if (fabsf(bu) > 1.0f || fabsf(bv) > 1.0f || fabsf(bw) > 1.0f) return 0;
+            if (!isfinite(bu) || !isfinite(bv) || !isfinite(bw)) return 0;   // IsValid, :4-17
+            outPA = ((bu * E.SA[a]) + (bv * E.SA[b])) + (bw * E.SA[c]);
+            outN = -1.0f * N;
+            outPB = ((bu * E.SB[a]) + (bv * E.SB[b])) + (bw * E.SB[c]);
+            return 1;
+        }
+        if (nv >= kEpaMaxVerts) { ovf |= OVF_EPA_FACES; return 0; }
+        E.P[nv] = ns.P; E.SA[nv] = ns.SupA; E.SB[nv] = ns.SupB;
+        // dissolve every face the new point can see (:869-891); survivors keep their order
+        int keep = 0;
+        for (int i = 0; i < nf; ++i) {
+            const float4 nd = E.fnd[i];
+            const uint32_t f = E.fidx[i];
+            const int a = f & 255, b = (f >> 8) & 255, c = (f >> 16) & 255;
+            const vec3 tmp = ns.P - E.P[a];
+            if (dot(face_normal_flipped(nd), tmp) > 0.0f) {
+                epa_push_edge(E, ne, a, b, ovf);
+                epa_push_edge(E, ne, b, c, ovf);
+                epa_push_edge(E, ne, c, a, ovf);
+            } else {
+                if (keep != i) { E.fnd[keep] = nd; E.fidx[keep] = f; }
+                ++keep;
+            }
+        }
+        nf = keep;
+        // one new face per horizon edge, in edge-list order (:894-901)
+        if (nf + ne > kEpaMaxFaces) { ovf |= OVF_EPA_FACES; return 0; }
+        for (int i = 0; i < ne; ++i) epa_push_face(E, nf, nv, E.edge[i] & 255, E.edge[i] >> 8);
+        ne = 0;
+        ++nv;
+    }
+    return 0;
+}
+
+struct NpResult { int hit, gjk; vec3 PA, PB, N; };
+
+// CheckCollision, code/nans.cpp:907-966
+template <bool A_SPHERE, bool B_SPHERE>
+__device__ __forceinline__ NpResult check_collision(const NpShape &A, const NpShape &B, EpaArena &E,
+                                                    int &ovf, int &max_faces)
+{
+    GjkVertex s[4];
+    int n = 0, ev = kStillEvolving, iter = 0;
+    while (ev == kStillEvolving && iter++ <= 64)   // MAX_GJK_ITERATIONS, code/nans.h:54
+        ev = evolve_simplex<A_SPHERE, B_SPHERE>(A, B, s, n);
+    NpResult r;
+    r.gjk = ev;
+    r.hit = 0;
+    r.PA = r.PB = r.N = V3(0.f, 0.f, 0.f);
+    if (ev == kFoundIntersection)
+        r.hit = epa_resolve<A_SPHERE, B_SPHERE>(A, B, s, E, r.PA, r.PB, r.N, ovf, max_faces);
+    return r;
+}
+
+}  // namespace nans

@@ -1,0 +1,133 @@
+// world.cuh — device-resident world: one arena, SoA body / shape / pair / contact regions.
+//
+// Replaces `sdl_state` (reference code/nans.h:374-386) and every std::vector on the step
+// (Pairs code/nans.h:385, Simplex/Edge/Triangle code/nans.cpp:791-792,1370).  See DESIGN.md §3.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/nans_b200.h"
+
+namespace nans {
+
+constexpr int kNumSMs = 148;            // B200
+constexpr int kEpaMaxVerts = 72;        // 4 + 65 iterations (MAX_EPA_ITERATIONS, code/nans.h:56), padded
+constexpr int kEpaMaxFaces = 200;       // manifold bound is 4 + 2*65 = 134; slack for degenerate horizons
+constexpr int kEpaMaxEdges = 96;
+constexpr int kMaxStatics = 16;
+
+// overflow bits (nans_step_stats.overflow)
+enum { OVF_PAIRS = 1, OVF_CONTACTS = 2, OVF_EPA_FACES = 4, OVF_EPA_EDGES = 8, OVF_CELL = 16 };
+
+// Device counters block (one per world, zeroed per detect).
+struct Counters {
+    int32_t n_pairs;
+    int32_t n_contacts;
+    int32_t n_gjk_found;
+    int32_t solver_levels;
+    int32_t overflow;
+    int32_t max_epa_faces;
+    int32_t frontier_n[3];   // solver frontier sizes (level L reads L%3, fills (L+1)%3, clears (L+2)%3)
+    int32_t pad[7];
+};
+
+// All pointers are DEVICE pointers into the arena.
+struct DeviceWorld {
+    int32_t n_cubes, n_spheres, n_statics, nb;
+    int32_t max_pairs, max_contacts;
+    // --- bodies (SoA, float4): rows cubes then spheres
+    float4 *pos;      // xyz = Position,  w = Mass
+    float4 *vel;      // xyz = V,         w = 1/Mass   (1.0f / Mass, the value Constraint recomputes)
+    float4 *angvel;   // xyz = W,         w = 1/MOI
+    float4 *ang;      // xyz = Angles,    w = MOI
+    float4 *force;    // xyz = Forces
+    float4 *torque;   // xyz = Torque
+    float4 *scale;    // xyz = model scale, w = Radius (spheres, else 0)
+    float4 *verts;    // [n_cubes][6] float4 = 8 packed vec3 (96 B per cube, reference vertex order)
+    int32_t *world_id; // [nb] or nullptr
+    // --- statics
+    float4 *st_pos;    // xyz = Position, w = 1/Mass
+    float4 *st_ang;    // xyz = Angles,   w = 1/MOI
+    float4 *st_scale;
+    float4 *st_verts;  // [n_statics][6]
+    float4 *st_aabb;   // [n_statics][2]
+    // --- broadphase
+    float4 *aabb_lo, *aabb_hi;          // [2*nb]: rows [0,nb) by body, [nb,2nb) in Morton order
+    uint32_t *key[2];                   // Morton cell keys (double buffer for the radix sort)
+    uint32_t *val[2];                   // body rows
+    uint32_t *radix_hist;               // [256 * radix_blocks]
+    uint32_t *cell_keys;                // hash table: key
+    uint32_t *cell_start;               //             first sorted position
+    uint32_t *cell_end;                 //             one past last
+    uint32_t cell_mask;                 // table size - 1
+    uint32_t *pair_count;               // [5 * nb + 1] per (type, body) candidate counts -> offsets
+    int32_t *pair_a, *pair_b;           // [max_pairs] body rows; static k encoded as -(k+1)
+    float cell_size;                    // >= largest body AABB extent (fixed at upload)
+    // --- narrowphase results per candidate
+    int32_t *pair_hit;                  // [max_pairs] 0/1
+    uint32_t *pair_hit_scan;            // [max_pairs + 1]
+    float4 *pair_out;                   // [max_pairs][3]: PointA, PointB, N
+    // --- contacts (reference order)
+    int32_t *c_a, *c_b;                 // body rows / -(k+1)
+    float4 *c_pa, *c_pb, *c_n;          // [max_contacts]
+    // --- solver schedule
+    uint32_t *deg;                      // [nb + 1] incidence counts -> offsets
+    uint32_t *cursor;                   // [nb]
+    int32_t *inc;                       // [2 * max_contacts] contact ids grouped by body
+    int32_t *succ_a, *succ_b;           // [max_contacts] next contact touching body A / B (-1 none)
+    int32_t *indeg;                     // [max_contacts]
+    int32_t *frontier[3];               // [max_contacts] each
+    // --- scan scratch
+    uint32_t *scan_block;               // block sums
+    Counters *counters;
+};
+
+// host-side bookkeeping
+struct World {
+    DeviceWorld d;
+    nans_world_desc desc;
+    void *arena;
+    size_t arena_bytes;
+    bool owns_arena;
+    cudaStream_t stream;
+    bool owns_stream;
+    bool have_contacts;
+    int device;
+    int coop_blocks_per_sm;
+    int32_t *h_counters;   // pinned mirror of Counters
+};
+
+extern thread_local char g_err[512];
+extern unsigned long long g_launches;
+
+#define NANS_CUDA(expr)                                                                      \
+    do {                                                                                     \
+        cudaError_t _e = (expr);                                                             \
+        if (_e != cudaSuccess) {                                                             \
+            snprintf(nans::g_err, sizeof(nans::g_err), "%s:%d %s: %s", __FILE__, __LINE__,   \
+                     #expr, cudaGetErrorString(_e));                                         \
+            return NANS_ERR_CUDA;                                                            \
+        }                                                                                    \
+    } while (0)
+
+#define NANS_LAUNCH_CHECK()                                                                  \
+    do { ++nans::g_launches; NANS_CUDA(cudaGetLastError()); } while (0)
+
+inline int div_up(int a, int b) { return (a + b - 1) / b; }
+inline int div_up_sz(size_t a, size_t b) { return (int)((a + b - 1) / b); }
+
+// stage launchers (each file owns its kernels)
+int launch_integrate_forces(World *w, float dt);
+int launch_integrate_velocities(World *w, float dt);
+int launch_rebuild_statics(World *w);
+int launch_broadphase(World *w);
+int launch_narrowphase(World *w);
+int launch_contacts(World *w);
+int launch_solver(World *w, float dt);
+int exclusive_scan_u32(const uint32_t *in, uint32_t *out, int n, uint32_t *block_scratch, cudaStream_t s);
+int exclusive_scan_u32_dn(const uint32_t *in, uint32_t *out, int cap_n, const int32_t *d_n, int extra,
+                          uint32_t *block_scratch, cudaStream_t s);
+int scan_scratch_elems(int n);
+
+}  // namespace nans
