@@ -1,0 +1,361 @@
+#!/usr/bin/env python
+"""bench.py — body-steps/s of the rigid-body step (BASELINE.json metric) on N B200s.
+
+    python bench.py --gpus 1 --steps 20 --warmup 5            # our arm
+    python bench.py --impl reference --steps 3 --warmup 1      # the reference's CPU path
+    torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A "step" is one pass of IntegrateForces -> DetectCollisions (broadphase + GJK/EPA) ->
+SolveConstraints -> IntegrateVelocities (+ vertex rebuild) over the whole world
+(reference code/nans.cpp:1758-1762).  Workload at N=1: the 1M-cube pile (BASELINE.json metric:
+"body-steps/sec at 1M cubes"), one world resident on one GPU.  At N>1 every rank steps its own
+independent 1M-cube world (north_star: "independent batched worlds ... shard embarrassingly
+across GPUs with no communication"), so scaling is weak and there is no data-path collective.
+Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+DT = np.float32(1 / 60.)
+# ALGORITHMIC bytes per unit (restated in DESIGN.md §5)
+BYTES = {"integrate_forces": 104, "integrate_velocities": 168, "aabb_key": 128, "radix_sort": 64,
+         "pair_emit": 8, "narrowphase": 264, "solver": 184}
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--bodies", type=int, default=1_000_000, help="cubes per world (per rank)")
+    ap.add_argument("--side", type=int, default=250, help="pile footprint: side x side cubes per layer")
+    ap.add_argument("--settle", type=int, default=40, help="untimed scene-preparation steps before warm-up")
+    ap.add_argument("--cpu-bodies", type=int, default=2048, help="size of the CPU-baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.rows, self.proc, self.idx = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.idx)], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        sm, mx, reasons = [], 0, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx = max(mx, float(r[2]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return json.load(open(p)).get("hbm_gbs", 6650.0), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
+
+
+def build_pile(bodies, side, seed):
+    from nans_projekat_b200 import scenes
+    layers = max(1, (bodies + side * side - 1) // (side * side))
+    return scenes.cube_pile(n_side=side, layers=layers, n=bodies, seed=seed), layers
+
+
+# --------------------------------------------------------------------------------------- CPU legs
+def cpu_port_baseline(state_scene, n_sample, budget_s=15.0):
+    """The oracle port (same all-pairs algorithm as the reference, 1 thread, -O2) on a bounded
+    sample of the SAME workload: the first n_sample cubes of the settled pile + the floor."""
+    from oracle import oracle as O
+    n = min(n_sample, state_scene.n_cubes)
+    w = O.World(n, 0, state_scene.n_statics)
+    for f in ("pos", "vel", "force", "ang", "angvel", "torque", "scale"):
+        getattr(w, f)[...] = getattr(state_scene, f)[:n]
+    w.mass[...] = state_scene.mass[:n]; w.moi[...] = state_scene.moi[:n]
+    w.verts[...] = state_scene.verts[:n]
+    for f in ("st_pos", "st_ang", "st_scale", "st_mass", "st_moi", "st_verts"):
+        getattr(w, f)[...] = getattr(state_scene, f)
+    steps, t0 = 0, time.perf_counter()
+    while True:
+        w.step(DT, prefilter=False)
+        steps += 1
+        el = time.perf_counter() - t0
+        if el > budget_s or steps >= 200:
+            break
+    return {"value": n * steps / el, "unit": "body-steps/s", "cores": 1, "kind": "port",
+            "sample": f"first {n} cubes of the settled pile + floor, {steps} all-pairs steps "
+                      f"(reference algorithm, O(N^2) GJK, oracle/nans_oracle.c -O2, 1 thread), {el:.1f} s"}
+
+
+def run_reference(args):
+    """Reference arm: the reference's OWN prebuilt plugin (oracle/_ref/nans.so, unmodified, -O0 as
+    shipped) stepping its physics stage functions, single thread (the reference has no threads), at
+    its hard cap of 16 cubes (MAX_CUBE_COUNT, code/nans.h:52): a 16-cube column sample of the pile.
+    Falls back to the oracle port when the binary was not staged."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import ctypes as C
+    from oracle import oracle as O
+    from nans_projekat_b200 import scenes
+    H = O.ref()
+    cfg = {"workload": "cube_pile", "bodies_per_world": args.bodies, "l2": "n/a (CPU)"}
+    # 16-cube sample: a 2x2 footprint, 4 layers of the same lattice, settled on the floor
+    s = scenes.cube_pile(n_side=2, layers=4, seed=7)
+    window = 25     # world steps per window; every window restarts from the same prepared state
+    if H is not None:
+        sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+        from make_golden import scene_to_ref_state
+        st = scene_to_ref_state(s)
+        kind, cores = "reference", 1
+        what = "oracle/_ref/nans.so (the reference's shipped -O0 build), stage functions code/nans.cpp:1758-1762"
+
+        def step():
+            """one world step; returns the seconds spent INSIDE the reference binary"""
+            t = time.perf_counter()
+            H.nansref_physics_step(O._sp(st), C.c_float(float(DT)), None, 0)
+            t = time.perf_counter() - t
+            r = st[0]   # the draw section's Model rebuild (untimed here; not part of :1758-1762)
+            for i in range(int(r["CubeCount"])):
+                c = r["Cubes"][i]
+                c["Model"] = O.model_vertices(c["Position"], c["Angles"], (c["Size"],) * 3)[0].reshape(16)
+            return t
+        save = lambda: st.copy()
+        def restore(x): st[...] = x
+    else:
+        w = O.World(s.n_cubes, 0, 1)
+        for f in s.ARRAYS:
+            getattr(w, f)[...] = getattr(s, f)
+        w.rebuild_vertices()
+        kind, cores, what = "port", 1, "oracle/nans_oracle.c (-O2 restatement; reference binary not staged)"
+
+        def step():
+            t = time.perf_counter()
+            w.step(DT, prefilter=False)
+            return time.perf_counter() - t
+        save = lambda: w.copy()
+        def restore(x):
+            for f in ("pos", "vel", "force", "ang", "angvel", "torque", "verts"):
+                getattr(w, f)[...] = getattr(x, f)
+    n = s.n_cubes
+    for _ in range(40):          # same scene preparation as our arm: let the column come into contact
+        step()
+    prepared = save()
+    inner = 40      # windows per bench step: one bench "step" = inner*window world steps (bounded sample)
+    for _ in range(max(args.warmup, 1)):
+        restore(prepared)
+        for _ in range(window):
+            step()
+    el = 0.0
+    for _ in range(args.steps):
+        for _ in range(inner):
+            restore(prepared)
+            for _ in range(window):
+                el += step()
+    inner = inner * window
+    value = n * inner * args.steps / el
+    line = {"impl": "reference", "metric": "body-steps/s", "value": value, "unit": "body-steps/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * el / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": dict(cfg, sample=f"{n}-cube column of the pile lattice + floor (the reference's "
+                                       f"MAX_CUBE_COUNT cap), {inner} world steps per bench step"),
+            "cpu_baseline": {"value": value, "unit": "body-steps/s", "cores": cores, "kind": kind,
+                             "sample": f"{what}; {n} cubes + floor, {inner * args.steps} steps, {el:.1f} s"},
+            "e2e": {"value": value, "unit": "body-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "host": {"nproc": os.cpu_count()}}
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------- our arm
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+    import torch
+    import torch.distributed as dist
+    from nans_projekat_b200.world import World, kernel_launches
+    from nans_projekat_b200.scenes import Scene
+
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    world_size = int(os.environ.get("WORLD_SIZE", "1"))
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    torch.cuda.set_device(local)
+    if world_size > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        if world_size > 1:
+            dist.barrier()
+
+    warmup = max(args.warmup, 3)
+    scene, layers = build_pile(args.bodies, args.side, seed=7 + rank)
+    nb = scene.n_cubes
+    stream = torch.cuda.Stream()
+    world = World(scene, device=local, stream=stream.cuda_stream)
+    world.rebuild_vertices()
+    FULL = ("pos", "vel", "force", "ang", "angvel", "torque", "verts")
+    for _ in range(args.settle):        # scene preparation: let the pile come into contact
+        world.step(DT)
+    world.synchronize()
+    # Every measured phase (device-timed, per-stage, e2e) starts from this same prepared state, so
+    # all three see the same contact-rich window of the simulation (the reference's bug-compatible
+    # solver eventually blows a large pile apart; the window ends before that).
+    prepared = world.download(fields=FULL)
+
+    def restore_and_warm():
+        world.upload(prepared, fields=FULL)
+        for _ in range(warmup):
+            world.step(DT)
+        world.synchronize()
+
+    restore_and_warm()
+
+    # ---- timed region: device-resident, CUDA events on the launching stream ----------------
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = kernel_launches()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier(); torch.cuda.synchronize()
+    e0.record(stream)
+    for _ in range(args.steps):
+        world.step(DT)
+    e1.record(stream)
+    torch.cuda.synchronize(); barrier()
+    ms = e0.elapsed_time(e1)
+    launches = kernel_launches() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    st1 = world.stats()          # raises on capacity overflow: a truncated step is not a valid step
+    t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+    if world_size > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    value = nb * world_size * args.steps / (ms_max * 1e-3)
+
+    # ---- per-stage pass over the same window: CUDA events between the stages ----------------
+    restore_and_warm()
+    stage = {}
+    pairs_acc = contacts_acc = 0
+    for _ in range(args.steps):
+        m = world.step_profiled(DT)
+        for k, v in m.items():
+            stage[k] = stage.get(k, 0.0) + v / args.steps
+        s_ = world.stats()
+        pairs_acc += s_["n_pairs"] / args.steps
+        contacts_acc += s_["n_contacts"] / args.steps
+    peak, peak_src = load_peaks()
+    alg = {"integrate_forces": nb * BYTES["integrate_forces"],
+           "broadphase": nb * (BYTES["aabb_key"] + BYTES["radix_sort"]) + pairs_acc * BYTES["pair_emit"],
+           "narrowphase": pairs_acc * BYTES["narrowphase"],
+           "solver": contacts_acc * BYTES["solver"],
+           "integrate_velocities": nb * BYTES["integrate_velocities"]}
+    dom = max(alg, key=lambda k: stage[k])
+    ach = alg[dom] / (stage[dom] * 1e-3) / 1e9
+    roofline = {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                "traffic": None, "peak_source": peak_src,
+                "share_of_step": stage[dom] / stage["step"],
+                "per_stage": {k: {"ms": stage[k], "alg_bytes": alg[k], "gbs": alg[k] / (stage[k] * 1e-3) / 1e9,
+                                  "frac": alg[k] / (stage[k] * 1e-3) / 1e9 / peak} for k in alg},
+                "note": "narrowphase (GJK+EPA) is FP32-pipe/divergence bound, its HBM fraction is reported for "
+                        "completeness; pairs/s = %.3g" % (pairs_acc / (stage["narrowphase"] * 1e-3))}
+
+    # ---- e2e: through the public API with HOST buffers, H2D + D2H inside the timed region ----
+    e2e = None
+    if not args.no_e2e:
+        def pinned(shape):
+            return torch.zeros(shape, dtype=torch.float32).pin_memory().numpy()
+        io = Scene.__new__(Scene)
+        io.n_cubes, io.n_spheres, io.n_statics, io.world_id = scene.n_cubes, 0, scene.n_statics, None
+        io.force, io.torque, io.pos, io.ang = pinned((nb, 3)), pinned((nb, 3)), pinned((nb, 3)), pinned((nb, 3))
+        world.upload(prepared, fields=FULL)
+        for _ in range(warmup):
+            world.upload(io, fields=("force", "torque")); world.step(DT); world.download_into(io, ("pos", "ang"))
+        barrier(); torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            world.upload(io, fields=("force", "torque"))      # this frame's external forces/torques
+            world.step(DT)
+            world.download_into(io, ("pos", "ang"))           # poses for the renderer / game layer
+        torch.cuda.synchronize()
+        el = torch.tensor([time.perf_counter() - t0], device="cuda", dtype=torch.float64)
+        if world_size > 1:
+            dist.all_reduce(el, op=dist.ReduceOp.MAX)
+        e2e = {"value": nb * world_size * args.steps / float(el.item()), "unit": "body-steps/s",
+               "h2d_bytes_per_step": int(2 * nb * 12), "d2h_bytes_per_step": int(2 * nb * 12),
+               "api": "World.upload(force,torque) -> World.step -> World.download(pos,ang) "
+                      "(nans_world_upload / nans_step / nans_world_download)"}
+        assert np.isfinite(io.pos).all(), "non-finite positions after the e2e loop"
+
+    cpu = None
+    if rank == 0 and world_size == 1 and not args.no_cpu_baseline:
+        state = prepared.copy()
+        for f in ("scale", "mass", "moi", "st_pos", "st_ang", "st_scale", "st_mass", "st_moi"):
+            getattr(state, f)[...] = getattr(scene, f)
+        sv = Scene(0, 0, scene.n_statics)
+        world.download_into(sv, ("st_verts",))
+        state.st_verts[...] = sv.st_verts
+        cpu = cpu_port_baseline(state, args.cpu_bodies)
+
+    if rank == 0:
+        line = {"metric": "body-steps/s", "value": value, "unit": "body-steps/s", "n_gpus": world_size,
+                "steps": args.steps, "warmup": warmup, "ms_per_step": ms_max / args.steps,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+                "data": "synthetic",
+                "config": {"workload": "cube_pile_1M" if nb == 1_000_000 else f"cube_pile_{nb}",
+                           "bodies_per_world": nb, "worlds": world_size, "footprint": f"{args.side}x{args.side}",
+                           "layers": layers, "spacing": 1.02, "dt": float(DT), "settle_steps": args.settle,
+                           "parallelism": "1 world per GPU, no collective" if world_size > 1 else "1 world on 1 GPU",
+                           "l2": "inputs larger than L2 (>= 1 GB of world state touched per step vs 126 MB L2)",
+                           "solver": "exact reference order (DAG levels)",
+                           "pairs_per_step": pairs_acc, "contacts_per_step": contacts_acc,
+                           "solver_levels": st1["solver_levels"]},
+                "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
+                "clocks": clocks,
+                "stages_ms": stage, "narrowphase_pairs_per_s": pairs_acc / (stage["narrowphase"] * 1e-3),
+                "host": {"nproc": os.cpu_count()}}
+        print(json.dumps(line), flush=True)
+    world.close()
+    if world_size > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

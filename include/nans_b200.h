@@ -116,6 +116,10 @@ int nans_rebuild_vertices(nans_world *w);
 /* the step as SimUpdateAndRender runs it (code/nans.cpp:1758-1762) */
 int nans_step(nans_world *w, float dt);
 int nans_synchronize(nans_world *w);
+/* nans_step with a CUDA event between the stages, recorded on the world's stream (measurement only):
+ * stage_ms[8] = integrate_forces, broadphase, narrowphase, contact compaction, solver,
+ * integrate_velocities+rebuild, whole step, 0.  Synchronises. */
+int nans_step_profiled(nans_world *w, float dt, float *stage_ms);
 
 /* results of the last detect/step */
 int nans_get_stats(nans_world *w, nans_step_stats *out);                 /* synchronises */

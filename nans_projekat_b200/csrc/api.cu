@@ -453,6 +453,40 @@ int nans_step(nans_world *h, float dt)
     return nans_integrate_velocities(h, dt);
 }
 
+// One step with a CUDA event between every stage (on the world's stream); stage_ms[8]:
+// 0 integrate_forces, 1 broadphase, 2 narrowphase, 3 contact compaction, 4 solver (schedule + levels),
+// 5 integrate_velocities + vertex rebuild, 6 whole step, 7 unused.  Synchronises.
+int nans_step_profiled(nans_world *h, float dt, float *stage_ms)
+{
+    if (!h || !stage_ms) return fail(NANS_ERR_ARG, "null argument");
+    WorldImpl *w = impl(h);
+    NANS_CUDA(cudaSetDevice(w->device));
+    static cudaEvent_t ev[7];
+    static bool have = false;
+    if (!have) { for (auto &e : ev) NANS_CUDA(cudaEventCreate(&e)); have = true; }
+    cudaStream_t s = w->stream;
+    int rc;
+    NANS_CUDA(cudaEventRecord(ev[0], s));
+    if ((rc = launch_integrate_forces(w, dt))) return rc;
+    NANS_CUDA(cudaEventRecord(ev[1], s));
+    if ((rc = launch_broadphase(w))) return rc;
+    NANS_CUDA(cudaEventRecord(ev[2], s));
+    if ((rc = launch_narrowphase(w))) return rc;
+    NANS_CUDA(cudaEventRecord(ev[3], s));
+    if ((rc = launch_contacts(w))) return rc;
+    w->have_contacts = true;
+    NANS_CUDA(cudaEventRecord(ev[4], s));
+    if ((rc = launch_solver(w, dt))) return rc;
+    NANS_CUDA(cudaEventRecord(ev[5], s));
+    if ((rc = launch_integrate_velocities(w, dt))) return rc;
+    NANS_CUDA(cudaEventRecord(ev[6], s));
+    NANS_CUDA(cudaEventSynchronize(ev[6]));
+    for (int k = 0; k < 6; ++k) NANS_CUDA(cudaEventElapsedTime(&stage_ms[k], ev[k], ev[k + 1]));
+    NANS_CUDA(cudaEventElapsedTime(&stage_ms[6], ev[0], ev[6]));
+    stage_ms[7] = 0.f;
+    return NANS_OK;
+}
+
 int nans_get_stats(nans_world *h, nans_step_stats *out)
 {
     if (!h || !out) return fail(NANS_ERR_ARG, "null argument");

@@ -125,6 +125,14 @@ class World:
     def step(self, dt):
         _lib.check(_lib.lib().nans_step(self._h, dt))
 
+    STAGES = ("integrate_forces", "broadphase", "narrowphase", "contacts", "solver", "integrate_velocities", "step")
+
+    def step_profiled(self, dt) -> dict:
+        """One step with CUDA events between the stages (measurement only). ms per stage."""
+        ms = np.zeros(8, np.float32)
+        _lib.check(_lib.lib().nans_step_profiled(self._h, dt, _fp(ms)))
+        return dict(zip(self.STAGES, ms[:7].tolist()))
+
     def synchronize(self):
         _lib.check(_lib.lib().nans_synchronize(self._h))
 
