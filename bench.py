@@ -35,12 +35,13 @@ BYTES = {"integrate_forces": 104, "integrate_velocities": 168, "aabb_key": 128, 
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--bodies", type=int, default=1_000_000, help="cubes per world (per rank)")
     ap.add_argument("--side", type=int, default=250, help="pile footprint: side x side cubes per layer")
     ap.add_argument("--settle", type=int, default=40, help="untimed scene-preparation steps before warm-up")
+    ap.add_argument("--window", type=int, default=20, help="steps between snapshot restores")
     ap.add_argument("--cpu-bodies", type=int, default=2048, help="size of the CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -66,13 +67,16 @@ class ClockSampler:
 
     def _pump(self):
         for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+            self.rows.append((time.time(), [x.strip() for x in line.split(",")]))
 
-    def stop(self):
+    def stop(self, t_begin=None, t_end=None):
         if self.proc:
             self.proc.terminate()
         sm, mx, reasons = [], 0, set()
-        for r in self.rows:
+        rows = [r for (ts, r) in self.rows if t_begin is None or (t_begin - 0.05 <= ts <= t_end + 0.15)]
+        if not rows:
+            rows = [r for (_, r) in self.rows]
+        for r in rows:
             try:
                 sm.append(float(r[1])); mx = max(mx, float(r[2]))
                 for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
@@ -235,34 +239,41 @@ def main():
     for _ in range(args.settle):        # scene preparation: let the pile come into contact
         world.step(DT)
     world.synchronize()
-    # Every measured phase (device-timed, per-stage, e2e) starts from this same prepared state, so
-    # all three see the same contact-rich window of the simulation (the reference's bug-compatible
-    # solver eventually blows a large pile apart; the window ends before that).
+    # The measured window is steps [settle, settle + window) of the simulation, the contact-rich phase
+    # of the pile.  The reference's bug-compatible solver (minus sign in the angular JMJ term, one
+    # Gauss-Seidel pass) eventually blows a large pile apart, so every `window` steps
+    # the world returns to the prepared state by a device-to-device snapshot restore (an episode
+    # reset, RL-style).  The restore is INSIDE the timed region; it is ~0.2 GB of D2D copy per window.
+    world.snapshot()
     prepared = world.download(fields=FULL)
+    window = args.window
 
-    def restore_and_warm():
-        world.upload(prepared, fields=FULL)
-        for _ in range(warmup):
-            world.step(DT)
-        world.synchronize()
+    def run_steps(n, step_fn):
+        for k in range(n):
+            if k % window == 0:
+                world.restore()
+            step_fn()
 
-    restore_and_warm()
+    run_steps(warmup, lambda: world.step(DT))
+    world.synchronize()
 
     # ---- timed region: device-resident, CUDA events on the launching stream ----------------
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+        time.sleep(0.5)          # let nvidia-smi start sampling before the timed region
     launches0 = kernel_launches()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier(); torch.cuda.synchronize()
+    t_begin = time.time()
     e0.record(stream)
-    for _ in range(args.steps):
-        world.step(DT)
+    run_steps(args.steps, lambda: world.step(DT))
     e1.record(stream)
     torch.cuda.synchronize(); barrier()
+    t_end = time.time()
     ms = e0.elapsed_time(e1)
     launches = kernel_launches() - launches0
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop(t_begin, t_end) if rank == 0 else None
     st1 = world.stats()          # raises on capacity overflow: a truncated step is not a valid step
     t = torch.tensor([ms], device="cuda", dtype=torch.float64)
     if world_size > 1:
@@ -271,16 +282,20 @@ def main():
     value = nb * world_size * args.steps / (ms_max * 1e-3)
 
     # ---- per-stage pass over the same window: CUDA events between the stages ----------------
-    restore_and_warm()
     stage = {}
-    pairs_acc = contacts_acc = 0
-    for _ in range(args.steps):
+    acc = {"pairs": 0.0, "contacts": 0.0, "levels": 0.0}
+    n_prof = min(args.steps, 2 * window)
+
+    def prof_step():
         m = world.step_profiled(DT)
         for k, v in m.items():
-            stage[k] = stage.get(k, 0.0) + v / args.steps
+            stage[k] = stage.get(k, 0.0) + v / n_prof
         s_ = world.stats()
-        pairs_acc += s_["n_pairs"] / args.steps
-        contacts_acc += s_["n_contacts"] / args.steps
+        acc["pairs"] += s_["n_pairs"] / n_prof
+        acc["contacts"] += s_["n_contacts"] / n_prof
+        acc["levels"] += s_["solver_levels"] / n_prof
+    run_steps(n_prof, prof_step)
+    pairs_acc, contacts_acc = acc["pairs"], acc["contacts"]
     peak, peak_src = load_peaks()
     alg = {"integrate_forces": nb * BYTES["integrate_forces"],
            "broadphase": nb * (BYTES["aabb_key"] + BYTES["radix_sort"]) + pairs_acc * BYTES["pair_emit"],
@@ -294,7 +309,9 @@ def main():
                 "share_of_step": stage[dom] / stage["step"],
                 "per_stage": {k: {"ms": stage[k], "alg_bytes": alg[k], "gbs": alg[k] / (stage[k] * 1e-3) / 1e9,
                                   "frac": alg[k] / (stage[k] * 1e-3) / 1e9 / peak} for k in alg},
-                "note": "narrowphase (GJK+EPA) is FP32-pipe/divergence bound, its HBM fraction is reported for "
+                "note": "stage = all kernels of that stage (CUDA events between stages on the launching stream); "
+                        "narrowphase (GJK+EPA) is FP32-latency/divergence bound and the solver is bound by the "
+                        "dependency depth of the exact-order sweep, their HBM fractions are reported for "
                         "completeness; pairs/s = %.3g" % (pairs_acc / (stage["narrowphase"] * 1e-3))}
 
     # ---- e2e: through the public API with HOST buffers, H2D + D2H inside the timed region ----
@@ -305,15 +322,15 @@ def main():
         io = Scene.__new__(Scene)
         io.n_cubes, io.n_spheres, io.n_statics, io.world_id = scene.n_cubes, 0, scene.n_statics, None
         io.force, io.torque, io.pos, io.ang = pinned((nb, 3)), pinned((nb, 3)), pinned((nb, 3)), pinned((nb, 3))
-        world.upload(prepared, fields=FULL)
-        for _ in range(warmup):
-            world.upload(io, fields=("force", "torque")); world.step(DT); world.download_into(io, ("pos", "ang"))
-        barrier(); torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        for _ in range(args.steps):
+
+        def e2e_step():
             world.upload(io, fields=("force", "torque"))      # this frame's external forces/torques
             world.step(DT)
             world.download_into(io, ("pos", "ang"))           # poses for the renderer / game layer
+        run_steps(warmup, e2e_step)
+        barrier(); torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        run_steps(args.steps, e2e_step)
         torch.cuda.synchronize()
         el = torch.tensor([time.perf_counter() - t0], device="cuda", dtype=torch.float64)
         if world_size > 1:
@@ -321,7 +338,7 @@ def main():
         e2e = {"value": nb * world_size * args.steps / float(el.item()), "unit": "body-steps/s",
                "h2d_bytes_per_step": int(2 * nb * 12), "d2h_bytes_per_step": int(2 * nb * 12),
                "api": "World.upload(force,torque) -> World.step -> World.download(pos,ang) "
-                      "(nans_world_upload / nans_step / nans_world_download)"}
+                      "(nans_world_upload / nans_step / nans_world_download), pinned host buffers, wall clock"}
         assert np.isfinite(io.pos).all(), "non-finite positions after the e2e loop"
 
     cpu = None
@@ -344,9 +361,11 @@ def main():
                            "layers": layers, "spacing": 1.02, "dt": float(DT), "settle_steps": args.settle,
                            "parallelism": "1 world per GPU, no collective" if world_size > 1 else "1 world on 1 GPU",
                            "l2": "inputs larger than L2 (>= 1 GB of world state touched per step vs 126 MB L2)",
-                           "solver": "exact reference order (DAG levels)",
+                           "window": f"steps [{args.settle}, {args.settle + window}) of the simulation, restored from a "
+                                     f"device snapshot every {window} steps inside the timed region",
+                           "solver": "exact reference order (dependency dataflow)",
                            "pairs_per_step": pairs_acc, "contacts_per_step": contacts_acc,
-                           "solver_levels": st1["solver_levels"]},
+                           "solver_dag_depth": acc["levels"]},
                 "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
                 "clocks": clocks,
                 "stages_ms": stage, "narrowphase_pairs_per_s": pairs_acc / (stage["narrowphase"] * 1e-3),

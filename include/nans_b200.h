@@ -104,6 +104,12 @@ int nans_world_add_force(nans_world *w, int32_t body_row, const float force[3], 
 int nans_world_set_body(nans_world *w, int32_t body_row, const float pos[3], const float vel[3],
                         const float angvel[3]);
 
+/* device-to-device snapshot / restore of the dynamic state (pose, velocities, forces, vertices);
+ * asynchronous on the world's stream.  The reference checkpoints implicitly: its whole world is one
+ * host block that survives plugin reloads (code/sdl_nans.cpp:541-555). */
+int nans_world_snapshot(nans_world *w);
+int nans_world_restore(nans_world *w);
+
 /* ---- the four stages, one entry per reference function (asynchronous on the world's stream) */
 int nans_integrate_forces(nans_world *w, float dt);     /* IntegrateForces     code/nans.cpp:975  */
 int nans_detect_collisions(nans_world *w);              /* DetectCollisions    code/nans.cpp:1352 */

@@ -54,6 +54,7 @@ struct Staging {            // per-field upload/download slots (device), carved 
 struct Layout {
     DeviceWorld d;
     Staging st;
+    float4 *snap;
     size_t bytes;
 };
 
@@ -78,13 +79,15 @@ static Layout carve(const nans_world_desc &desc, char *base)
     d.world_id = b.take<int32_t>(nb);
     d.st_pos = b.take<float4>(ns); d.st_ang = b.take<float4>(ns); d.st_scale = b.take<float4>(ns);
     d.st_verts = b.take<float4>(6 * ns); d.st_aabb = b.take<float4>(2 * ns);
-    d.aabb_lo = b.take<float4>(2 * nb); d.aabb_hi = b.take<float4>(2 * nb);
+    d.aabb_lo = b.take<float4>(nb); d.aabb_hi = b.take<float4>(nb);
+    d.sbox = b.take<float4>(2 * nb);
+    d.pair_tmp = b.take<uint32_t>(24 * nb);
     for (int k = 0; k < 2; ++k) { d.key[k] = b.take<uint32_t>(nb); d.val[k] = b.take<uint32_t>(nb); }
     const size_t radix_blocks = (nb + 4095) / 4096;
     d.radix_hist = b.take<uint32_t>(256 * radix_blocks);
     const uint32_t table = pow2_at_least((uint32_t)(2 * nb));
     d.cell_mask = table - 1;
-    d.cell_keys = b.take<uint32_t>(table); d.cell_start = b.take<uint32_t>(table); d.cell_end = b.take<uint32_t>(table);
+    d.cell_tab = b.take<uint4>(table);
     d.pair_count = b.take<uint32_t>(5 * nb + 1);
     d.pair_a = b.take<int32_t>(mp); d.pair_b = b.take<int32_t>(mp);
     d.pair_hit = b.take<int32_t>(mp + 1); d.pair_hit_scan = b.take<uint32_t>(mp + 1);
@@ -104,6 +107,7 @@ static Layout carve(const nans_world_desc &desc, char *base)
     for (int k = 0; k < 3; ++k) L.st.scal[k] = b.take<float>(nb);
     L.st.verts = b.take<float>(24 * nc);
     L.st.wid = b.take<int32_t>(nb);
+    L.snap = b.take<float4>(6 * nb + 6 * nc);   // device-side snapshot of the dynamic state
     d.cell_size = 2.0f;
     L.bytes = (b.used + 255) & ~(size_t)255;
     return L;
@@ -111,6 +115,7 @@ static Layout carve(const nans_world_desc &desc, char *base)
 
 struct WorldImpl : World {
     Staging st;
+    float4 *snap;
     bool has_world_id;
     int32_t *d_world_id_storage;
 };
@@ -220,6 +225,7 @@ int nans_world_create(const nans_world_desc *desc, nans_world **out)
     Layout L = carve(*desc, (char *)w->arena);
     w->d = L.d;
     w->st = L.st;
+    w->snap = L.snap;
     w->d_world_id_storage = L.d.world_id;
     w->d.world_id = nullptr;
     w->has_world_id = false;
@@ -393,6 +399,30 @@ int nans_world_set_body(nans_world *h, int32_t row, const float p[3], const floa
     return NANS_OK;
 }
 
+// Device-to-device snapshot / restore of the dynamic state (pose, velocities, forces, vertices):
+// the hot-reload host keeps its whole world in one block so it can be checkpointed by copying it
+// (code/sdl_nans.cpp:541-555); this is the device-side equivalent (episode reset, bench windows).
+static int snapshot_copy(WorldImpl *w, bool restore)
+{
+    DeviceWorld &d = w->d;
+    NANS_CUDA(cudaSetDevice(w->device));
+    float4 *rows[6] = {d.pos, d.vel, d.angvel, d.ang, d.force, d.torque};
+    const size_t nb = (size_t)d.nb, nc = (size_t)d.n_cubes;
+    for (int k = 0; k < 6 && nb; ++k) {
+        float4 *snap = w->snap + k * nb;
+        NANS_CUDA(cudaMemcpyAsync(restore ? rows[k] : snap, restore ? snap : rows[k], sizeof(float4) * nb,
+                                  cudaMemcpyDeviceToDevice, w->stream));
+    }
+    if (nc) {
+        float4 *snap = w->snap + 6 * nb;
+        NANS_CUDA(cudaMemcpyAsync(restore ? d.verts : snap, restore ? snap : d.verts, sizeof(float4) * 6 * nc,
+                                  cudaMemcpyDeviceToDevice, w->stream));
+    }
+    return NANS_OK;
+}
+int nans_world_snapshot(nans_world *h) { return h ? snapshot_copy(impl(h), false) : fail(NANS_ERR_ARG, "null world"); }
+int nans_world_restore(nans_world *h) { return h ? snapshot_copy(impl(h), true) : fail(NANS_ERR_ARG, "null world"); }
+
 // ---- stages ------------------------------------------------------------------------------------
 int nans_integrate_forces(nans_world *h, float dt)
 {
@@ -498,6 +528,7 @@ int nans_get_stats(nans_world *h, nans_step_stats *out)
     memset(out, 0, sizeof(*out));
     out->n_pairs = c->n_pairs; out->n_contacts = c->n_contacts; out->n_gjk_found = c->n_gjk_found;
     out->solver_levels = c->solver_levels; out->overflow = c->overflow; out->max_epa_faces = c->max_epa_faces;
+    if (c->frontier_n[2]) return fail(NANS_ERR_STATE, "solver: dependency schedule stalled (spin cap hit)");
     if (c->overflow) {
         snprintf(g_err, sizeof(g_err), "capacity exceeded (overflow bits 0x%x: 1 pairs, 2 contacts, 4 EPA faces, 8 EPA edges)",
                  c->overflow);
@@ -563,6 +594,8 @@ int nans_set_contacts(nans_world *h, const nans_contact *in, int32_t count)
         else b[i] = (c.type == NANS_CS || c.type == NANS_SS) ? d.n_cubes + c.b : c.b;
         pa[i] = make_float4(c.point_a[0], c.point_a[1], c.point_a[2], 0.f);
         pb[i] = make_float4(c.point_b[0], c.point_b[1], c.point_b[2], 0.f);
+        memcpy(&pa[i].w, &a[i], 4);   // body rows ride in the w lanes (solver.cu)
+        memcpy(&pb[i].w, &b[i], 4);
         nn[i] = make_float4(c.n[0], c.n[1], c.n[2], 0.f);
     }
     cudaStream_t s = w->stream;

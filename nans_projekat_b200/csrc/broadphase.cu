@@ -189,10 +189,11 @@ __global__ void __launch_bounds__(kRadixThreads) radix_scatter_kernel(
 }
 
 // ---------------------------------------------------------------------------------------------
-// After the sort: AABBs in Morton order, w lanes carry body row / world id; hash table of cells.
+// After the sort: AABBs in Morton order as one 32-byte record per body (one L2 sector per
+// candidate test): {lo.xyz, row} {hi.xyz, world id}; and the hash table of cells, one 16-byte
+// entry {key, start, end, -} per slot (one sector per probe).
 __global__ void __launch_bounds__(256) gather_sorted_kernel(DeviceWorld w, const uint32_t *__restrict__ keys,
-                                                            const uint32_t *__restrict__ vals,
-                                                            float4 *__restrict__ s_lo, float4 *__restrict__ s_hi)
+                                                            const uint32_t *__restrict__ vals)
 {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= w.nb) return;
@@ -200,8 +201,8 @@ __global__ void __launch_bounds__(256) gather_sorted_kernel(DeviceWorld w, const
     float4 lo = w.aabb_lo[row], hi = w.aabb_hi[row];
     lo.w = __int_as_float((int)row);
     hi.w = __int_as_float(w.world_id ? w.world_id[row] : 0);
-    s_lo[t] = lo;
-    s_hi[t] = hi;
+    w.sbox[2 * (size_t)t] = lo;
+    w.sbox[2 * (size_t)t + 1] = hi;
     // cell table: heads write start, tails write end (both find-or-insert, so no ordering race)
     const uint32_t key = keys[t];
     const bool head = (t == 0) || (keys[t - 1] != key);
@@ -210,12 +211,12 @@ __global__ void __launch_bounds__(256) gather_sorted_kernel(DeviceWorld w, const
         uint32_t h = key * 0x9E3779B1u;
         uint32_t slot = (h ^ (h >> 15)) & w.cell_mask;
         while (true) {
-            const uint32_t prev = atomicCAS(&w.cell_keys[slot], kEmptyKey, key);
+            const uint32_t prev = atomicCAS(&w.cell_tab[slot].x, kEmptyKey, key);
             if (prev == kEmptyKey || prev == key) break;
             slot = (slot + 1) & w.cell_mask;
         }
-        if (head) w.cell_start[slot] = (uint32_t)t;
-        if (tail) w.cell_end[slot] = (uint32_t)t + 1u;
+        if (head) w.cell_tab[slot].y = (uint32_t)t;
+        if (tail) w.cell_tab[slot].z = (uint32_t)t + 1u;
     }
 }
 
@@ -224,9 +225,9 @@ __device__ __forceinline__ bool cell_lookup(const DeviceWorld &w, uint32_t key, 
     uint32_t h = key * 0x9E3779B1u;
     uint32_t slot = (h ^ (h >> 15)) & w.cell_mask;
     while (true) {
-        const uint32_t k = __ldg(&w.cell_keys[slot]);
-        if (k == key) { start = __ldg(&w.cell_start[slot]); end = __ldg(&w.cell_end[slot]); return true; }
-        if (k == kEmptyKey) return false;
+        const uint4 e = __ldg(&w.cell_tab[slot]);
+        if (e.x == key) { start = e.y; end = e.z; return true; }
+        if (e.x == kEmptyKey) return false;
         slot = (slot + 1) & w.cell_mask;
     }
 }
@@ -242,11 +243,9 @@ enum { SEG_CC = 0, SEG_CF = 1, SEG_SF = 2, SEG_CS = 3, SEG_SS = 4 };
 // Visit every dynamic partner of sorted entry t that the reference would list under body `row`.
 // F(seg, partner_row)
 template <typename F>
-__device__ __forceinline__ void for_each_partner(const DeviceWorld &w, const uint32_t *__restrict__ keys,
-                                                 const float4 *__restrict__ s_lo, const float4 *__restrict__ s_hi,
-                                                 int t, F f)
+__device__ __forceinline__ void for_each_partner(const DeviceWorld &w, const uint32_t *__restrict__ keys, int t, F f)
 {
-    const float4 alo = s_lo[t], ahi = s_hi[t];
+    const float4 alo = w.sbox[2 * (size_t)t], ahi = w.sbox[2 * (size_t)t + 1];
     const int row = __float_as_int(alo.w);
     const int wid = __float_as_int(ahi.w);
     const bool a_cube = row < w.n_cubes;
@@ -260,7 +259,7 @@ __device__ __forceinline__ void for_each_partner(const DeviceWorld &w, const uin
                 uint32_t s, e;
                 if (!cell_lookup(w, morton30((uint32_t)nx, (uint32_t)ny, (uint32_t)nz), s, e)) continue;
                 for (uint32_t u = s; u < e; ++u) {
-                    const float4 blo = s_lo[u], bhi = s_hi[u];
+                    const float4 blo = __ldg(&w.sbox[2 * (size_t)u]), bhi = __ldg(&w.sbox[2 * (size_t)u + 1]);
                     const int brow = __float_as_int(blo.w);
                     if (__float_as_int(bhi.w) != wid) continue;
                     const bool b_cube = brow < w.n_cubes;
@@ -278,17 +277,26 @@ __device__ __forceinline__ void for_each_partner(const DeviceWorld &w, const uin
             }
 }
 
-__global__ void __launch_bounds__(128) pair_count_kernel(DeviceWorld w, const uint32_t *__restrict__ keys,
-                                                         const float4 *__restrict__ s_lo,
-                                                         const float4 *__restrict__ s_hi)
+// One neighbourhood scan per body: counts per (type, body) AND the partners themselves, parked in
+// a fixed-stride slot buffer (kPairSlots per body, tagged seg<<28 | row).  The emit pass only moves
+// them to their scanned offsets; a body with more partners than slots (crowded cell) is rescanned.
+constexpr int kPairSlots = 24;
+
+__global__ void __launch_bounds__(128) pair_count_kernel(DeviceWorld w, const uint32_t *__restrict__ keys)
 {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= w.nb) return;
-    const float4 alo = s_lo[t], ahi = s_hi[t];
+    const float4 alo = w.sbox[2 * (size_t)t], ahi = w.sbox[2 * (size_t)t + 1];
     const int row = __float_as_int(alo.w);
     uint32_t cnt[5] = {0, 0, 0, 0, 0};
-    for_each_partner(w, keys, s_lo, s_hi, t, [&](int seg, int) { cnt[seg]++; });
-    // statics: CF for cubes, SF for spheres, static index ascending
+    uint32_t filled = 0;
+    uint32_t *slots = w.pair_tmp + (size_t)t * kPairSlots;
+    for_each_partner(w, keys, t, [&](int seg, int brow) {
+        cnt[seg]++;
+        if (filled < (uint32_t)kPairSlots) slots[filled] = ((uint32_t)seg << 28) | (uint32_t)brow;
+        ++filled;
+    });
+    // statics: CF for cubes, SF for spheres, static index ascending (recomputed in the emit pass)
     uint32_t ns = 0;
     for (int k = 0; k < w.n_statics; ++k)
         if (overlap(alo, ahi, w.st_aabb[2 * k], w.st_aabb[2 * k + 1])) ++ns;
@@ -297,28 +305,36 @@ __global__ void __launch_bounds__(128) pair_count_kernel(DeviceWorld w, const ui
     for (int s = 0; s < 5; ++s) w.pair_count[(size_t)s * w.nb + row] = cnt[s];
 }
 
-__global__ void __launch_bounds__(128) pair_emit_kernel(DeviceWorld w, const uint32_t *__restrict__ keys,
-                                                        const float4 *__restrict__ s_lo,
-                                                        const float4 *__restrict__ s_hi)
+__global__ void __launch_bounds__(128) pair_emit_kernel(DeviceWorld w, const uint32_t *__restrict__ keys)
 {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= w.nb) return;
-    const float4 alo = s_lo[t], ahi = s_hi[t];
+    const float4 alo = w.sbox[2 * (size_t)t], ahi = w.sbox[2 * (size_t)t + 1];
     const int row = __float_as_int(alo.w);
     uint32_t off[5], fill[5] = {0, 0, 0, 0, 0};
+    // scanned table: offsets; the entry after (s,row) is the next run's start, i.e. this run's end
 #pragma unroll
-    for (int s = 0; s < 5; ++s) off[s] = w.pair_count[(size_t)s * w.nb + row];   // scanned: offsets
+    for (int s = 0; s < 5; ++s) off[s] = w.pair_count[(size_t)s * w.nb + row];
+    const uint32_t n_dyn = (w.pair_count[(size_t)SEG_CC * w.nb + row + 1] - off[SEG_CC]) +
+                           (w.pair_count[(size_t)SEG_CS * w.nb + row + 1] - off[SEG_CS]) +
+                           (w.pair_count[(size_t)SEG_SS * w.nb + row + 1] - off[SEG_SS]);
     const uint32_t cap = (uint32_t)w.max_pairs;
-    for_each_partner(w, keys, s_lo, s_hi, t, [&](int seg, int brow) {
+    auto put = [&](int seg, int brow) {
         const uint32_t p = off[seg] + fill[seg]++;
         if (p < cap) { w.pair_a[p] = row; w.pair_b[p] = brow; }
-    });
+    };
+    if (n_dyn <= (uint32_t)kPairSlots) {
+        const uint32_t *slots = w.pair_tmp + (size_t)t * kPairSlots;
+        for (uint32_t k = 0; k < n_dyn; ++k) {
+            const uint32_t e = slots[k];
+            put((int)(e >> 28), (int)(e & 0x0fffffffu));
+        }
+    } else {
+        for_each_partner(w, keys, t, put);
+    }
     const int sseg = row < w.n_cubes ? SEG_CF : SEG_SF;
     for (int k = 0; k < w.n_statics; ++k)
-        if (overlap(alo, ahi, w.st_aabb[2 * k], w.st_aabb[2 * k + 1])) {
-            const uint32_t p = off[sseg] + fill[sseg]++;
-            if (p < cap) { w.pair_a[p] = row; w.pair_b[p] = -(k + 1); }
-        }
+        if (overlap(alo, ahi, w.st_aabb[2 * k], w.st_aabb[2 * k + 1])) put(sseg, -(k + 1));
     // each (body, type) run in ascending partner order = the reference's inner loop order
     // (insertion sort in place; runs are a handful of entries)
 #pragma unroll
@@ -363,17 +379,15 @@ int launch_broadphase(World *w)
                                                                 nb, pass * 8, d.radix_hist, n_blocks);
         NANS_LAUNCH_CHECK();
     }
-    // sorted AABBs reuse key[1]/val[1]'s neighbours: dedicated arrays carved as aabb_lo+nb.. (see api.cu)
-    float4 *s_lo = d.aabb_lo + nb, *s_hi = d.aabb_hi + nb;
-    NANS_CUDA(cudaMemsetAsync(d.cell_keys, 0xff, sizeof(uint32_t) * ((size_t)d.cell_mask + 1), s));
-    gather_sorted_kernel<<<div_up(nb, 256), 256, 0, s>>>(d, d.key[0], d.val[0], s_lo, s_hi);
+    NANS_CUDA(cudaMemsetAsync(d.cell_tab, 0xff, sizeof(uint4) * ((size_t)d.cell_mask + 1), s));
+    gather_sorted_kernel<<<div_up(nb, 256), 256, 0, s>>>(d, d.key[0], d.val[0]);
     NANS_LAUNCH_CHECK();
-    pair_count_kernel<<<div_up(nb, 128), 128, 0, s>>>(d, d.key[0], s_lo, s_hi);
+    pair_count_kernel<<<div_up(nb, 128), 128, 0, s>>>(d, d.key[0]);
     NANS_LAUNCH_CHECK();
     NANS_CUDA(cudaMemsetAsync(d.pair_count + (size_t)5 * nb, 0, sizeof(uint32_t), s));
     int rc = exclusive_scan_u32(d.pair_count, d.pair_count, 5 * nb + 1, d.scan_block, s);
     if (rc) return rc;
-    pair_emit_kernel<<<div_up(nb, 128), 128, 0, s>>>(d, d.key[0], s_lo, s_hi);
+    pair_emit_kernel<<<div_up(nb, 128), 128, 0, s>>>(d, d.key[0]);
     NANS_LAUNCH_CHECK();
     return NANS_OK;
 }

@@ -45,8 +45,11 @@ __global__ void __launch_bounds__(256) contact_compact_kernel(DeviceWorld w)
         w.c_a[c] = w.pair_a[p];
         w.c_b[c] = w.pair_b[p];
         const float4 *o = w.pair_out + 3 * (size_t)p;
-        w.c_pa[c] = o[0];
-        w.c_pb[c] = o[1];
+        float4 qa = o[0], qb = o[1];
+        qa.w = __int_as_float(w.pair_a[p]);   // the solver reads the body rows from the w lanes
+        qb.w = __int_as_float(w.pair_b[p]);
+        w.c_pa[c] = qa;
+        w.c_pb[c] = qb;
         w.c_n[c] = o[2];
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) {

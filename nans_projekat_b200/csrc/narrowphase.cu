@@ -7,32 +7,35 @@
 
 namespace nans {
 
-__device__ __forceinline__ void load_box(NpShape &S, const float4 *__restrict__ v6)
+__device__ __forceinline__ void load_box(float *sv, int side, const float4 *__restrict__ v6)
 {
+    float *p = sv + 24 * side * kNpThreads;
 #pragma unroll
     for (int q = 0; q < 6; ++q) {
         const float4 t = __ldg(v6 + q);
-        S.v[4 * q] = t.x; S.v[4 * q + 1] = t.y; S.v[4 * q + 2] = t.z; S.v[4 * q + 3] = t.w;
+        p[(4 * q) * kNpThreads] = t.x; p[(4 * q + 1) * kNpThreads] = t.y;
+        p[(4 * q + 2) * kNpThreads] = t.z; p[(4 * q + 3) * kNpThreads] = t.w;
     }
 }
 
-__device__ __forceinline__ NpResult dispatch(bool a_sphere, bool b_sphere, const NpShape &A, const NpShape &B,
-                                             EpaArena &E, int &ovf, int &max_faces)
+__device__ __forceinline__ NpResult dispatch(bool a_sphere, bool b_sphere, const NpShapes &S, EpaArena &E,
+                                             int &ovf, int &max_faces)
 {
-    if (!a_sphere && !b_sphere) return check_collision<false, false>(A, B, E, ovf, max_faces);
-    if (!a_sphere && b_sphere) return check_collision<false, true>(A, B, E, ovf, max_faces);
-    if (a_sphere && !b_sphere) return check_collision<true, false>(A, B, E, ovf, max_faces);
-    return check_collision<true, true>(A, B, E, ovf, max_faces);
+    if (!a_sphere && !b_sphere) return check_collision<false, false>(S, E, ovf, max_faces);
+    if (!a_sphere && b_sphere) return check_collision<false, true>(S, E, ovf, max_faces);
+    if (a_sphere && !b_sphere) return check_collision<true, false>(S, E, ovf, max_faces);
+    return check_collision<true, true>(S, E, ovf, max_faces);
 }
 
-constexpr int kNpThreads = 128;
-
-__global__ void __launch_bounds__(kNpThreads) narrowphase_world_kernel(DeviceWorld w, int *work_counter)
+__global__ void __launch_bounds__(kNpThreads, 5) narrowphase_world_kernel(DeviceWorld w, int *work_counter)
 {
+    __shared__ float smem[48 * kNpThreads];   // both shapes' vertices, transposed: [float][thread]
     EpaArena E;
     const int lane = threadIdx.x & 31;
     const int n_pairs = w.counters->n_pairs;
     int ovf = 0, max_faces = 0, found = 0;
+    NpShapes S;
+    S.sv = smem + threadIdx.x;
     while (true) {
         int base = 0;
         if (lane == 0) base = atomicAdd(work_counter, 32);
@@ -41,23 +44,21 @@ __global__ void __launch_bounds__(kNpThreads) narrowphase_world_kernel(DeviceWor
         const int p = base + lane;
         if (p < n_pairs) {
             const int ra = w.pair_a[p], rb = w.pair_b[p];
-            NpShape A, B;
             const bool a_sphere = ra >= w.n_cubes;
             const bool b_sphere = rb >= w.n_cubes;   // statics are negative -> box
-            const float4 pa = w.pos[ra];
-            A.pos = V3(pa);
-            A.radius = 0.f;
-            if (a_sphere) A.radius = w.scale[ra].w; else load_box(A, w.verts + 6 * (size_t)ra);
-            B.radius = 0.f;
+            S.posA = V3(w.pos[ra]);
+            S.radA = 0.f;
+            if (a_sphere) S.radA = w.scale[ra].w; else load_box(smem + threadIdx.x, 0, w.verts + 6 * (size_t)ra);
+            S.radB = 0.f;
             if (rb < 0) {
                 const int k = -rb - 1;
-                B.pos = V3(w.st_pos[k]);
-                load_box(B, w.st_verts + 6 * k);
+                S.posB = V3(w.st_pos[k]);
+                load_box(smem + threadIdx.x, 1, w.st_verts + 6 * k);
             } else {
-                B.pos = V3(w.pos[rb]);
-                if (b_sphere) B.radius = w.scale[rb].w; else load_box(B, w.verts + 6 * (size_t)rb);
+                S.posB = V3(w.pos[rb]);
+                if (b_sphere) S.radB = w.scale[rb].w; else load_box(smem + threadIdx.x, 1, w.verts + 6 * (size_t)rb);
             }
-            const NpResult r = dispatch(a_sphere, b_sphere, A, B, E, ovf, max_faces);
+            const NpResult r = dispatch(a_sphere, b_sphere, S, E, ovf, max_faces);
             found += (r.gjk == kFoundIntersection);
             w.pair_hit[p] = r.hit;
             if (r.hit) {
@@ -80,15 +81,18 @@ __global__ void __launch_bounds__(kNpThreads) narrowphase_world_kernel(DeviceWor
 }
 
 // stand-alone pairs (config C3): type per pair, shapes given explicitly
-__global__ void __launch_bounds__(kNpThreads) narrowphase_batch_kernel(
+__global__ void __launch_bounds__(kNpThreads, 5) narrowphase_batch_kernel(
     int n, const int32_t *__restrict__ type, const float4 *__restrict__ posrad_a,
     const float4 *__restrict__ verts_a, const float4 *__restrict__ posrad_b,
     const float4 *__restrict__ verts_b, int32_t *__restrict__ hit, int32_t *__restrict__ gjk,
     float4 *__restrict__ out, int *work_counter, Counters *counters)
 {
+    __shared__ float smem[48 * kNpThreads];
     EpaArena E;
     const int lane = threadIdx.x & 31;
     int ovf = 0, max_faces = 0;
+    NpShapes S;
+    S.sv = smem + threadIdx.x;
     while (true) {
         int base = 0;
         if (lane == 0) base = atomicAdd(work_counter, 32);
@@ -99,13 +103,12 @@ __global__ void __launch_bounds__(kNpThreads) narrowphase_batch_kernel(
             const int t = type[p];
             const bool a_sphere = (t == NANS_SS || t == NANS_SF);
             const bool b_sphere = (t == NANS_CS || t == NANS_SS);
-            NpShape A, B;
             const float4 pa = posrad_a[p], pb = posrad_b[p];
-            A.pos = V3(pa); A.radius = pa.w;
-            B.pos = V3(pb); B.radius = pb.w;
-            if (!a_sphere) load_box(A, verts_a + 6 * (size_t)p);
-            if (!b_sphere) load_box(B, verts_b + 6 * (size_t)p);
-            const NpResult r = dispatch(a_sphere, b_sphere, A, B, E, ovf, max_faces);
+            S.posA = V3(pa); S.radA = pa.w;
+            S.posB = V3(pb); S.radB = pb.w;
+            if (!a_sphere) load_box(smem + threadIdx.x, 0, verts_a + 6 * (size_t)p);
+            if (!b_sphere) load_box(smem + threadIdx.x, 1, verts_b + 6 * (size_t)p);
+            const NpResult r = dispatch(a_sphere, b_sphere, S, E, ovf, max_faces);
             hit[p] = r.hit;
             if (gjk) gjk[p] = r.gjk;
             float4 *o = out + 3 * (size_t)p;

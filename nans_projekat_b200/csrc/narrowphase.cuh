@@ -2,14 +2,18 @@
 //
 // Restructured from the reference's CheckCollision / EvolveSimplex / ResolveCollision
 // (code/nans.cpp:907-966, 572-769, 788-904) with bit-identical arithmetic (nans_math.cuh):
+//   * both shapes' support vertices are staged in SHARED memory, transposed ([48][threads], bank
+//     conflict free), so the support scans index them dynamically at no register cost and a box
+//     support is remembered as a 1-byte vertex index instead of a copied vec3;
 //   * the GJK simplex (std::vector<vertex>, <= 4 entries while GJK runs) lives in registers;
 //     erase()/swap are predicated register moves;
-//   * the EPA polytope is index-based: vertices P/SupA/SupB in a per-thread arena, faces as three
-//     byte indices plus a CACHED unflipped unit normal n and signed plane offset d = dot(n, A.P).
-//     The reference recomputes normalize(cross(AB,AC)) for every face twice per iteration
-//     (closest-face scan :813-821 and visibility test :873-881); both are pure functions of the
-//     face's vertices, so they are computed once at face creation: |d| is the scan distance, the
-//     flipped normal is (d < 0 ? -n : n) = PushTriangle's stored N (:316-320);
+//   * the EPA polytope is index-based and lives in a per-thread arena: vertices P plus support
+//     indices (or the sphere support point), faces as three byte indices plus a CACHED unflipped
+//     unit normal n and signed plane offset d = dot(n, A.P).  The reference recomputes
+//     normalize(cross(AB,AC)) for every face twice per iteration (closest-face scan :813-821 and
+//     visibility test :873-881); both are pure functions of the face's vertices, so they are
+//     computed once at face creation: |d| is the scan distance, the flipped normal is
+//     (d < 0 ? -n : n) = PushTriangle's stored N (:316-320);
 //   * std::vector<edge>/<triangle> erase/push_back order is preserved exactly (the closest-face
 //     tie-break is "first minimum", so face order is observable).
 #pragma once
@@ -20,25 +24,35 @@ namespace nans {
 
 enum { kNoIntersection = 0, kFoundIntersection = 1, kStillEvolving = 2 };  // evolve_result, code/nans.h:89-94
 
-struct GjkVertex { vec3 P, SupA, SupB; };  // struct vertex, code/nans.h:245-255
+constexpr int kNpThreads = 128;
+constexpr int kNoVertex = 8;   // box support when every compare failed (NaN direction): vec3(0)
 
-struct NpShape {
-    float v[24];   // box: 8 world vertices in reference order
-    vec3 pos;      // body centre (GJK start direction; sphere support)
-    float radius;  // sphere
+// Per-thread view of the two shapes.  Box vertices: smem[(24*side + 3*k + r) * kNpThreads + tid].
+struct NpShapes {
+    const float *sv;     // &smem[tid]
+    vec3 posA, posB;     // body centres (GJK start direction; sphere support)
+    float radA, radB;    // spheres
+    __device__ __forceinline__ vec3 vertex(int side, int k) const
+    {
+        if (k >= 8) return V3(0.f, 0.f, 0.f);
+        const float *p = sv + (24 * side + 3 * k) * kNpThreads;
+        return V3(p[0], p[kNpThreads], p[2 * kNpThreads]);
+    }
 };
 
 // GetCubeSupport / GetFloorSupport, code/nans.cpp:410-430,441-461: first vertex with strictly
 // greater dot; vec3(0) if every compare fails (NaN direction)
-__device__ __forceinline__ vec3 box_support(const float (&v)[24], vec3 d)
+__device__ __forceinline__ vec3 box_support(const NpShapes &S, int side, vec3 d, int &idx)
 {
     float best = -FLT_MAX;
     vec3 res = V3(0.f, 0.f, 0.f);
+    idx = kNoVertex;
+    const float *p = S.sv + 24 * side * kNpThreads;
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-        const vec3 c = V3(v[3 * k], v[3 * k + 1], v[3 * k + 2]);
+        const vec3 c = V3(p[(3 * k) * kNpThreads], p[(3 * k + 1) * kNpThreads], p[(3 * k + 2) * kNpThreads]);
         const float dist = dot(c, d);
-        if (dist > best) { best = dist; res = c; }
+        if (dist > best) { best = dist; res = c; idx = k; }
     }
     return res;
 }
@@ -48,25 +62,53 @@ __device__ __forceinline__ vec3 sphere_support(vec3 pos, float radius, vec3 d)
     return pos + radius * normalize(d);
 }
 
+// A support record: vertex index for a box, the point itself for a sphere.
+template <bool SPHERE> struct SupRec;
+template <> struct SupRec<false> { int idx; };
+template <> struct SupRec<true> { vec3 v; };
+
 template <bool A_SPHERE, bool B_SPHERE>
-__device__ __forceinline__ GjkVertex calc_support(const NpShape &A, const NpShape &B, vec3 d)
+struct GjkVertex {           // struct vertex, code/nans.h:245-255
+    vec3 P;
+    SupRec<A_SPHERE> a;
+    SupRec<B_SPHERE> b;
+};
+
+template <bool SPHERE>
+__device__ __forceinline__ vec3 support_of(const NpShapes &S, int side, vec3 d, SupRec<SPHERE> &rec)
 {
-    GjkVertex r;   // CalculateSupport, code/nans.cpp:464-519
-    r.SupA = A_SPHERE ? sphere_support(A.pos, A.radius, d) : box_support(A.v, d);
-    const vec3 nd = -1.0f * d;
-    r.SupB = B_SPHERE ? sphere_support(B.pos, B.radius, nd) : box_support(B.v, nd);
-    r.P = r.SupA - r.SupB;
+    if constexpr (SPHERE) {
+        rec.v = sphere_support(side ? S.posB : S.posA, side ? S.radB : S.radA, d);
+        return rec.v;
+    } else {
+        return box_support(S, side, d, rec.idx);
+    }
+}
+template <bool SPHERE>
+__device__ __forceinline__ vec3 support_point(const NpShapes &S, int side, const SupRec<SPHERE> &rec)
+{
+    if constexpr (SPHERE) return rec.v; else return S.vertex(side, rec.idx);
+}
+
+// CalculateSupport, code/nans.cpp:464-519
+template <bool AS, bool BS>
+__device__ __forceinline__ GjkVertex<AS, BS> calc_support(const NpShapes &S, vec3 d)
+{
+    GjkVertex<AS, BS> r;
+    const vec3 sa = support_of<AS>(S, 0, d, r.a);
+    const vec3 sb = support_of<BS>(S, 1, -1.0f * d, r.b);
+    r.P = sa - sb;
     return r;
 }
 
-__device__ __forceinline__ void simplex_erase(GjkVertex (&s)[4], int &n, int i)
+template <typename V> __device__ __forceinline__ void simplex_erase(V (&s)[4], int &n, int i)
 {
 #pragma unroll
     for (int k = 0; k < 3; ++k)
         if (k >= i) s[k] = s[k + 1];
     --n;
 }
-__device__ __forceinline__ void simplex_push(GjkVertex (&s)[4], int &n, const GjkVertex &v)
+template <typename V> __device__ __forceinline__ void simplex_push(V (&s)[4], int &n, const V &v)
 {
 #pragma unroll
     for (int k = 0; k < 4; ++k)
@@ -78,10 +120,10 @@ __device__ __forceinline__ void simplex_push(GjkVertex (&s)[4], int &n, const Gj
 __device__ __forceinline__ vec3 triple_cross(vec3 A, vec3 B, vec3 C) { return (B * dot(C, A)) - (A * dot(C, B)); }
 
 // EvolveSimplex, code/nans.cpp:572-769
-template <bool A_SPHERE, bool B_SPHERE>
-__device__ __forceinline__ int evolve_simplex(const NpShape &A, const NpShape &B, GjkVertex (&s)[4], int &n)
+template <bool AS, bool BS>
+__device__ __forceinline__ int evolve_simplex(const NpShapes &S, GjkVertex<AS, BS> (&s)[4], int &n)
 {
-    vec3 dir = normalize(B.pos - A.pos);
+    vec3 dir = normalize(S.posB - S.posA);
     if (n == 1) {
         dir = dir * -1.0f;
     } else if (n == 2) {
@@ -116,7 +158,7 @@ __device__ __forceinline__ int evolve_simplex(const NpShape &A, const NpShape &B
             dir = tn;
         } else {
             dir = -tn;
-            const GjkVertex t = s[1]; s[1] = s[2]; s[2] = t;
+            const GjkVertex<AS, BS> t = s[1]; s[1] = s[2]; s[2] = t;
         }
     } else if (n == 4) {
         const vec3 da = s[0].P - s[3].P;
@@ -131,24 +173,43 @@ __device__ __forceinline__ int evolve_simplex(const NpShape &A, const NpShape &B
     }
     if (length(dir) <= 0.0001f) return kNoIntersection;
     // AddSupport, code/nans.cpp:522-537
-    const GjkVertex nv = calc_support<A_SPHERE, B_SPHERE>(A, B, dir);
+    const GjkVertex<AS, BS> nv = calc_support<AS, BS>(S, dir);
     simplex_push(s, n, nv);
     return dot(dir, nv.P) >= 0.0f ? kStillEvolving : kNoIntersection;
 }
 
 // ---- EPA --------------------------------------------------------------------------------------
-struct EpaArena {                        // per-thread (local memory; touched part stays in L1/L2)
-    vec3 P[kEpaMaxVerts], SA[kEpaMaxVerts], SB[kEpaMaxVerts];
+struct EpaArena {                        // per-thread (local memory; only the touched part costs traffic)
+    vec3 P[kEpaMaxVerts];
+    vec3 SA[kEpaMaxVerts], SB[kEpaMaxVerts];   // sphere sides only
+    uint8_t ia[kEpaMaxVerts], ib[kEpaMaxVerts]; // box sides only
     float4 fnd[kEpaMaxFaces];            // unflipped unit normal, d = dot(n, A.P)
     uint32_t fidx[kEpaMaxFaces];         // a | b<<8 | c<<16
     uint16_t edge[kEpaMaxEdges];         // a | b<<8
 };
 
+template <bool AS, bool BS>
+__device__ __forceinline__ void epa_store_vertex(EpaArena &E, int i, const GjkVertex<AS, BS> &v)
+{
+    E.P[i] = v.P;
+    if constexpr (AS) E.SA[i] = v.a.v; else E.ia[i] = (uint8_t)v.a.idx;
+    if constexpr (BS) E.SB[i] = v.b.v; else E.ib[i] = (uint8_t)v.b.idx;
+}
+template <bool AS> __device__ __forceinline__ vec3 epa_sup_a(const EpaArena &E, const NpShapes &S, int i)
+{
+    if constexpr (AS) return E.SA[i]; else return S.vertex(0, E.ia[i]);
+}
+template <bool BS> __device__ __forceinline__ vec3 epa_sup_b(const EpaArena &E, const NpShapes &S, int i)
+{
+    if constexpr (BS) return E.SB[i]; else return S.vertex(1, E.ib[i]);
+}
+
 __device__ __forceinline__ void epa_push_face(EpaArena &E, int &nf, int a, int b, int c)
 {
     // PushTriangle, code/nans.cpp:293-322 (flip folded into the sign of d)
-    const vec3 n = normalize(cross(E.P[b] - E.P[a], E.P[c] - E.P[a]));
-    const float d = dot(E.P[a], n);
+    const vec3 pa = E.P[a];
+    const vec3 n = normalize(cross(E.P[b] - pa, E.P[c] - pa));
+    const float d = dot(pa, n);
     E.fnd[nf] = make_float4(n.x, n.y, n.z, d);
     E.fidx[nf] = (uint32_t)a | ((uint32_t)b << 8) | ((uint32_t)c << 16);
     ++nf;
@@ -176,13 +237,12 @@ __device__ __forceinline__ void epa_push_edge(EpaArena &E, int &ne, int a, int b
 }
 
 // ResolveCollision, code/nans.cpp:788-904.  Returns the bool32 result; fills PointA/PointB/N.
-template <bool A_SPHERE, bool B_SPHERE>
-__device__ __noinline__ int epa_resolve(const NpShape &A, const NpShape &B, const GjkVertex (&s)[4],
-                                        EpaArena &E, vec3 &outPA, vec3 &outPB, vec3 &outN, int &ovf,
-                                        int &max_faces)
+template <bool AS, bool BS>
+__device__ __forceinline__ int epa_resolve(const NpShapes &S, const GjkVertex<AS, BS> (&s)[4], EpaArena &E,
+                                           vec3 &outPA, vec3 &outPB, vec3 &outN, int &ovf, int &max_faces)
 {
 #pragma unroll
-    for (int k = 0; k < 4; ++k) { E.P[k] = s[k].P; E.SA[k] = s[k].SupA; E.SB[k] = s[k].SupB; }
+    for (int k = 0; k < 4; ++k) epa_store_vertex<AS, BS>(E, k, s[k]);
     int nv = 4, nf = 0, ne = 0;
     epa_push_face(E, nf, 0, 1, 2);  // ABC
     epa_push_face(E, nf, 0, 2, 3);  // ACD
@@ -200,13 +260,14 @@ __device__ __noinline__ int epa_resolve(const NpShape &A, const NpShape &B, cons
         }
         const float4 cnd = E.fnd[ci];
         const vec3 N = face_normal_flipped(cnd);
-        const GjkVertex ns = calc_support<A_SPHERE, B_SPHERE>(A, B, N);
+        const GjkVertex<AS, BS> ns = calc_support<AS, BS>(S, N);
         if (fsub(dot(N, ns.P), cur) < 0.001f) {   // MAX_EPA_ERROR, code/nans.h:55
             const uint32_t f = E.fidx[ci];
             const int a = f & 255, b = (f >> 8) & 255, c = (f >> 16) & 255;
             // Barycentric, code/nans.cpp:772-785
             const vec3 Pp = N * cur;
-            const vec3 v0 = E.P[b] - E.P[a], v1 = E.P[c] - E.P[a], v2 = Pp - E.P[a];
+            const vec3 A0 = E.P[a];
+            const vec3 v0 = E.P[b] - A0, v1 = E.P[c] - A0, v2 = Pp - A0;
             const float d00 = dot(v0, v0), d01 = dot(v0, v1), d11 = dot(v1, v1);
             const float d20 = dot(v2, v0), d21 = dot(v2, v1);
             const float denom = fsub(fmul(d00, d11), fmul(d01, d01));
@@ -215,13 +276,13 @@ __device__ __noinline__ int epa_resolve(const NpShape &A, const NpShape &B, cons
             const float bu = fsub(fsub(1.0f, bv), bw);
             if (fabsf(bu) > 1.0f || fabsf(bv) > 1.0f || fabsf(bw) > 1.0f) return 0;
             if (!isfinite(bu) || !isfinite(bv) || !isfinite(bw)) return 0;   // IsValid, :4-17
-            outPA = ((bu * E.SA[a]) + (bv * E.SA[b])) + (bw * E.SA[c]);
+            outPA = ((bu * epa_sup_a<AS>(E, S, a)) + (bv * epa_sup_a<AS>(E, S, b))) + (bw * epa_sup_a<AS>(E, S, c));
             outN = -1.0f * N;
-            outPB = ((bu * E.SB[a]) + (bv * E.SB[b])) + (bw * E.SB[c]);
+            outPB = ((bu * epa_sup_b<BS>(E, S, a)) + (bv * epa_sup_b<BS>(E, S, b))) + (bw * epa_sup_b<BS>(E, S, c));
             return 1;
         }
         if (nv >= kEpaMaxVerts) { ovf |= OVF_EPA_FACES; return 0; }
-        E.P[nv] = ns.P; E.SA[nv] = ns.SupA; E.SB[nv] = ns.SupB;
+        epa_store_vertex<AS, BS>(E, nv, ns);
         // dissolve every face the new point can see (:869-891); survivors keep their order
         int keep = 0;
         for (int i = 0; i < nf; ++i) {
@@ -251,20 +312,18 @@ __device__ __noinline__ int epa_resolve(const NpShape &A, const NpShape &B, cons
 struct NpResult { int hit, gjk; vec3 PA, PB, N; };
 
 // CheckCollision, code/nans.cpp:907-966
-template <bool A_SPHERE, bool B_SPHERE>
-__device__ __forceinline__ NpResult check_collision(const NpShape &A, const NpShape &B, EpaArena &E,
-                                                    int &ovf, int &max_faces)
+template <bool AS, bool BS>
+__device__ __noinline__ NpResult check_collision(const NpShapes &S, EpaArena &E, int &ovf, int &max_faces)
 {
-    GjkVertex s[4];
+    GjkVertex<AS, BS> s[4];
     int n = 0, ev = kStillEvolving, iter = 0;
     while (ev == kStillEvolving && iter++ <= 64)   // MAX_GJK_ITERATIONS, code/nans.h:54
-        ev = evolve_simplex<A_SPHERE, B_SPHERE>(A, B, s, n);
+        ev = evolve_simplex<AS, BS>(S, s, n);
     NpResult r;
     r.gjk = ev;
     r.hit = 0;
     r.PA = r.PB = r.N = V3(0.f, 0.f, 0.f);
-    if (ev == kFoundIntersection)
-        r.hit = epa_resolve<A_SPHERE, B_SPHERE>(A, B, s, E, r.PA, r.PB, r.N, ovf, max_faces);
+    if (ev == kFoundIntersection) r.hit = epa_resolve<AS, BS>(S, s, E, r.PA, r.PB, r.N, ovf, max_faces);
     return r;
 }
 

@@ -1,21 +1,33 @@
-// solver.cu — sequential-impulse contact solver, exact reference order, parallel by dependency level.
+// solver.cu — sequential-impulse contact solver in the reference's exact order, run as a dataflow.
 //
 // The reference (SolveConstraints code/nans.cpp:1539-1548 -> Constraint :1021-1329) makes ONE
 // Gauss-Seidel pass over the contact list in list order; each Constraint reads the velocities the
 // previous ones left.  Two contacts commute iff they share no dynamic body, so the sweep is a DAG:
 // contact c depends on the previous contact touching its body A and the previous one touching its
-// body B.  The colours here are the levels of that DAG (an ORDER-PRESERVING colouring): every
-// level is a set of body-disjoint contacts, applied atomics-free, and the result is bit-identical
-// to the sequential sweep (a free greedy colouring would reorder the sweep and change velocities
-// by far more than 1e-4 wherever contacts share bodies).
+// body B.  Executing the DAG in any topological order is bit-identical to the sequential sweep (a
+// free greedy colouring would reorder it and change velocities by far more than 1e-4 wherever
+// contacts share bodies).  The "colours" here are therefore the DAG's own antichains, discovered
+// on the fly: no atomics on body state, every body is touched by one contact at a time.
 //
-//   incidence_count / scan / fill     per-body lists of incident contacts
-//   schedule_kernel                   sort each list by contact id -> successor links + in-degrees
-//   solve_levels_kernel (cooperative) frontier = contacts with in-degree 0; per level: apply the
-//                                     frontier, decrement successors, grid.sync()
+//   incidence_count / scan / fill   per-body lists of incident contacts
+//   schedule_kernel                 sort each list by contact id -> successor links + in-degrees
+//   seed_kernel                     contacts with in-degree 0 enter the ready queue
+//   solve_dataflow_kernel           persistent warps take 32 queue tickets at a time, apply every
+//                                   ticket whose contact has arrived (converged lanes), decrement
+//                                   the successors' in-degrees and append the newly ready ones.
 //
-// HBM-bound in bytes (184 B/contact), latency-bound in practice: depth x (grid sync + one Constraint).
+// Progress: queue slot t is filled once the contacts in slots < t that it depends on are done, and
+// tickets are issued in order, so every ticket a warp waits on is owed by a warp that is already
+// running (no co-residency requirement, no grid barrier).  A spin cap turns any violation into an
+// error instead of a hang.  v1 of this file ran level-synchronously (cooperative grid.sync per DAG
+// level: 63 % of stall samples sat at the barrier, profiles/r1_v1_ncu_full_summary.txt); that
+// kernel is kept for A/B runs (NANS_SOLVER=levels).
+//
+// HBM-bound in bytes (184 B/contact), latency-bound in practice: critical path = DAG depth x
+// (publish -> poll -> gather -> one Constraint).
 #include <cooperative_groups.h>
+#include <stdlib.h>
+#include <string.h>
 
 #include "nans_math.cuh"
 #include "world.cuh"
@@ -35,6 +47,8 @@ __global__ void __launch_bounds__(256) incidence_count_kernel(DeviceWorld w)
         w.indeg[c] = 0;
         w.succ_a[c] = -1;
         w.succ_b[c] = -1;
+        w.frontier[0][c] = -1;   // ready queue: empty slots
+        w.frontier[1][c] = 0;    // DAG level of the contact (statistic)
     }
 }
 
@@ -71,12 +85,34 @@ __global__ void __launch_bounds__(256) schedule_kernel(DeviceWorld w)
     }
 }
 
+// ready queue = frontier[0]; counters->frontier_n[0] = head (tickets issued), [1] = tail (slots filled)
+__global__ void __launch_bounds__(256) seed_kernel(DeviceWorld w)
+{
+    const int n = w.counters->n_contacts;
+    const int stride = gridDim.x * blockDim.x;
+    const int lane = threadIdx.x & 31;
+    for (int c0 = (blockIdx.x * blockDim.x + threadIdx.x) - lane; c0 < n; c0 += stride) {
+        const int c = c0 + lane;
+        const bool root = c < n && w.indeg[c] == 0;
+        const unsigned m = __ballot_sync(0xffffffffu, root);
+        if (m == 0) continue;
+        int base = 0;
+        if (lane == 0) base = atomicAdd(&w.counters->frontier_n[1], __popc(m));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (root) {
+            w.frontier[0][base + __popc(m & ((1u << lane) - 1u))] = c;
+            w.frontier[1][c] = 1;
+        }
+    }
+}
+
 // Constraint, code/nans.cpp:1021-1329 — bug-compatible: minus sign on body B's
 // angular JMJ term, cross(W, N) instead of cross(W, R), un-normalised T1, 70 iterations over
 // constants of which only the last delta is applied, friction bound evaluated in fp64.
 __device__ __forceinline__ void apply_constraint(const DeviceWorld &w, int c, float dt)
 {
-    const int ia = w.c_a[c], ib = w.c_b[c];
+    const float4 cpa = w.c_pa[c], cpb = w.c_pb[c];      // w lanes carry the body rows
+    const int ia = __float_as_int(cpa.w), ib = __float_as_int(cpb.w);
     const float4 pa4 = w.pos[ia];
     float4 va4 = __ldcg(&w.vel[ia]);      // w = 1/Mass
     float4 wa4 = __ldcg(&w.angvel[ia]);   // w = 1/MOI
@@ -101,8 +137,8 @@ __device__ __forceinline__ void apply_constraint(const DeviceWorld &w, int c, fl
     }
     vec3 N = normalize(V3(w.c_n[c]));
     if (equal(N, V3(0.f, 0.f, 0.f))) N = normalize(posB - posA);   // :1115-1119
-    const vec3 R1 = V3(w.c_pa[c]) - posA;
-    const vec3 R2 = V3(w.c_pb[c]) - posB;
+    const vec3 R1 = V3(cpa) - posA;
+    const vec3 R2 = V3(cpb) - posB;
     vec3 T1;
     if (N.x >= 0.57735f) T1 = V3(N.y, -N.x, 0.0f); else T1 = V3(0.0f, N.z, -N.y);
     const vec3 T2 = cross(N, T1);                                    // T1 is NOT normalised (:1133)
@@ -171,6 +207,69 @@ __device__ __forceinline__ void apply_constraint(const DeviceWorld &w, int c, fl
     }
 }
 
+// ---- dataflow execution -------------------------------------------------------------------------
+constexpr int kFlowThreads = 256;
+constexpr int kSpinCap = 1 << 22;   // polls before declaring the schedule broken (seconds of wall time)
+
+__global__ void __launch_bounds__(kFlowThreads) solve_dataflow_kernel(DeviceWorld w, float dt)
+{
+    const int n = w.counters->n_contacts;
+    const int lane = threadIdx.x & 31;
+    const unsigned lt = (1u << lane) - 1u;
+    int *head = &w.counters->frontier_n[0];
+    int *tail = &w.counters->frontier_n[1];
+    volatile int *abort_flag = &w.counters->frontier_n[2];
+    volatile int32_t *queue = w.frontier[0];
+    int32_t *level = w.frontier[1];
+    int max_level = 0;
+    while (true) {
+        int base = 0;
+        if (lane == 0) base = atomicAdd(head, 32);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (base >= n) break;
+        const int t = base + lane;
+        bool done = t >= n;
+        int spins = 0;
+        while (!__all_sync(0xffffffffu, done)) {
+            int c = -1;
+            if (!done) c = queue[t];
+            const bool go = c >= 0;
+            if (go) {
+                __threadfence();                       // acquire: the predecessors' velocity writes
+                apply_constraint(w, c, dt);
+                const int lv = __ldcg(&level[c]);
+                max_level = max(max_level, lv);
+                const int sa = w.succ_a[c], sb = w.succ_b[c];
+                __threadfence();                       // release: publish this contact's writes
+                bool pa = false, pb = false;
+                if (sa >= 0) { atomicMax(&level[sa], lv + 1); pa = atomicSub(&w.indeg[sa], 1) == 1; }
+                if (sb >= 0) { atomicMax(&level[sb], lv + 1); pb = atomicSub(&w.indeg[sb], 1) == 1; }
+                // append the newly ready successors: one tail atomic per converged group
+                const unsigned am = __activemask();
+                const unsigned b1 = __ballot_sync(am, pa), b2 = __ballot_sync(am, pb);
+                const int total = __popc(b1) + __popc(b2);
+                if (total) {
+                    const int leader = __ffs(am) - 1;
+                    int slot = 0;
+                    if (lane == leader) slot = atomicAdd(tail, total);
+                    slot = __shfl_sync(am, slot, leader) + __popc(b1 & lt) + __popc(b2 & lt);
+                    __threadfence();                   // order the in-degree RMWs before the slot stores
+                    if (pa) queue[slot++] = sa;
+                    if (pb) queue[slot] = sb;
+                }
+                done = true;
+            }
+            if (!__any_sync(0xffffffffu, go)) {
+                if (++spins > kSpinCap || *abort_flag) { *abort_flag = 1; return; }
+                __nanosleep(40);
+            }
+        }
+    }
+    max_level = __reduce_max_sync(0xffffffffu, max_level);
+    if (lane == 0 && max_level) atomicMax(&w.counters->solver_levels, max_level);
+}
+
+// ---- v1: level-synchronous execution (kept for A/B, NANS_SOLVER=levels) -----------------------
 constexpr int kSolveThreads = 256;
 
 __global__ void __launch_bounds__(kSolveThreads) solve_levels_kernel(DeviceWorld w, float dt)
@@ -180,7 +279,6 @@ __global__ void __launch_bounds__(kSolveThreads) solve_levels_kernel(DeviceWorld
     const int tid = blockIdx.x * blockDim.x + threadIdx.x;
     const int nthreads = gridDim.x * blockDim.x;
     volatile int32_t *fn = w.counters->frontier_n;
-    // level-0 frontier: contacts with no predecessor
     for (int c = tid; c < n; c += nthreads)
         if (w.indeg[c] == 0) w.frontier[0][atomicAdd(&w.counters->frontier_n[0], 1)] = c;
     grid.sync();
@@ -211,6 +309,14 @@ int launch_solver(World *w, float dt)
     DeviceWorld &d = w->d;
     if (d.nb == 0) return NANS_OK;
     cudaStream_t s = w->stream;
+    static int mode = -1, sm_count = 0;
+    if (mode < 0) {
+        const char *e = getenv("NANS_SOLVER");
+        mode = (e && !strcmp(e, "levels")) ? 1 : 0;
+        cudaDeviceProp prop;
+        NANS_CUDA(cudaGetDeviceProperties(&prop, w->device));
+        sm_count = prop.multiProcessorCount;
+    }
     NANS_CUDA(cudaMemsetAsync(d.deg, 0, sizeof(uint32_t) * ((size_t)d.nb + 1), s));
     NANS_CUDA(cudaMemsetAsync(d.cursor, 0, sizeof(uint32_t) * (size_t)d.nb, s));
     NANS_CUDA(cudaMemsetAsync(d.counters->frontier_n, 0, sizeof(int32_t) * 3, s));
@@ -224,18 +330,28 @@ int launch_solver(World *w, float dt)
     schedule_kernel<<<div_up(d.nb, 256), 256, 0, s>>>(d);
     NANS_LAUNCH_CHECK();
 
-    if (!w->coop_blocks_per_sm) {
-        int per_sm = 0;
-        NANS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, solve_levels_kernel, kSolveThreads, 0));
-        w->coop_blocks_per_sm = per_sm < 1 ? 1 : (per_sm > 2 ? 2 : per_sm);
+    if (mode == 1) {
+        if (!w->coop_blocks_per_sm) {
+            int per_sm = 0;
+            NANS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, solve_levels_kernel, kSolveThreads, 0));
+            w->coop_blocks_per_sm = per_sm < 1 ? 1 : (per_sm > 2 ? 2 : per_sm);
+        }
+        void *args[] = {(void *)&d, (void *)&dt};
+        NANS_CUDA(cudaLaunchCooperativeKernel((void *)solve_levels_kernel, dim3(sm_count * w->coop_blocks_per_sm),
+                                              dim3(kSolveThreads), args, 0, s));
+        ++g_launches;
+        return NANS_OK;
     }
-    cudaDeviceProp prop;
-    static int sm_count = 0;
-    if (!sm_count) { NANS_CUDA(cudaGetDeviceProperties(&prop, w->device)); sm_count = prop.multiProcessorCount; }
-    void *args[] = {(void *)&d, (void *)&dt};
-    NANS_CUDA(cudaLaunchCooperativeKernel((void *)solve_levels_kernel, dim3(sm_count * w->coop_blocks_per_sm),
-                                          dim3(kSolveThreads), args, 0, s));
-    ++g_launches;
+    seed_kernel<<<grid, 256, 0, s>>>(d);
+    NANS_LAUNCH_CHECK();
+    static int flow_blocks = 0;
+    if (!flow_blocks) {
+        int per_sm = 0;
+        NANS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, solve_dataflow_kernel, kFlowThreads, 0));
+        flow_blocks = sm_count * (per_sm < 1 ? 1 : (per_sm > 3 ? 3 : per_sm));
+    }
+    solve_dataflow_kernel<<<flow_blocks, kFlowThreads, 0, s>>>(d, dt);
+    NANS_LAUNCH_CHECK();
     return NANS_OK;
 }
 

@@ -53,13 +53,13 @@ struct DeviceWorld {
     float4 *st_verts;  // [n_statics][6]
     float4 *st_aabb;   // [n_statics][2]
     // --- broadphase
-    float4 *aabb_lo, *aabb_hi;          // [2*nb]: rows [0,nb) by body, [nb,2nb) in Morton order
+    float4 *aabb_lo, *aabb_hi;          // [nb] by body row
     uint32_t *key[2];                   // Morton cell keys (double buffer for the radix sort)
     uint32_t *val[2];                   // body rows
     uint32_t *radix_hist;               // [256 * radix_blocks]
-    uint32_t *cell_keys;                // hash table: key
-    uint32_t *cell_start;               //             first sorted position
-    uint32_t *cell_end;                 //             one past last
+    uint4 *cell_tab;                    // hash table of cells: {key, first sorted position, one past last, -}
+    float4 *sbox;                       // [2*nb] Morton-ordered AABB records {lo.xyz,row}{hi.xyz,world}
+    uint32_t *pair_tmp;                 // [nb * 24] partner slots filled by the counting pass
     uint32_t cell_mask;                 // table size - 1
     uint32_t *pair_count;               // [5 * nb + 1] per (type, body) candidate counts -> offsets
     int32_t *pair_a, *pair_b;           // [max_pairs] body rows; static k encoded as -(k+1)

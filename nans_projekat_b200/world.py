@@ -106,6 +106,14 @@ class World:
         arrs = [None if x is None else np.asarray(x, np.float32) for x in (pos, vel, angvel)]
         _lib.check(_lib.lib().nans_world_set_body(self._h, body_row, *[_fp(a) for a in arrs]))
 
+    def snapshot(self):
+        """Device-side copy of the dynamic state (asynchronous)."""
+        _lib.check(_lib.lib().nans_world_snapshot(self._h))
+
+    def restore(self):
+        """Back to the last snapshot (device-to-device, asynchronous)."""
+        _lib.check(_lib.lib().nans_world_restore(self._h))
+
     # ---- stages -------------------------------------------------------------------------
     def integrate_forces(self, dt):
         _lib.check(_lib.lib().nans_integrate_forces(self._h, dt))
