@@ -528,7 +528,7 @@ int nans_get_stats(nans_world *h, nans_step_stats *out)
     memset(out, 0, sizeof(*out));
     out->n_pairs = c->n_pairs; out->n_contacts = c->n_contacts; out->n_gjk_found = c->n_gjk_found;
     out->solver_levels = c->solver_levels; out->overflow = c->overflow; out->max_epa_faces = c->max_epa_faces;
-    if (c->frontier_n[2]) return fail(NANS_ERR_STATE, "solver: dependency schedule stalled (spin cap hit)");
+    if (c->pad[1]) return fail(NANS_ERR_STATE, "solver: dependency schedule stalled (spin cap hit)");
     if (c->overflow) {
         snprintf(g_err, sizeof(g_err), "capacity exceeded (overflow bits 0x%x: 1 pairs, 2 contacts, 4 EPA faces, 8 EPA edges)",
                  c->overflow);

@@ -218,7 +218,7 @@ __global__ void __launch_bounds__(kFlowThreads) solve_dataflow_kernel(DeviceWorl
     const unsigned lt = (1u << lane) - 1u;
     int *head = &w.counters->frontier_n[0];
     int *tail = &w.counters->frontier_n[1];
-    volatile int *abort_flag = &w.counters->frontier_n[2];
+    volatile int *abort_flag = &w.counters->pad[1];
     volatile int32_t *queue = w.frontier[0];
     int32_t *level = w.frontier[1];
     int max_level = 0;
