@@ -5,7 +5,8 @@
 // CS (cube-major), SS (i<j) — so that compaction of the narrowphase hits yields the reference's
 // contact list with no sort of the contacts.
 //
-//   aabb_key_kernel      AABB per body (8 vertices / centre +- radius) + 30-bit Morton cell key
+//   aabb_kernel          AABB per body (8 vertices / centre +- radius) + this step's largest extent
+//   key_kernel           30-bit Morton key of the cell (edge = largest extent) holding the AABB centre
 //   radix sort           4 x 8-bit LSD passes (histogram -> scan -> stable scatter), key+row payload
 //   gather_sorted_kernel AABBs permuted into Morton order (neighbour scans read contiguous ranges)
 //   cell_table_kernel    open-addressing hash: cell key -> [start, end) in the sorted order
@@ -84,7 +85,8 @@ __device__ __forceinline__ int cell_coord(float c, float inv_cell)
     return (int)f + 512;   // NaN -> (int)NaN = 0 -> 512
 }
 
-__global__ void __launch_bounds__(256) aabb_key_kernel(DeviceWorld w, float inv_cell)
+// AABB per body + the largest AABB extent of this step (block reduce -> one atomicMax per block).
+__global__ void __launch_bounds__(256) aabb_kernel(DeviceWorld w)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < w.n_statics) {   // statics: AABB only (tested against every body, never sorted)
@@ -93,23 +95,51 @@ __global__ void __launch_bounds__(256) aabb_key_kernel(DeviceWorld w, float inv_
         w.st_aabb[2 * i] = make_float4(lo[0], lo[1], lo[2], 0.f);
         w.st_aabb[2 * i + 1] = make_float4(hi[0], hi[1], hi[2], 0.f);
     }
-    if (i >= w.nb) return;
-    float lo[3], hi[3];
-    if (i < w.n_cubes) {
-        box_aabb(w.verts + 6 * (size_t)i, lo, hi);
-    } else {
-        const float4 p = w.pos[i];
-        const float r = w.scale[i].w;
-        lo[0] = p.x - r; lo[1] = p.y - r; lo[2] = p.z - r;
-        hi[0] = p.x + r; hi[1] = p.y + r; hi[2] = p.z + r;
+    float ext = 0.f;
+    if (i < w.nb) {
+        float lo[3], hi[3];
+        if (i < w.n_cubes) {
+            box_aabb(w.verts + 6 * (size_t)i, lo, hi);
+        } else {
+            const float4 p = w.pos[i];
+            const float r = w.scale[i].w;
+            lo[0] = p.x - r; lo[1] = p.y - r; lo[2] = p.z - r;
+            hi[0] = p.x + r; hi[1] = p.y + r; hi[2] = p.z + r;
 #pragma unroll
-        for (int k = 0; k < 3; ++k) inflate(lo[k], hi[k]);
+            for (int k = 0; k < 3; ++k) inflate(lo[k], hi[k]);
+        }
+        w.aabb_lo[i] = make_float4(lo[0], lo[1], lo[2], 0.f);
+        w.aabb_hi[i] = make_float4(hi[0], hi[1], hi[2], 0.f);
+        ext = fmaxf(fmaxf(hi[0] - lo[0], hi[1] - lo[1]), hi[2] - lo[2]);   // fmaxf drops NaN
     }
-    w.aabb_lo[i] = make_float4(lo[0], lo[1], lo[2], 0.f);
-    w.aabb_hi[i] = make_float4(hi[0], hi[1], hi[2], 0.f);
-    int cx = cell_coord(0.5f * (lo[0] + hi[0]), inv_cell);
-    int cy = cell_coord(0.5f * (lo[1] + hi[1]), inv_cell);
-    int cz = cell_coord(0.5f * (lo[2] + hi[2]), inv_cell);
+    // non-negative floats order like their bit patterns
+    ext = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(fmaxf(ext, 0.f))));
+    __shared__ float wmax[8];
+    if ((threadIdx.x & 31) == 0) wmax[threadIdx.x >> 5] = ext;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float m = wmax[0];
+#pragma unroll
+        for (int k = 1; k < 8; ++k) m = fmaxf(m, wmax[k]);
+        atomicMax((unsigned int *)&w.counters->pad[2], __float_as_uint(m));   // non-negative floats order as uints
+    }
+}
+
+// Morton cell key of the AABB centre.  The cell edge is this step's largest AABB extent (so that
+// AABB-overlapping bodies always sit in adjacent cells) — far tighter than the static bound (box
+// diagonal) while the bodies are near axis-aligned; the static bound is the fallback if it is not finite.
+__global__ void __launch_bounds__(256) key_kernel(DeviceWorld w)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= w.nb) return;
+    float cell = __uint_as_float((unsigned int)w.counters->pad[2]) * 1.0001f + 1e-4f;
+    if (!isfinite(cell)) cell = w.cell_size;             // overflowed vertices: static bound (box diagonal)
+    cell = fmaxf(cell, 0.05f);
+    const float inv_cell = 1.0f / cell;
+    const float4 lo = w.aabb_lo[i], hi = w.aabb_hi[i];
+    int cx = cell_coord(0.5f * (lo.x + hi.x), inv_cell);
+    int cy = cell_coord(0.5f * (lo.y + hi.y), inv_cell);
+    int cz = cell_coord(0.5f * (lo.z + hi.z), inv_cell);
     if (w.world_id) {
         // batched independent worlds: each world owns a 16x16 column of cells in x,z
         const int wid = w.world_id[i];
@@ -364,7 +394,9 @@ int launch_broadphase(World *w)
     const int nb = d.nb;
     NANS_CUDA(cudaMemsetAsync(d.counters, 0, sizeof(Counters), s));
     if (nb == 0) return NANS_OK;
-    aabb_key_kernel<<<div_up(max(nb, d.n_statics), 256), 256, 0, s>>>(d, 1.0f / d.cell_size);
+    aabb_kernel<<<div_up(max(nb, d.n_statics), 256), 256, 0, s>>>(d);
+    NANS_LAUNCH_CHECK();
+    key_kernel<<<div_up(nb, 256), 256, 0, s>>>(d);
     NANS_LAUNCH_CHECK();
 
     // radix sort on key[0]/val[0] <-> key[1]/val[1]; 30-bit keys = 4 passes, ends in buffer 0

@@ -7,9 +7,9 @@
 
 namespace nans {
 
-__device__ __forceinline__ void load_box(float *sv, int side, const float4 *__restrict__ v6)
+__device__ __forceinline__ void load_box(int side, const float4 *__restrict__ v6)
 {
-    float *p = sv + 24 * side * kNpThreads;
+    float *p = g_np_verts + 24 * side * kNpThreads + threadIdx.x;
 #pragma unroll
     for (int q = 0; q < 6; ++q) {
         const float4 t = __ldg(v6 + q);
@@ -18,7 +18,7 @@ __device__ __forceinline__ void load_box(float *sv, int side, const float4 *__re
     }
 }
 
-__device__ __forceinline__ NpResult dispatch(bool a_sphere, bool b_sphere, const NpShapes &S, EpaArena &E,
+__device__ __forceinline__ NpResult dispatch(bool a_sphere, bool b_sphere, NpShapes &S, EpaArena &E,
                                              int &ovf, int &max_faces)
 {
     if (!a_sphere && !b_sphere) return check_collision<false, false>(S, E, ovf, max_faces);
@@ -29,13 +29,11 @@ __device__ __forceinline__ NpResult dispatch(bool a_sphere, bool b_sphere, const
 
 __global__ void __launch_bounds__(kNpThreads, 5) narrowphase_world_kernel(DeviceWorld w, int *work_counter)
 {
-    __shared__ float smem[48 * kNpThreads];   // both shapes' vertices, transposed: [float][thread]
     EpaArena E;
     const int lane = threadIdx.x & 31;
     const int n_pairs = w.counters->n_pairs;
     int ovf = 0, max_faces = 0, found = 0;
     NpShapes S;
-    S.sv = smem + threadIdx.x;
     while (true) {
         int base = 0;
         if (lane == 0) base = atomicAdd(work_counter, 32);
@@ -48,15 +46,15 @@ __global__ void __launch_bounds__(kNpThreads, 5) narrowphase_world_kernel(Device
             const bool b_sphere = rb >= w.n_cubes;   // statics are negative -> box
             S.posA = V3(w.pos[ra]);
             S.radA = 0.f;
-            if (a_sphere) S.radA = w.scale[ra].w; else load_box(smem + threadIdx.x, 0, w.verts + 6 * (size_t)ra);
+            if (a_sphere) S.radA = w.scale[ra].w; else load_box(0, w.verts + 6 * (size_t)ra);
             S.radB = 0.f;
             if (rb < 0) {
                 const int k = -rb - 1;
                 S.posB = V3(w.st_pos[k]);
-                load_box(smem + threadIdx.x, 1, w.st_verts + 6 * k);
+                load_box(1, w.st_verts + 6 * k);
             } else {
                 S.posB = V3(w.pos[rb]);
-                if (b_sphere) S.radB = w.scale[rb].w; else load_box(smem + threadIdx.x, 1, w.verts + 6 * (size_t)rb);
+                if (b_sphere) S.radB = w.scale[rb].w; else load_box(1, w.verts + 6 * (size_t)rb);
             }
             const NpResult r = dispatch(a_sphere, b_sphere, S, E, ovf, max_faces);
             found += (r.gjk == kFoundIntersection);
@@ -87,12 +85,10 @@ __global__ void __launch_bounds__(kNpThreads, 5) narrowphase_batch_kernel(
     const float4 *__restrict__ verts_b, int32_t *__restrict__ hit, int32_t *__restrict__ gjk,
     float4 *__restrict__ out, int *work_counter, Counters *counters)
 {
-    __shared__ float smem[48 * kNpThreads];
     EpaArena E;
     const int lane = threadIdx.x & 31;
     int ovf = 0, max_faces = 0;
     NpShapes S;
-    S.sv = smem + threadIdx.x;
     while (true) {
         int base = 0;
         if (lane == 0) base = atomicAdd(work_counter, 32);
@@ -106,8 +102,8 @@ __global__ void __launch_bounds__(kNpThreads, 5) narrowphase_batch_kernel(
             const float4 pa = posrad_a[p], pb = posrad_b[p];
             S.posA = V3(pa); S.radA = pa.w;
             S.posB = V3(pb); S.radB = pb.w;
-            if (!a_sphere) load_box(smem + threadIdx.x, 0, verts_a + 6 * (size_t)p);
-            if (!b_sphere) load_box(smem + threadIdx.x, 1, verts_b + 6 * (size_t)p);
+            if (!a_sphere) load_box(0, verts_a + 6 * (size_t)p);
+            if (!b_sphere) load_box(1, verts_b + 6 * (size_t)p);
             const NpResult r = dispatch(a_sphere, b_sphere, S, E, ovf, max_faces);
             hit[p] = r.hit;
             if (gjk) gjk[p] = r.gjk;

@@ -27,15 +27,20 @@ enum { kNoIntersection = 0, kFoundIntersection = 1, kStillEvolving = 2 };  // ev
 constexpr int kNpThreads = 128;
 constexpr int kNoVertex = 8;   // box support when every compare failed (NaN direction): vec3(0)
 
-// Per-thread view of the two shapes.  Box vertices: smem[(24*side + 3*k + r) * kNpThreads + tid].
+// Both shapes' box vertices, transposed: g_np_verts[(24*side + 3*k + r) * kNpThreads + tid].
+// File-scope __shared__ so every access compiles to LDS/STS (a pointer carried through the call
+// chain degrades to generic loads).
+__shared__ float g_np_verts[48 * kNpThreads];
+
+// Per-thread view of the two shapes.
 struct NpShapes {
-    const float *sv;     // &smem[tid]
     vec3 posA, posB;     // body centres (GJK start direction; sphere support)
+    vec3 dir0;           // normalize(posB - posA): EvolveSimplex recomputes it every call (:575); hoisted
     float radA, radB;    // spheres
     __device__ __forceinline__ vec3 vertex(int side, int k) const
     {
         if (k >= 8) return V3(0.f, 0.f, 0.f);
-        const float *p = sv + (24 * side + 3 * k) * kNpThreads;
+        const float *p = g_np_verts + (24 * side + 3 * k) * kNpThreads + threadIdx.x;
         return V3(p[0], p[kNpThreads], p[2 * kNpThreads]);
     }
 };
@@ -47,7 +52,7 @@ __device__ __forceinline__ vec3 box_support(const NpShapes &S, int side, vec3 d,
     float best = -FLT_MAX;
     vec3 res = V3(0.f, 0.f, 0.f);
     idx = kNoVertex;
-    const float *p = S.sv + 24 * side * kNpThreads;
+    const float *p = g_np_verts + 24 * side * kNpThreads + threadIdx.x;
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
         const vec3 c = V3(p[(3 * k) * kNpThreads], p[(3 * k + 1) * kNpThreads], p[(3 * k + 2) * kNpThreads]);
@@ -123,7 +128,7 @@ __device__ __forceinline__ vec3 triple_cross(vec3 A, vec3 B, vec3 C) { return (B
 template <bool AS, bool BS>
 __device__ __forceinline__ int evolve_simplex(const NpShapes &S, GjkVertex<AS, BS> (&s)[4], int &n)
 {
-    vec3 dir = normalize(S.posB - S.posA);
+    vec3 dir = S.dir0;
     if (n == 1) {
         dir = dir * -1.0f;
     } else if (n == 2) {
@@ -313,10 +318,11 @@ struct NpResult { int hit, gjk; vec3 PA, PB, N; };
 
 // CheckCollision, code/nans.cpp:907-966
 template <bool AS, bool BS>
-__device__ __noinline__ NpResult check_collision(const NpShapes &S, EpaArena &E, int &ovf, int &max_faces)
+__device__ __noinline__ NpResult check_collision(NpShapes &S, EpaArena &E, int &ovf, int &max_faces)
 {
     GjkVertex<AS, BS> s[4];
     int n = 0, ev = kStillEvolving, iter = 0;
+    S.dir0 = normalize(S.posB - S.posA);
     while (ev == kStillEvolving && iter++ <= 64)   // MAX_GJK_ITERATIONS, code/nans.h:54
         ev = evolve_simplex<AS, BS>(S, s, n);
     NpResult r;
