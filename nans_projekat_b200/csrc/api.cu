@@ -467,9 +467,7 @@ int nans_rebuild_vertices(nans_world *h)
     if (!h) return fail(NANS_ERR_ARG, "null world");
     WorldImpl *w = impl(h);
     NANS_CUDA(cudaSetDevice(w->device));
-    int rc = launch_integrate_velocities(w, 0.0f);   // Position += 0*V is exact for finite V; rebuilds Model
-    if (rc) return rc;
-    return launch_rebuild_statics(w);
+    return launch_integrate_velocities(w, 0.0f);   // Position += 0*V is exact for finite V; rebuilds every Model
 }
 
 int nans_step(nans_world *h, float dt)

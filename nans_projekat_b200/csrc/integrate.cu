@@ -172,7 +172,8 @@ int launch_integrate_velocities(World *w, float dt)
     if (w->d.nb == 0) return NANS_OK;
     integrate_velocities_kernel<<<div_up(w->d.nb, 128), 128, 0, w->stream>>>(w->d, dt);
     NANS_LAUNCH_CHECK();
-    return NANS_OK;
+    // the draw section also refreshes the Floor's Model and vertices every frame (:1870-1881)
+    return launch_rebuild_statics(w);
 }
 
 int launch_rebuild_statics(World *w)

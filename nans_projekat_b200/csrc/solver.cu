@@ -211,6 +211,28 @@ __device__ __forceinline__ void apply_constraint(const DeviceWorld &w, int c, fl
 constexpr int kFlowThreads = 256;
 constexpr int kSpinCap = 1 << 22;   // polls before declaring the schedule broken (seconds of wall time)
 
+// gpu-scope acquire/release primitives (cheaper than the sequentially-consistent __threadfence())
+__device__ __forceinline__ int ld_acquire(const int *p)
+{
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release(int *p, int v)
+{
+    asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ int atom_add_acq_rel(int *p, int v)
+{
+    int o;
+    asm volatile("atom.acq_rel.gpu.global.add.s32 %0, [%1], %2;" : "=r"(o) : "l"(p), "r"(v) : "memory");
+    return o;
+}
+
+// Memory ordering: a contact's velocity stores are released by the acq_rel decrement of each
+// successor's in-degree; whoever performs the LAST decrement has thereby acquired both predecessors'
+// stores (RMW chain on the same counter) and either runs the successor itself or hands it over
+// through a release store to the queue slot, which the ticket holder reads with an acquire load.
 __global__ void __launch_bounds__(kFlowThreads) solve_dataflow_kernel(DeviceWorld w, float dt)
 {
     const int n = w.counters->n_contacts;
@@ -218,8 +240,9 @@ __global__ void __launch_bounds__(kFlowThreads) solve_dataflow_kernel(DeviceWorl
     const unsigned lt = (1u << lane) - 1u;
     int *head = &w.counters->frontier_n[0];
     int *tail = &w.counters->frontier_n[1];
+    int *finished = &w.counters->frontier_n[2];
     volatile int *abort_flag = &w.counters->pad[1];
-    volatile int32_t *queue = w.frontier[0];
+    int32_t *queue = w.frontier[0];
     int32_t *level = w.frontier[1];
     int max_level = 0;
     while (true) {
@@ -229,41 +252,54 @@ __global__ void __launch_bounds__(kFlowThreads) solve_dataflow_kernel(DeviceWorl
         if (base >= n) break;
         const int t = base + lane;
         bool done = t >= n;
-        int spins = 0;
+        bool ticket_open = !done;     // queue slot t not consumed yet
+        int c = -1;                   // contact in hand (from the queue, or followed along a chain)
+        int spins = 0, processed = 0;
         while (!__all_sync(0xffffffffu, done)) {
-            int c = -1;
-            if (!done) c = queue[t];
+            if (ticket_open && c < 0) {
+                c = ld_acquire(queue + t);
+                if (c >= 0) ticket_open = false;
+            }
             const bool go = c >= 0;
             if (go) {
-                __threadfence();                       // acquire: the predecessors' velocity writes
                 apply_constraint(w, c, dt);
+                ++processed;
                 const int lv = __ldcg(&level[c]);
                 max_level = max(max_level, lv);
                 const int sa = w.succ_a[c], sb = w.succ_b[c];
-                __threadfence();                       // release: publish this contact's writes
-                bool pa = false, pb = false;
-                if (sa >= 0) { atomicMax(&level[sa], lv + 1); pa = atomicSub(&w.indeg[sa], 1) == 1; }
-                if (sb >= 0) { atomicMax(&level[sb], lv + 1); pb = atomicSub(&w.indeg[sb], 1) == 1; }
-                // append the newly ready successors: one tail atomic per converged group
+                bool ra = false, rb = false;
+                if (sa >= 0) { atomicMax(&level[sa], lv + 1); ra = atom_add_acq_rel(&w.indeg[sa], -1) == 1; }
+                if (sb >= 0) { atomicMax(&level[sb], lv + 1); rb = atom_add_acq_rel(&w.indeg[sb], -1) == 1; }
+                // a successor we completed is run by this lane straight away (chain following: no
+                // queue round trip); if both became ready the second one goes to the queue
+                const bool push_b = ra && rb;
                 const unsigned am = __activemask();
-                const unsigned b1 = __ballot_sync(am, pa), b2 = __ballot_sync(am, pb);
-                const int total = __popc(b1) + __popc(b2);
-                if (total) {
+                const unsigned pb = __ballot_sync(am, push_b);
+                if (pb) {
                     const int leader = __ffs(am) - 1;
                     int slot = 0;
-                    if (lane == leader) slot = atomicAdd(tail, total);
-                    slot = __shfl_sync(am, slot, leader) + __popc(b1 & lt) + __popc(b2 & lt);
-                    __threadfence();                   // order the in-degree RMWs before the slot stores
-                    if (pa) queue[slot++] = sa;
-                    if (pb) queue[slot] = sb;
+                    if (lane == leader) slot = atomicAdd(tail, __popc(pb));
+                    slot = __shfl_sync(am, slot, leader) + __popc(pb & lt);
+                    if (push_b) st_release(queue + slot, sb);
                 }
-                done = true;
+                c = ra ? sa : (rb ? sb : -1);
+                if (c < 0 && !ticket_open) done = true;
             }
             if (!__any_sync(0xffffffffu, go)) {
+                // nothing arrived: publish this warp's progress, then check whether everything is
+                // finished (chain following leaves tickets unfilled, so emptiness is decided by count)
+                const int p = __reduce_add_sync(0xffffffffu, processed);
+                if (p) {
+                    if (lane == 0) atomicAdd(finished, p);
+                    processed = 0;
+                }
+                if (*(volatile int *)finished >= n) { done = true; continue; }
                 if (++spins > kSpinCap || *abort_flag) { *abort_flag = 1; return; }
-                __nanosleep(40);
+                __nanosleep(32);
             }
         }
+        processed = __reduce_add_sync(0xffffffffu, processed);
+        if (lane == 0 && processed) atomicAdd(finished, processed);
     }
     max_level = __reduce_max_sync(0xffffffffu, max_level);
     if (lane == 0 && max_level) atomicMax(&w.counters->solver_levels, max_level);
