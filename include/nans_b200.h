@@ -43,7 +43,7 @@ typedef struct {
     int32_t n_spheres;      /* dynamic spheres, body rows [n_cubes, n_cubes+n_spheres) */
     int32_t n_statics;      /* floor-type slabs (reference: exactly one, the Floor) */
     int32_t max_pairs;      /* broadphase candidate capacity (0 = default 24 * bodies) */
-    int32_t max_contacts;   /* contact capacity            (0 = default 12 * bodies) */
+    int32_t max_contacts;   /* contact capacity            (0 = default 8 * bodies) */
     int32_t device;         /* CUDA device ordinal */
     void *arena;            /* optional caller-provided device arena (e.g. a torch tensor) */
     uint64_t arena_bytes;   /* its size; ignored when arena == NULL */
@@ -149,6 +149,9 @@ int nans_check_collision_device(int32_t n, const int32_t *d_type,
                                 const float *d_posrad_a, const float *d_verts_a,
                                 const float *d_posrad_b, const float *d_verts_b,
                                 int32_t *d_hit, float *d_out, void *stream);
+
+/* debug aid: per-contact start time (ns) and dependency level of the last solve (NANS_SOLVER_TRACE=1) */
+int nans_debug_solver_trace(nans_world *w, uint64_t *times, int32_t *levels, int32_t cap);
 
 /* kernel-launch counter (all launches issued by this library in this process) */
 uint64_t nans_kernel_launches(void);

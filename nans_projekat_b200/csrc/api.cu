@@ -70,7 +70,7 @@ static Layout carve(const nans_world_desc &desc, char *base)
     const size_t nc = (size_t)(d.n_cubes > 0 ? d.n_cubes : 1);
     const size_t ns = (size_t)(d.n_statics > 0 ? d.n_statics : 1);
     d.max_pairs = desc.max_pairs > 0 ? desc.max_pairs : (int32_t)(24 * nb + 1024);
-    d.max_contacts = desc.max_contacts > 0 ? desc.max_contacts : (int32_t)(12 * nb + 1024);
+    d.max_contacts = desc.max_contacts > 0 ? desc.max_contacts : (int32_t)(8 * nb + 1024);
     const size_t mp = (size_t)d.max_pairs, mc = (size_t)d.max_contacts;
     d.pos = b.take<float4>(nb); d.vel = b.take<float4>(nb); d.angvel = b.take<float4>(nb);
     d.ang = b.take<float4>(nb); d.force = b.take<float4>(nb); d.torque = b.take<float4>(nb);
@@ -98,6 +98,7 @@ static Layout carve(const nans_world_desc &desc, char *base)
     d.inc = b.take<int32_t>(2 * mc);
     d.succ_a = b.take<int32_t>(mc); d.succ_b = b.take<int32_t>(mc); d.indeg = b.take<int32_t>(mc);
     for (int k = 0; k < 3; ++k) d.frontier[k] = b.take<int32_t>(mc);
+    d.crec = b.take<float4>(10 * mc);
     size_t scan_n = mp + 1;
     if (5 * nb + 1 > scan_n) scan_n = 5 * nb + 1;
     if (256 * radix_blocks > scan_n) scan_n = 256 * radix_blocks;
@@ -608,6 +609,18 @@ int nans_set_contacts(nans_world *h, const nans_contact *in, int32_t count)
     NANS_CUDA(cudaMemcpyAsync(&d.counters->n_contacts, &count, sizeof(int32_t), cudaMemcpyHostToDevice, s));
     NANS_CUDA(cudaStreamSynchronize(s));
     w->have_contacts = true;
+    return NANS_OK;
+}
+
+// debug: per-contact start time (ns, %globaltimer) and DAG level of the last solve; needs NANS_SOLVER_TRACE=1
+int nans_debug_solver_trace(nans_world *h, uint64_t *times, int32_t *levels, int32_t cap)
+{
+    if (!h) return fail(NANS_ERR_ARG, "null world");
+    WorldImpl *w = impl(h);
+    NANS_CUDA(cudaSetDevice(w->device));
+    NANS_CUDA(cudaStreamSynchronize(w->stream));
+    if (times) NANS_CUDA(cudaMemcpy(times, w->d.pair_out, sizeof(uint64_t) * cap, cudaMemcpyDeviceToHost));
+    if (levels) NANS_CUDA(cudaMemcpy(levels, w->d.frontier[1], sizeof(int32_t) * cap, cudaMemcpyDeviceToHost));
     return NANS_OK;
 }
 

@@ -109,55 +109,103 @@ __global__ void __launch_bounds__(256) seed_kernel(DeviceWorld w)
 // Constraint, code/nans.cpp:1021-1329 — bug-compatible: minus sign on body B's
 // angular JMJ term, cross(W, N) instead of cross(W, R), un-normalised T1, 70 iterations over
 // constants of which only the last delta is applied, friction bound evaluated in fp64.
-__device__ __forceinline__ void apply_constraint(const DeviceWorld &w, int c, float dt)
+//
+// Split in two so that the dependency-critical part is as short as possible:
+//   contact_prep_kernel  everything that does not read velocities (N, T1, T2, the six R x axis
+//                        vectors, the three effective masses, the Baumgarte term, inverse masses) —
+//                        embarrassingly parallel, one 160-byte record per contact;
+//   apply_prepared       what must wait for the predecessors: relative velocities, the 70-iteration
+//                        accumulation, the impulses.  One contiguous record load + four body rows.
+// The arithmetic (operations, order, roundings) is exactly that of the single function.
+constexpr int kRecQuads = 10;   // float4 per contact record
+
+__global__ void __launch_bounds__(256) contact_prep_kernel(DeviceWorld w, float dt)
 {
-    const float4 cpa = w.c_pa[c], cpb = w.c_pb[c];      // w lanes carry the body rows
-    const int ia = __float_as_int(cpa.w), ib = __float_as_int(cpb.w);
-    const float4 pa4 = w.pos[ia];
-    float4 va4 = __ldcg(&w.vel[ia]);      // w = 1/Mass
-    float4 wa4 = __ldcg(&w.angvel[ia]);   // w = 1/MOI
-    const vec3 posA = V3(pa4);
-    const float invM1 = va4.w, invI1 = wa4.w;
-    vec3 V1 = V3(va4), W1 = V3(wa4);
-    vec3 posB, V2, W2;
-    float invM2, invI2;
-    float4 vb4 = make_float4(0, 0, 0, 0), wb4 = make_float4(0, 0, 0, 0);
-    if (ib >= 0) {
-        posB = V3(w.pos[ib]);
-        vb4 = __ldcg(&w.vel[ib]);
-        wb4 = __ldcg(&w.angvel[ib]);
-        invM2 = vb4.w; invI2 = wb4.w;
-        V2 = V3(vb4); W2 = V3(wb4);
-    } else {
-        const int k = -ib - 1;                 // the Floor: V = W = 0, never updated (:1278-1289)
-        const float4 sp = w.st_pos[k], sa = w.st_ang[k];
-        posB = V3(sp);
-        invM2 = sp.w; invI2 = sa.w;
-        V2 = V3(0.f, 0.f, 0.f); W2 = V3(0.f, 0.f, 0.f);
+    const int n = w.counters->n_contacts;
+    const int stride = gridDim.x * blockDim.x;
+    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < n; c += stride) {
+        const float4 cpa = w.c_pa[c], cpb = w.c_pb[c];      // w lanes carry the body rows
+        const int ia = __float_as_int(cpa.w), ib = __float_as_int(cpb.w);
+        const vec3 posA = V3(w.pos[ia]);
+        const float invM1 = w.vel[ia].w, invI1 = w.angvel[ia].w;
+        vec3 posB;
+        float invM2, invI2;
+        if (ib >= 0) {
+            posB = V3(w.pos[ib]);
+            invM2 = w.vel[ib].w; invI2 = w.angvel[ib].w;
+        } else {
+            const int k = -ib - 1;                 // the Floor (:1065-1077)
+            const float4 sp = w.st_pos[k], sa = w.st_ang[k];
+            posB = V3(sp);
+            invM2 = sp.w; invI2 = sa.w;
+        }
+        vec3 N = normalize(V3(w.c_n[c]));
+        if (equal(N, V3(0.f, 0.f, 0.f))) N = normalize(posB - posA);   // :1115-1119
+        const vec3 R1 = V3(cpa) - posA;
+        const vec3 R2 = V3(cpb) - posB;
+        vec3 T1;
+        if (N.x >= 0.57735f) T1 = V3(N.y, -N.x, 0.0f); else T1 = V3(0.0f, N.z, -N.y);
+        const vec3 T2 = cross(N, T1);                                    // T1 is NOT normalised (:1133)
+        const float depth = dot((posA + R1) - (posB + R2), N);
+        const vec3 RN1 = cross(R1, N), RN2 = cross(R2, N);
+        float JMJn = fadd(invM1, invM2);
+        JMJn = fadd(JMJn, fsub(fmul(invI1, dot(RN1, RN1)), fmul(invI2, dot(-RN2, -RN2))));
+        JMJn = fdiv(1.0f, JMJn);
+        const vec3 R1T1 = cross(R1, T1), R2T1 = cross(R2, T1), R1T2 = cross(R1, T2), R2T2 = cross(R2, T2);
+        float JMJt1 = fadd(invM1, invM2);
+        JMJt1 = fadd(JMJt1, fsub(fmul(invI1, dot(R1T1, R1T1)), fmul(invI2, dot(-R2T1, -R2T1))));
+        JMJt1 = fdiv(1.0f, JMJt1);
+        float JMJt2 = fadd(invM1, invM2);
+        JMJt2 = fadd(JMJt2, fsub(fmul(invI1, dot(R1T2, R1T2)), fmul(invI2, dot(-R2T2, -R2T2))));
+        JMJt2 = fdiv(1.0f, JMJt2);
+        const float Bd = fmul(fdiv(-0.3f, dt), depth);                  // (-Beta / dt) * Depth (:1156)
+        float4 *r = w.crec + (size_t)kRecQuads * c;
+        r[0] = make_float4(N.x, N.y, N.z, JMJn);
+        r[1] = make_float4(T1.x, T1.y, T1.z, JMJt1);
+        r[2] = make_float4(T2.x, T2.y, T2.z, JMJt2);
+        r[3] = make_float4(RN1.x, RN1.y, RN1.z, invM1);
+        r[4] = make_float4(RN2.x, RN2.y, RN2.z, invM2);
+        r[5] = make_float4(R1T1.x, R1T1.y, R1T1.z, invI1);
+        r[6] = make_float4(R2T1.x, R2T1.y, R2T1.z, invI2);
+        r[7] = make_float4(R1T2.x, R1T2.y, R1T2.z, Bd);
+        r[8] = make_float4(R2T2.x, R2T2.y, R2T2.z, 0.f);
+        r[9] = make_float4(__int_as_float(ia), __int_as_float(ib), __int_as_float(w.succ_a[c]),
+                           __int_as_float(w.succ_b[c]));
     }
-    vec3 N = normalize(V3(w.c_n[c]));
-    if (equal(N, V3(0.f, 0.f, 0.f))) N = normalize(posB - posA);   // :1115-1119
-    const vec3 R1 = V3(cpa) - posA;
-    const vec3 R2 = V3(cpb) - posB;
-    vec3 T1;
-    if (N.x >= 0.57735f) T1 = V3(N.y, -N.x, 0.0f); else T1 = V3(0.0f, N.z, -N.y);
-    const vec3 T2 = cross(N, T1);                                    // T1 is NOT normalised (:1133)
-    const float depth = dot((posA + R1) - (posB + R2), N);
-    const vec3 RN1 = cross(R1, N), RN2 = cross(R2, N);
-    float JMJn = fadd(invM1, invM2);
-    JMJn = fadd(JMJn, fsub(fmul(invI1, dot(RN1, RN1)), fmul(invI2, dot(-RN2, -RN2))));
-    JMJn = fdiv(1.0f, JMJn);
+}
+
+// the velocity-dependent part; returns the successor links through sa / sb
+__device__ __forceinline__ void apply_prepared(const DeviceWorld &w, int c, int &sa, int &sb)
+{
+    const float4 *r = w.crec + (size_t)kRecQuads * c;
+    float4 q[kRecQuads];
+#pragma unroll
+    for (int k = 0; k < kRecQuads; ++k) q[k] = __ldcg(r + k);
+    const int ia = __float_as_int(q[9].x), ib = __float_as_int(q[9].y);
+    sa = __float_as_int(q[9].z);
+    sb = __float_as_int(q[9].w);
+    float4 va4 = __ldcg(&w.vel[ia]), wa4 = __ldcg(&w.angvel[ia]);
+    float4 vb4 = make_float4(0, 0, 0, 0), wb4 = make_float4(0, 0, 0, 0);
+    if (ib >= 0) { vb4 = __ldcg(&w.vel[ib]); wb4 = __ldcg(&w.angvel[ib]); }
+    // the successors' records will be wanted next: pull them towards L2 while this contact computes
+    if (sa >= 0) {
+        const char *p = (const char *)(w.crec + (size_t)kRecQuads * sa);
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(p + 128));
+    }
+    if (sb >= 0) {
+        const char *p = (const char *)(w.crec + (size_t)kRecQuads * sb);
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(p + 128));
+    }
+    const vec3 N = V3(q[0]), T1 = V3(q[1]), T2 = V3(q[2]);
+    const float JMJn = q[0].w, JMJt1 = q[1].w, JMJt2 = q[2].w;
+    const vec3 RN1 = V3(q[3]), RN2 = V3(q[4]), R1T1 = V3(q[5]), R2T1 = V3(q[6]), R1T2 = V3(q[7]), R2T2 = V3(q[8]);
+    const float invM1 = q[3].w, invM2 = q[4].w, invI1 = q[5].w, invI2 = q[6].w, Bd = q[7].w;
+    vec3 V1 = V3(va4), W1 = V3(wa4), V2 = V3(vb4), W2 = V3(wb4);   // the Floor: V = W = 0 (:1278-1289)
     const vec3 dVn = ((V1 + cross(W1, N)) - V2) - cross(W2, N);
     const float JdVn = dot(dVn, N);
-    const float Beta = 0.3f, Cr = 0.1f;
-    const float B = fadd(fmul(fdiv(-Beta, dt), depth), fmul(Cr, JdVn));
-    const vec3 R1T1 = cross(R1, T1), R2T1 = cross(R2, T1), R1T2 = cross(R1, T2), R2T2 = cross(R2, T2);
-    float JMJt1 = fadd(invM1, invM2);
-    JMJt1 = fadd(JMJt1, fsub(fmul(invI1, dot(R1T1, R1T1)), fmul(invI2, dot(-R2T1, -R2T1))));
-    JMJt1 = fdiv(1.0f, JMJt1);
-    float JMJt2 = fadd(invM1, invM2);
-    JMJt2 = fadd(JMJt2, fsub(fmul(invI1, dot(R1T2, R1T2)), fmul(invI2, dot(-R2T2, -R2T2))));
-    JMJt2 = fdiv(1.0f, JMJt2);
+    const float B = fadd(Bd, fmul(0.1f, JdVn));                        // + Cr * JdVn
     const vec3 dVt1 = ((V1 + cross(W1, T1)) - V2) - cross(W2, T1);
     const float JdVt1 = dot(dVt1, T1);
     const vec3 dVt2 = ((V1 + cross(W1, T2)) - V2) - cross(W2, T2);
@@ -233,7 +281,7 @@ __device__ __forceinline__ int atom_add_acq_rel(int *p, int v)
 // successor's in-degree; whoever performs the LAST decrement has thereby acquired both predecessors'
 // stores (RMW chain on the same counter) and either runs the successor itself or hands it over
 // through a release store to the queue slot, which the ticket holder reads with an acquire load.
-__global__ void __launch_bounds__(kFlowThreads) solve_dataflow_kernel(DeviceWorld w, float dt)
+__global__ void __launch_bounds__(kFlowThreads) solve_dataflow_kernel(DeviceWorld w, unsigned long long *trace)
 {
     const int n = w.counters->n_contacts;
     const int lane = threadIdx.x & 31;
@@ -262,11 +310,16 @@ __global__ void __launch_bounds__(kFlowThreads) solve_dataflow_kernel(DeviceWorl
             }
             const bool go = c >= 0;
             if (go) {
-                apply_constraint(w, c, dt);
-                ++processed;
+                if (trace) {   // debug: wall-clock (ns) at which each contact starts
+                    unsigned long long tns;
+                    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(tns));
+                    trace[c] = tns;
+                }
                 const int lv = __ldcg(&level[c]);
+                int sa, sb;
+                apply_prepared(w, c, sa, sb);
+                ++processed;
                 max_level = max(max_level, lv);
-                const int sa = w.succ_a[c], sb = w.succ_b[c];
                 bool ra = false, rb = false;
                 if (sa >= 0) { atomicMax(&level[sa], lv + 1); ra = atom_add_acq_rel(&w.indeg[sa], -1) == 1; }
                 if (sb >= 0) { atomicMax(&level[sb], lv + 1); rb = atom_add_acq_rel(&w.indeg[sb], -1) == 1; }
@@ -308,7 +361,7 @@ __global__ void __launch_bounds__(kFlowThreads) solve_dataflow_kernel(DeviceWorl
 // ---- v1: level-synchronous execution (kept for A/B, NANS_SOLVER=levels) -----------------------
 constexpr int kSolveThreads = 256;
 
-__global__ void __launch_bounds__(kSolveThreads) solve_levels_kernel(DeviceWorld w, float dt)
+__global__ void __launch_bounds__(kSolveThreads) solve_levels_kernel(DeviceWorld w)
 {
     cg::grid_group grid = cg::this_grid();
     const int n = w.counters->n_contacts;
@@ -327,8 +380,8 @@ __global__ void __launch_bounds__(kSolveThreads) solve_levels_kernel(DeviceWorld
         const int32_t *fr = w.frontier[cur];
         for (int i = tid; i < fcount; i += nthreads) {
             const int c = __ldcg(&fr[i]);
-            apply_constraint(w, c, dt);
-            const int sa = w.succ_a[c], sb = w.succ_b[c];
+            int sa, sb;
+            apply_prepared(w, c, sa, sb);
             if (sa >= 0 && atomicSub(&w.indeg[sa], 1) == 1)
                 w.frontier[nxt][atomicAdd(&w.counters->frontier_n[nxt], 1)] = sa;
             if (sb >= 0 && atomicSub(&w.indeg[sb], 1) == 1)
@@ -365,6 +418,8 @@ int launch_solver(World *w, float dt)
     NANS_LAUNCH_CHECK();
     schedule_kernel<<<div_up(d.nb, 256), 256, 0, s>>>(d);
     NANS_LAUNCH_CHECK();
+    contact_prep_kernel<<<grid, 256, 0, s>>>(d, dt);
+    NANS_LAUNCH_CHECK();
 
     if (mode == 1) {
         if (!w->coop_blocks_per_sm) {
@@ -372,7 +427,7 @@ int launch_solver(World *w, float dt)
             NANS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, solve_levels_kernel, kSolveThreads, 0));
             w->coop_blocks_per_sm = per_sm < 1 ? 1 : (per_sm > 2 ? 2 : per_sm);
         }
-        void *args[] = {(void *)&d, (void *)&dt};
+        void *args[] = {(void *)&d};
         NANS_CUDA(cudaLaunchCooperativeKernel((void *)solve_levels_kernel, dim3(sm_count * w->coop_blocks_per_sm),
                                               dim3(kSolveThreads), args, 0, s));
         ++g_launches;
@@ -386,7 +441,10 @@ int launch_solver(World *w, float dt)
         NANS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, solve_dataflow_kernel, kFlowThreads, 0));
         flow_blocks = sm_count * (per_sm < 1 ? 1 : (per_sm > 3 ? 3 : per_sm));
     }
-    solve_dataflow_kernel<<<flow_blocks, kFlowThreads, 0, s>>>(d, dt);
+    static int trace_on = -1;
+    if (trace_on < 0) trace_on = getenv("NANS_SOLVER_TRACE") ? 1 : 0;
+    // debug trace reuses the narrowphase output block (idle during the solve)
+    solve_dataflow_kernel<<<flow_blocks, kFlowThreads, 0, s>>>(d, trace_on ? (unsigned long long *)d.pair_out : nullptr);
     NANS_LAUNCH_CHECK();
     return NANS_OK;
 }
