@@ -98,7 +98,7 @@ static Layout carve(const nans_world_desc &desc, char *base)
     d.inc = b.take<int32_t>(2 * mc);
     d.succ_a = b.take<int32_t>(mc); d.succ_b = b.take<int32_t>(mc); d.indeg = b.take<int32_t>(mc);
     for (int k = 0; k < 3; ++k) d.frontier[k] = b.take<int32_t>(mc);
-    d.crec = b.take<float4>(10 * mc);
+    d.crec = b.take<float4>(11 * mc);
     size_t scan_n = mp + 1;
     if (5 * nb + 1 > scan_n) scan_n = 5 * nb + 1;
     if (256 * radix_blocks > scan_n) scan_n = 256 * radix_blocks;

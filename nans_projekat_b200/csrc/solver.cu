@@ -117,7 +117,7 @@ __global__ void __launch_bounds__(256) seed_kernel(DeviceWorld w)
 //   apply_prepared       what must wait for the predecessors: relative velocities, the 70-iteration
 //                        accumulation, the impulses.  One contiguous record load + four body rows.
 // The arithmetic (operations, order, roundings) is exactly that of the single function.
-constexpr int kRecQuads = 10;   // float4 per contact record
+constexpr int kRecQuads = 11;   // float4 per contact record
 
 __global__ void __launch_bounds__(256) contact_prep_kernel(DeviceWorld w, float dt)
 {
@@ -169,32 +169,46 @@ __global__ void __launch_bounds__(256) contact_prep_kernel(DeviceWorld w, float 
         r[6] = make_float4(R2T1.x, R2T1.y, R2T1.z, invI2);
         r[7] = make_float4(R1T2.x, R1T2.y, R1T2.z, Bd);
         r[8] = make_float4(R2T2.x, R2T2.y, R2T2.z, 0.f);
-        r[9] = make_float4(__int_as_float(ia), __int_as_float(ib), __int_as_float(w.succ_a[c]),
-                           __int_as_float(w.succ_b[c]));
+        const int sa = w.succ_a[c], sb = w.succ_b[c];
+        r[9] = make_float4(__int_as_float(ia), __int_as_float(ib), __int_as_float(sa), __int_as_float(sb));
+        // body rows of the successors, so that whoever runs a successor can issue its record loads and
+        // its velocity loads in ONE round trip instead of two
+        const int none = 0x7fffffff;
+        r[10] = make_float4(__int_as_float(sa >= 0 ? __float_as_int(w.c_pa[sa].w) : none),
+                            __int_as_float(sa >= 0 ? __float_as_int(w.c_pb[sa].w) : none),
+                            __int_as_float(sb >= 0 ? __float_as_int(w.c_pa[sb].w) : none),
+                            __int_as_float(sb >= 0 ? __float_as_int(w.c_pb[sb].w) : none));
     }
 }
 
-// the velocity-dependent part; returns the successor links through sa / sb
-__device__ __forceinline__ void apply_prepared(const DeviceWorld &w, int c, int &sa, int &sb)
+// the velocity-dependent part.  rows = (ia, ib) if the caller already knows the body rows (chain
+// following), else kRowsUnknown; returns the successor links and the successors' body rows.
+constexpr int kRowsUnknown = 0x7fffffff;
+struct NextRows { int sa, sb, sa_ia, sa_ib, sb_ia, sb_ib; };
+
+__device__ __forceinline__ NextRows apply_prepared(const DeviceWorld &w, int c, int known_ia, int known_ib)
 {
     const float4 *r = w.crec + (size_t)kRecQuads * c;
     float4 q[kRecQuads];
 #pragma unroll
     for (int k = 0; k < kRecQuads; ++k) q[k] = __ldcg(r + k);
-    const int ia = __float_as_int(q[9].x), ib = __float_as_int(q[9].y);
-    sa = __float_as_int(q[9].z);
-    sb = __float_as_int(q[9].w);
+    int ia = known_ia, ib = known_ib;
+    if (ia == kRowsUnknown) { ia = __float_as_int(q[9].x); ib = __float_as_int(q[9].y); }   // second round trip
     float4 va4 = __ldcg(&w.vel[ia]), wa4 = __ldcg(&w.angvel[ia]);
     float4 vb4 = make_float4(0, 0, 0, 0), wb4 = make_float4(0, 0, 0, 0);
     if (ib >= 0) { vb4 = __ldcg(&w.vel[ib]); wb4 = __ldcg(&w.angvel[ib]); }
+    NextRows nx;
+    nx.sa = __float_as_int(q[9].z); nx.sb = __float_as_int(q[9].w);
+    nx.sa_ia = __float_as_int(q[10].x); nx.sa_ib = __float_as_int(q[10].y);
+    nx.sb_ia = __float_as_int(q[10].z); nx.sb_ib = __float_as_int(q[10].w);
     // the successors' records will be wanted next: pull them towards L2 while this contact computes
-    if (sa >= 0) {
-        const char *p = (const char *)(w.crec + (size_t)kRecQuads * sa);
+    if (nx.sa >= 0) {
+        const char *p = (const char *)(w.crec + (size_t)kRecQuads * nx.sa);
         asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
         asm volatile("prefetch.global.L2 [%0];" ::"l"(p + 128));
     }
-    if (sb >= 0) {
-        const char *p = (const char *)(w.crec + (size_t)kRecQuads * sb);
+    if (nx.sb >= 0) {
+        const char *p = (const char *)(w.crec + (size_t)kRecQuads * nx.sb);
         asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
         asm volatile("prefetch.global.L2 [%0];" ::"l"(p + 128));
     }
@@ -253,10 +267,12 @@ __device__ __forceinline__ void apply_prepared(const DeviceWorld &w, int c, int 
         __stcg(&w.vel[ib], make_float4(V2.x, V2.y, V2.z, vb4.w));
         __stcg(&w.angvel[ib], make_float4(W2.x, W2.y, W2.z, wb4.w));
     }
+    return nx;
 }
 
 // ---- dataflow execution -------------------------------------------------------------------------
 constexpr int kFlowThreads = 256;
+constexpr int kMaxHops = 8;        // contacts a lane runs back to back before the warp polls again
 constexpr int kSpinCap = 1 << 22;   // polls before declaring the schedule broken (seconds of wall time)
 
 // gpu-scope acquire/release primitives (cheaper than the sequentially-consistent __threadfence())
@@ -269,6 +285,16 @@ __device__ __forceinline__ int ld_acquire(const int *p)
 __device__ __forceinline__ void st_release(int *p, int v)
 {
     asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void fence_acq_rel()
+{
+    asm volatile("fence.acq_rel.gpu;" ::: "memory");
+}
+__device__ __forceinline__ int atom_add_relaxed(int *p, int v)
+{
+    int o;
+    asm volatile("atom.relaxed.gpu.global.add.s32 %0, [%1], %2;" : "=r"(o) : "l"(p), "r"(v) : "memory");
+    return o;
 }
 __device__ __forceinline__ int atom_add_acq_rel(int *p, int v)
 {
@@ -302,6 +328,7 @@ __global__ void __launch_bounds__(kFlowThreads) solve_dataflow_kernel(DeviceWorl
         bool done = t >= n;
         bool ticket_open = !done;     // queue slot t not consumed yet
         int c = -1;                   // contact in hand (from the queue, or followed along a chain)
+        int rows_a = kRowsUnknown, rows_b = kRowsUnknown;   // its body rows when already known
         int spins = 0, processed = 0;
         while (!__all_sync(0xffffffffu, done)) {
             if (ticket_open && c < 0) {
@@ -310,33 +337,42 @@ __global__ void __launch_bounds__(kFlowThreads) solve_dataflow_kernel(DeviceWorl
             }
             const bool go = c >= 0;
             if (go) {
-                if (trace) {   // debug: wall-clock (ns) at which each contact starts
-                    unsigned long long tns;
-                    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(tns));
-                    trace[c] = tns;
+                // run the contact in hand, then keep following the chain it unlocks (bounded, so the
+                // sibling lanes get back to polling their tickets)
+                for (int hop = 0; hop < kMaxHops && c >= 0; ++hop) {
+                    if (trace) {   // debug: wall-clock (ns) at which each contact starts
+                        unsigned long long tns;
+                        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(tns));
+                        trace[c] = tns;
+                    }
+                    const int lv = __ldcg(&level[c]);
+                    const NextRows nx = apply_prepared(w, c, rows_a, rows_b);
+                    ++processed;
+                    max_level = max(max_level, lv);
+                    if (nx.sa >= 0) atomicMax(&level[nx.sa], lv + 1);
+                    if (nx.sb >= 0) atomicMax(&level[nx.sb], lv + 1);
+                    fence_acq_rel();                   // release: this contact's velocity stores
+                    const int oa = nx.sa >= 0 ? atom_add_relaxed(&w.indeg[nx.sa], -1) : 0;
+                    const int ob = nx.sb >= 0 ? atom_add_relaxed(&w.indeg[nx.sb], -1) : 0;
+                    const bool ra = oa == 1, rb = ob == 1;
+                    if (ra || rb) fence_acq_rel();     // acquire: the other predecessors' stores
+                    // a successor we completed is run by this lane straight away (no queue round
+                    // trip); if both became ready the second one goes to the queue
+                    const bool push_b = ra && rb;
+                    const unsigned am = __activemask();
+                    const unsigned pb = __ballot_sync(am, push_b);
+                    if (pb) {
+                        const int leader = __ffs(am) - 1;
+                        int slot = 0;
+                        if (lane == leader) slot = atomicAdd(tail, __popc(pb));
+                        slot = __shfl_sync(am, slot, leader) + __popc(pb & lt);
+                        if (push_b) st_release(queue + slot, nx.sb);
+                    }
+                    c = ra ? nx.sa : (rb ? nx.sb : -1);
+                    rows_a = ra ? nx.sa_ia : nx.sb_ia;
+                    rows_b = ra ? nx.sa_ib : nx.sb_ib;
                 }
-                const int lv = __ldcg(&level[c]);
-                int sa, sb;
-                apply_prepared(w, c, sa, sb);
-                ++processed;
-                max_level = max(max_level, lv);
-                bool ra = false, rb = false;
-                if (sa >= 0) { atomicMax(&level[sa], lv + 1); ra = atom_add_acq_rel(&w.indeg[sa], -1) == 1; }
-                if (sb >= 0) { atomicMax(&level[sb], lv + 1); rb = atom_add_acq_rel(&w.indeg[sb], -1) == 1; }
-                // a successor we completed is run by this lane straight away (chain following: no
-                // queue round trip); if both became ready the second one goes to the queue
-                const bool push_b = ra && rb;
-                const unsigned am = __activemask();
-                const unsigned pb = __ballot_sync(am, push_b);
-                if (pb) {
-                    const int leader = __ffs(am) - 1;
-                    int slot = 0;
-                    if (lane == leader) slot = atomicAdd(tail, __popc(pb));
-                    slot = __shfl_sync(am, slot, leader) + __popc(pb & lt);
-                    if (push_b) st_release(queue + slot, sb);
-                }
-                c = ra ? sa : (rb ? sb : -1);
-                if (c < 0 && !ticket_open) done = true;
+                if (c < 0) { rows_a = kRowsUnknown; rows_b = kRowsUnknown; if (!ticket_open) done = true; }
             }
             if (!__any_sync(0xffffffffu, go)) {
                 // nothing arrived: publish this warp's progress, then check whether everything is
@@ -380,8 +416,8 @@ __global__ void __launch_bounds__(kSolveThreads) solve_levels_kernel(DeviceWorld
         const int32_t *fr = w.frontier[cur];
         for (int i = tid; i < fcount; i += nthreads) {
             const int c = __ldcg(&fr[i]);
-            int sa, sb;
-            apply_prepared(w, c, sa, sb);
+            const NextRows nx = apply_prepared(w, c, kRowsUnknown, kRowsUnknown);
+            const int sa = nx.sa, sb = nx.sb;
             if (sa >= 0 && atomicSub(&w.indeg[sa], 1) == 1)
                 w.frontier[nxt][atomicAdd(&w.counters->frontier_n[nxt], 1)] = sa;
             if (sb >= 0 && atomicSub(&w.indeg[sb], 1) == 1)

@@ -77,7 +77,7 @@ struct DeviceWorld {
     int32_t *inc;                       // [2 * max_contacts] contact ids grouped by body
     int32_t *succ_a, *succ_b;           // [max_contacts] next contact touching body A / B (-1 none)
     int32_t *indeg;                     // [max_contacts]
-    float4 *crec;                       // [10 * max_contacts] velocity-independent part of each Constraint
+    float4 *crec;                       // [11 * max_contacts] velocity-independent part of each Constraint
     int32_t *frontier[3];               // [max_contacts] each
     // --- scan scratch
     uint32_t *scan_block;               // block sums
