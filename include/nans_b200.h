@@ -110,6 +110,19 @@ int nans_world_set_body(nans_world *w, int32_t body_row, const float pos[3], con
 int nans_world_snapshot(nans_world *w);
 int nans_world_restore(nans_world *w);
 
+/* ---- one world over several GPUs, split by contiguous body-index ranges (cube-only worlds).
+ * No reference counterpart (the reference is one process); the multi-GPU result is bit-identical to
+ * the single-GPU one.  Rows [0, n_owned) are owned, rows [n_owned, n_owned+n_ghosts) are copies of
+ * higher-rank bodies; buffers are DEVICE pointers (the exchange is NCCL, driven by the host):
+ * halo record = 160 B/body (pos, vel, angvel, 8 vertices, global id), velocity record = 32 B/body. */
+int nans_world_set_partition(nans_world *w, int32_t n_owned, int32_t n_ghosts);
+int nans_world_bounds(nans_world *w, float out_lo_hi[6]);           /* AABB of the owned bodies (synchronises) */
+int nans_slab_pack_halo(nans_world *w, const float box_lo_hi[6], int32_t gid_base, void *d_out, int32_t cap,
+                        int32_t list_offset, int32_t *count);         /* owned bodies reaching into the box, in row order */
+int nans_slab_unpack_halo(nans_world *w, const void *d_in, int32_t count, int32_t row0);
+int nans_slab_pack_ghost_vel(nans_world *w, int32_t row0, int32_t count, void *d_out);
+int nans_slab_unpack_owned_vel(nans_world *w, int32_t list_offset, int32_t count, const void *d_in);
+
 /* ---- the four stages, one entry per reference function (asynchronous on the world's stream) */
 int nans_integrate_forces(nans_world *w, float dt);     /* IntegrateForces     code/nans.cpp:975  */
 int nans_detect_collisions(nans_world *w);              /* DetectCollisions    code/nans.cpp:1352 */

@@ -321,6 +321,11 @@ __global__ void __launch_bounds__(128) pair_count_kernel(DeviceWorld w, const ui
     uint32_t cnt[5] = {0, 0, 0, 0, 0};
     uint32_t filled = 0;
     uint32_t *slots = w.pair_tmp + (size_t)t * kPairSlots;
+    if (row >= w.n_owned) {   // slab mode: a ghost's pairs belong to its owner rank
+#pragma unroll
+        for (int s = 0; s < 5; ++s) w.pair_count[(size_t)s * w.nb + row] = 0;
+        return;
+    }
     for_each_partner(w, keys, t, [&](int seg, int brow) {
         cnt[seg]++;
         if (filled < (uint32_t)kPairSlots) slots[filled] = ((uint32_t)seg << 28) | (uint32_t)brow;
@@ -341,6 +346,14 @@ __global__ void __launch_bounds__(128) pair_emit_kernel(DeviceWorld w, const uin
     if (t >= w.nb) return;
     const float4 alo = w.sbox[2 * (size_t)t], ahi = w.sbox[2 * (size_t)t + 1];
     const int row = __float_as_int(alo.w);
+    if (row >= w.n_owned) {
+        if (t == 0) {
+            const uint32_t total = w.pair_count[(size_t)5 * w.nb];
+            w.counters->n_pairs = (int32_t)min(total, (uint32_t)w.max_pairs);
+            if (total > (uint32_t)w.max_pairs) atomicOr(&w.counters->overflow, OVF_PAIRS);
+        }
+        return;
+    }
     uint32_t off[5], fill[5] = {0, 0, 0, 0, 0};
     // scanned table: offsets; the entry after (s,row) is the next run's start, i.e. this run's end
 #pragma unroll
@@ -384,6 +397,16 @@ __global__ void __launch_bounds__(128) pair_emit_kernel(DeviceWorld w, const uin
         w.counters->n_pairs = (int32_t)min(total, cap);
         if (total > cap) atomicOr(&w.counters->overflow, OVF_PAIRS);
     }
+}
+
+// AABBs only (slab mode needs them before the halo exchange)
+int launch_aabb_only(World *w)
+{
+    DeviceWorld &d = w->d;
+    if (d.nb == 0) return NANS_OK;
+    aabb_kernel<<<div_up(max(d.nb, d.n_statics), 256), 256, 0, w->stream>>>(d);
+    NANS_LAUNCH_CHECK();
+    return NANS_OK;
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -230,24 +230,42 @@ __device__ __forceinline__ NextRows apply_prepared(const DeviceWorld &w, int c, 
     const float lambdaT1 = fmul(-JdVt1, JMJt1);
     const float lambdaT2 = fmul(-JdVt2, JMJt2);
     const double kFric = 1.4142135623730951 * (double)0.1f;   // sqrt(2) * Cf, evaluated in fp64 (:1197)
+    // Three dependency chains per iteration: the normal sum, and the two tangent sums clamped by a
+    // bound derived (in fp64) from the normal sum of the SAME iteration.  This runs on a warp that is
+    // usually alone on its scheduler, so the chains are software-pipelined by hand: the normal chain
+    // (and the fp64 bound) runs kBlk iterations ahead of the tangent chains.
     float DLN = 0.f, sumN = 0.f, DLT1 = 0.f, sumT1 = 0.f, DLT2 = 0.f, sumT2 = 0.f;
-#pragma unroll 2
-    for (int iter = 0; iter < 70; ++iter) {
+    constexpr int kBlk = 10;
+    float bound[kBlk], bound_next[kBlk];
+    auto normal_step = [&]() -> float {
         const float oldN = sumN;
         sumN = fadd(sumN, lambdaN);
         if (sumN < 0) sumN = 0.0f;
         DLN = fsub(sumN, oldN);
-        const float maxT = __double2float_rn(__dmul_rn(kFric, (double)sumN));
-        const float oldT1 = sumT1;
-        sumT1 = fadd(sumT1, lambdaT1);
-        if (sumT1 < -maxT) sumT1 = -maxT;
-        if (sumT1 > maxT) sumT1 = maxT;
-        DLT1 = fsub(sumT1, oldT1);
-        const float oldT2 = sumT2;
-        sumT2 = fadd(sumT2, lambdaT2);
-        if (sumT2 < -maxT) sumT2 = -maxT;
-        if (sumT2 > maxT) sumT2 = maxT;
-        DLT2 = fsub(sumT2, oldT2);
+        return __double2float_rn(__dmul_rn(kFric, (double)sumN));
+    };
+#pragma unroll
+    for (int j = 0; j < kBlk; ++j) bound_next[j] = normal_step();
+#pragma unroll 1
+    for (int blk = 0; blk < 70 / kBlk; ++blk) {
+#pragma unroll
+        for (int j = 0; j < kBlk; ++j) bound[j] = bound_next[j];
+        const bool more = blk + 1 < 70 / kBlk;
+#pragma unroll
+        for (int j = 0; j < kBlk; ++j) {
+            if (more) bound_next[j] = normal_step();
+            const float maxT = bound[j];
+            const float oldT1 = sumT1;
+            sumT1 = fadd(sumT1, lambdaT1);
+            if (sumT1 < -maxT) sumT1 = -maxT;
+            if (sumT1 > maxT) sumT1 = maxT;
+            DLT1 = fsub(sumT1, oldT1);
+            const float oldT2 = sumT2;
+            sumT2 = fadd(sumT2, lambdaT2);
+            if (sumT2 < -maxT) sumT2 = -maxT;
+            if (sumT2 > maxT) sumT2 = maxT;
+            DLT2 = fsub(sumT2, oldT2);
+        }
     }
     const vec3 LI = N * DLN, LIT1 = T1 * DLT1, LIT2 = T2 * DLT2;
     const vec3 AI1 = RN1 * DLN, AI2 = RN2 * DLN;
@@ -307,7 +325,8 @@ __device__ __forceinline__ int atom_add_acq_rel(int *p, int v)
 // successor's in-degree; whoever performs the LAST decrement has thereby acquired both predecessors'
 // stores (RMW chain on the same counter) and either runs the successor itself or hands it over
 // through a release store to the queue slot, which the ticket holder reads with an acquire load.
-__global__ void __launch_bounds__(kFlowThreads) solve_dataflow_kernel(DeviceWorld w, unsigned long long *trace)
+__global__ void __launch_bounds__(kFlowThreads) solve_dataflow_kernel(DeviceWorld w, unsigned long long *trace,
+                                                                      int max_hops, int atomic_mode, int sleep_ns)
 {
     const int n = w.counters->n_contacts;
     const int lane = threadIdx.x & 31;
@@ -339,7 +358,7 @@ __global__ void __launch_bounds__(kFlowThreads) solve_dataflow_kernel(DeviceWorl
             if (go) {
                 // run the contact in hand, then keep following the chain it unlocks (bounded, so the
                 // sibling lanes get back to polling their tickets)
-                for (int hop = 0; hop < kMaxHops && c >= 0; ++hop) {
+                for (int hop = 0; hop < max_hops && c >= 0; ++hop) {
                     if (trace) {   // debug: wall-clock (ns) at which each contact starts
                         unsigned long long tns;
                         asm volatile("mov.u64 %0, %globaltimer;" : "=l"(tns));
@@ -351,11 +370,17 @@ __global__ void __launch_bounds__(kFlowThreads) solve_dataflow_kernel(DeviceWorl
                     max_level = max(max_level, lv);
                     if (nx.sa >= 0) atomicMax(&level[nx.sa], lv + 1);
                     if (nx.sb >= 0) atomicMax(&level[nx.sb], lv + 1);
-                    fence_acq_rel();                   // release: this contact's velocity stores
-                    const int oa = nx.sa >= 0 ? atom_add_relaxed(&w.indeg[nx.sa], -1) : 0;
-                    const int ob = nx.sb >= 0 ? atom_add_relaxed(&w.indeg[nx.sb], -1) : 0;
+                    int oa = 0, ob = 0;
+                    if (atomic_mode == 0) {            // one release fence, two relaxed RMWs in flight together
+                        fence_acq_rel();               // release: this contact's velocity stores
+                        if (nx.sa >= 0) oa = atom_add_relaxed(&w.indeg[nx.sa], -1);
+                        if (nx.sb >= 0) ob = atom_add_relaxed(&w.indeg[nx.sb], -1);
+                        if (oa == 1 || ob == 1) fence_acq_rel();   // acquire: the other predecessors' stores
+                    } else {                           // acq_rel RMWs
+                        if (nx.sa >= 0) oa = atom_add_acq_rel(&w.indeg[nx.sa], -1);
+                        if (nx.sb >= 0) ob = atom_add_acq_rel(&w.indeg[nx.sb], -1);
+                    }
                     const bool ra = oa == 1, rb = ob == 1;
-                    if (ra || rb) fence_acq_rel();     // acquire: the other predecessors' stores
                     // a successor we completed is run by this lane straight away (no queue round
                     // trip); if both became ready the second one goes to the queue
                     const bool push_b = ra && rb;
@@ -384,7 +409,7 @@ __global__ void __launch_bounds__(kFlowThreads) solve_dataflow_kernel(DeviceWorl
                 }
                 if (*(volatile int *)finished >= n) { done = true; continue; }
                 if (++spins > kSpinCap || *abort_flag) { *abort_flag = 1; return; }
-                __nanosleep(32);
+                if (sleep_ns) __nanosleep(sleep_ns);
             }
         }
         processed = __reduce_add_sync(0xffffffffu, processed);
@@ -475,12 +500,23 @@ int launch_solver(World *w, float dt)
     if (!flow_blocks) {
         int per_sm = 0;
         NANS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, solve_dataflow_kernel, kFlowThreads, 0));
-        flow_blocks = sm_count * (per_sm < 1 ? 1 : (per_sm > 3 ? 3 : per_sm));
+        (void)per_sm;
+        flow_blocks = sm_count;   // one CTA per SM: more polling warps only add interference (profiles/r1 sweep)
     }
     static int trace_on = -1;
     if (trace_on < 0) trace_on = getenv("NANS_SOLVER_TRACE") ? 1 : 0;
     // debug trace reuses the narrowphase output block (idle during the solve)
-    solve_dataflow_kernel<<<flow_blocks, kFlowThreads, 0, s>>>(d, trace_on ? (unsigned long long *)d.pair_out : nullptr);
+    static int hops = -1, amode = 0, sleep_ns = 32;
+    if (hops < 0) {   // tuning knobs (defaults chosen from the sweeps in profiles/)
+        const char *e;
+        hops = (e = getenv("NANS_FLOW_HOPS")) ? atoi(e) : 1;
+        amode = (e = getenv("NANS_FLOW_ATOMICS")) ? atoi(e) : 0;
+        sleep_ns = (e = getenv("NANS_FLOW_SLEEP")) ? atoi(e) : 32;
+        if ((e = getenv("NANS_FLOW_BLOCKS"))) flow_blocks = sm_count * atoi(e);
+        if (hops < 1) hops = 1;
+    }
+    solve_dataflow_kernel<<<flow_blocks, kFlowThreads, 0, s>>>(d, trace_on ? (unsigned long long *)d.pair_out : nullptr,
+                                                               hops, amode, sleep_ns);
     NANS_LAUNCH_CHECK();
     return NANS_OK;
 }

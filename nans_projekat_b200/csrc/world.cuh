@@ -35,6 +35,7 @@ struct Counters {
 // All pointers are DEVICE pointers into the arena.
 struct DeviceWorld {
     int32_t n_cubes, n_spheres, n_statics, nb;
+    int32_t n_owned;   // slab mode: rows >= n_owned are ghosts of higher ranks (== nb otherwise)
     int32_t max_pairs, max_contacts;
     // --- bodies (SoA, float4): rows cubes then spheres
     float4 *pos;      // xyz = Position,  w = Mass
@@ -46,6 +47,7 @@ struct DeviceWorld {
     float4 *scale;    // xyz = model scale, w = Radius (spheres, else 0)
     float4 *verts;    // [n_cubes][6] float4 = 8 packed vec3 (96 B per cube, reference vertex order)
     int32_t *world_id; // [nb] or nullptr
+    int32_t *gid;      // [nb] global body id (slab mode)
     // --- statics
     float4 *st_pos;    // xyz = Position, w = 1/Mass
     float4 *st_ang;    // xyz = Angles,   w = 1/MOI
@@ -126,6 +128,13 @@ int launch_broadphase(World *w);
 int launch_narrowphase(World *w);
 int launch_contacts(World *w);
 int launch_solver(World *w, float dt);
+int launch_aabb_only(World *w);
+int slab_bounds(World *w, float *scratch, float *out6_dev);
+int slab_pack_halo(World *w, const float box[6], int gid_base, float4 *out, int32_t *sent_rows, int cap,
+                   int32_t *count_dev);
+int slab_unpack_halo(World *w, const float4 *in, int count, int row0, int32_t *gid);
+int slab_pack_ghost_vel(World *w, int row0, int count, float4 *out);
+int slab_unpack_owned_vel(World *w, const int32_t *rows, int count, const float4 *in);
 int exclusive_scan_u32(const uint32_t *in, uint32_t *out, int n, uint32_t *block_scratch, cudaStream_t s);
 int exclusive_scan_u32_dn(const uint32_t *in, uint32_t *out, int cap_n, const int32_t *d_n, int extra,
                           uint32_t *block_scratch, cudaStream_t s);
