@@ -5,6 +5,10 @@
 // 216 B in + 48 B out per pair against ~1-5 kflop of unfused fp32.
 #include "narrowphase.cuh"
 
+#ifndef NANS_NP_MINBLOCKS
+#define NANS_NP_MINBLOCKS 5   // 96 registers/thread: best of the sweep in profiles/ (4: 128 regs, 6: 80 regs + spills)
+#endif
+
 namespace nans {
 
 __device__ __forceinline__ void load_box(int side, const float4 *__restrict__ v6)
@@ -27,7 +31,7 @@ __device__ __forceinline__ NpResult dispatch(bool a_sphere, bool b_sphere, NpSha
     return check_collision<true, true>(S, E, ovf, max_faces);
 }
 
-__global__ void __launch_bounds__(kNpThreads, 5) narrowphase_world_kernel(DeviceWorld w, int *work_counter)
+__global__ void __launch_bounds__(kNpThreads, NANS_NP_MINBLOCKS) narrowphase_world_kernel(DeviceWorld w, int *work_counter)
 {
     EpaArena E;
     const int lane = threadIdx.x & 31;
@@ -79,7 +83,7 @@ __global__ void __launch_bounds__(kNpThreads, 5) narrowphase_world_kernel(Device
 }
 
 // stand-alone pairs (config C3): type per pair, shapes given explicitly
-__global__ void __launch_bounds__(kNpThreads, 5) narrowphase_batch_kernel(
+__global__ void __launch_bounds__(kNpThreads, NANS_NP_MINBLOCKS) narrowphase_batch_kernel(
     int n, const int32_t *__restrict__ type, const float4 *__restrict__ posrad_a,
     const float4 *__restrict__ verts_a, const float4 *__restrict__ posrad_b,
     const float4 *__restrict__ verts_b, int32_t *__restrict__ hit, int32_t *__restrict__ gjk,

@@ -24,7 +24,10 @@ namespace nans {
 
 enum { kNoIntersection = 0, kFoundIntersection = 1, kStillEvolving = 2 };  // evolve_result, code/nans.h:89-94
 
-constexpr int kNpThreads = 128;
+#ifndef NANS_NP_THREADS
+#define NANS_NP_THREADS 128
+#endif
+constexpr int kNpThreads = NANS_NP_THREADS;
 constexpr int kNoVertex = 8;   // box support when every compare failed (NaN direction): vec3(0)
 
 // Both shapes' box vertices, transposed: g_np_verts[(24*side + 3*k + r) * kNpThreads + tid].
