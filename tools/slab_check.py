@@ -10,7 +10,7 @@ import numpy as np
 import torch
 import torch.distributed as dist
 from nans_projekat_b200 import scenes
-from nans_projekat_b200.slab import SlabWorld
+from nans_projekat_b200.slab import SlabWorld, CudaEngine
 from nans_projekat_b200.world import World
 
 side = int(sys.argv[1]) if len(sys.argv) > 1 else 48
@@ -22,8 +22,9 @@ torch.cuda.set_device(local)
 dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 scene = scenes.cube_pile(n_side=side, layers=layers, seed=7)
 scene.pos[:, 1] -= 0.0
-sw = SlabWorld(scene, rank, size, local)
-sw.rebuild_vertices()
+eng = CudaEngine(scene, rank, size, local)
+eng.rebuild_vertices()
+sw = SlabWorld(eng, rank, size, dist)
 ref = None
 if rank == 0:
     ref = World(scene, device=local)
@@ -36,10 +37,10 @@ for k in range(settle + steps):
         ref.step(dt)
     if k < settle and k % 10:
         continue
-    owned = sw.download_owned()
-    cg = sw.contacts_global()
+    owned = eng.download_owned()
+    cg = eng.contacts_global()
     parts = [None] * size
-    dist.all_gather_object(parts, (sw.lo, sw.hi, {f: getattr(owned, f) for f in ("pos", "vel", "ang", "angvel", "verts")}, cg,
+    dist.all_gather_object(parts, (eng.lo, eng.hi, {f: getattr(owned, f) for f in ("pos", "vel", "ang", "angvel", "verts")}, cg,
                                    sw.n_ghosts, sw.halo_bytes))
     if rank == 0:
         full = ref.download()
