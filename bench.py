@@ -45,6 +45,11 @@ def parse():
     ap.add_argument("--cpu-bodies", type=int, default=2048, help="size of the CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--mode", default="worlds", choices=["worlds", "slab"],
+                    help="N>1: 'worlds' = one independent world per GPU (weak scaling, no collective; default); "
+                         "'slab' = ONE world split by body-index slabs with NCCL halo exchange (strong scaling)")
+    ap.add_argument("--c3", type=int, default=0, metavar="PAIRS",
+                    help="also run the GJK+EPA microbench (config C3) on this many random pairs (e.g. 16777216)")
     return ap.parse_args()
 
 
@@ -206,11 +211,115 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def run_c3(n_pairs, device, reps=5):
+    """Config C3: GJK+EPA pairs/s on random cube/sphere pairs (strata CC:CS:SS = 8:7:1), device-resident
+    inputs, CUDA events; flags of a 64 Ki subsample are checked bit-exact against the CPU oracle."""
+    import ctypes as C
+    import torch
+    from nans_projekat_b200 import scenes, _lib
+    chunk = 1 << 20
+    parts = [scenes.narrowphase_pairs(min(chunk, n_pairs - o), seed=1234 + o) for o in range(0, n_pairs, chunk)]
+    cat = lambda k: np.concatenate([p[k] for p in parts])
+    t = cat("type")
+    posrad = lambda pk, rk: np.concatenate([cat(pk), cat(rk)[:, None]], 1).astype(np.float32)
+    dev = torch.device("cuda", device)
+    d = {k: torch.from_numpy(np.ascontiguousarray(v)).to(dev) for k, v in
+         dict(type=t, pa=posrad("pos_a", "rad_a"), va=cat("verts_a"), pb=posrad("pos_b", "rad_b"), vb=cat("verts_b")).items()}
+    hit = torch.empty(n_pairs, dtype=torch.int32, device=dev)
+    out = torch.empty((n_pairs, 12), dtype=torch.float32, device=dev)
+    L = _lib.lib()
+    stream = torch.cuda.current_stream(dev)
+    call = lambda: _lib.check(L.nans_check_collision_device(n_pairs, d["type"].data_ptr(), d["pa"].data_ptr(),
+                                                             d["va"].data_ptr(), d["pb"].data_ptr(), d["vb"].data_ptr(),
+                                                             hit.data_ptr(), out.data_ptr(), stream.cuda_stream))
+    for _ in range(3):
+        call()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record(stream)
+    for _ in range(reps):
+        call()
+    e1.record(stream)
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    res = {"pairs": n_pairs, "ms": ms, "pairs_per_s": n_pairs / (ms * 1e-3), "hit_rate": float(hit.float().mean().item()),
+           "strata": "CC:CS:SS = 8:7:1, rotated unit cubes, r in [0.1,0.5], seed 1234 (+ chunk offset)",
+           "alg_bytes_per_pair": 264}
+    try:
+        from oracle import oracle as O
+        m = min(1 << 16, n_pairs)
+        idx = np.linspace(0, n_pairs - 1, m).astype(np.int64)
+        o = O.check_collision_batch(t[idx], cat("pos_a")[idx], cat("verts_a")[idx], cat("rad_a")[idx],
+                                    cat("pos_b")[idx], cat("verts_b")[idx], cat("rad_b")[idx])
+        res["flags_bit_exact_vs_oracle"] = bool(np.array_equal(hit.cpu().numpy()[idx], o["hit"]))
+        res["checked"] = int(m)
+    except Exception as ex:  # the oracle is optional here
+        res["flags_bit_exact_vs_oracle"] = f"not checked ({ex})"
+    return res
+
+
+def main_slab(args):
+    """ONE 1M-cube world over N GPUs (config C5): slab decomposition + NCCL halo exchange, exact."""
+    import torch
+    import torch.distributed as dist
+    from nans_projekat_b200.slab import SlabWorld, CudaEngine
+    from nans_projekat_b200.world import kernel_launches
+    rank, local, size = int(os.environ["RANK"]), int(os.environ["LOCAL_RANK"]), int(os.environ["WORLD_SIZE"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    scene, layers = build_pile(args.bodies, args.side, seed=7)
+    eng = CudaEngine(scene, rank, size, local)
+    eng.rebuild_vertices()
+    sw = SlabWorld(eng, rank, size, dist)
+    warmup = max(args.warmup, 3)
+    for _ in range(args.settle):
+        sw.step(DT)
+    eng.set_ghosts(0)
+    eng.world.snapshot()
+
+    def run_steps(n):
+        for k in range(n):
+            if k % args.window == 0:
+                eng.world.restore()
+            sw.step(DT)
+    run_steps(warmup)
+    torch.cuda.synchronize(); dist.barrier()
+    launches0 = kernel_launches()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(eng.stream)
+    run_steps(args.steps)
+    e1.record(eng.stream)
+    torch.cuda.synchronize(); dist.barrier()
+    t = torch.tensor([e0.elapsed_time(e1)], device="cuda", dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    st = eng.world.stats()
+    info = [None] * size
+    dist.all_gather_object(info, {"owned": eng.n_owned, "ghosts": sw.n_ghosts, "halo_bytes": sw.halo_bytes,
+                                  "contacts": st["n_contacts"], "pairs": st["n_pairs"]})
+    if rank == 0:
+        ms = float(t.item())
+        line = {"metric": "body-steps/s", "value": scene.n_cubes * args.steps / (ms * 1e-3), "unit": "body-steps/s",
+                "n_gpus": size, "steps": args.steps, "warmup": warmup, "ms_per_step": ms / args.steps,
+                "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": "cube_pile_1M_one_world" if scene.n_cubes == 1_000_000 else f"cube_pile_{scene.n_cubes}_one_world",
+                           "bodies": scene.n_cubes, "footprint": f"{args.side}x{args.side}", "layers": layers,
+                           "parallelism": f"{size} slabs by body index (layers), NCCL halo exchange, exact-order solve "
+                                          f"pipelined over ranks", "settle_steps": args.settle, "window": args.window,
+                           "l2": "inputs larger than L2", "per_rank": info},
+                "gpu_launches": int(kernel_launches() - launches0), "roofline": None, "cpu_baseline": None, "e2e": None}
+        print(json.dumps(line), flush=True)
+    eng.close()
+    dist.destroy_process_group()
+
+
 # --------------------------------------------------------------------------------------- our arm
 def main():
     args = parse()
     if args.impl == "reference":
         run_reference(args)
+        return
+    if args.mode == "slab" and int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        main_slab(args)
         return
     import torch
     import torch.distributed as dist
@@ -351,6 +460,7 @@ def main():
         state.st_verts[...] = sv.st_verts
         cpu = cpu_port_baseline(state, args.cpu_bodies)
 
+    c3 = run_c3(args.c3, local) if (args.c3 and rank == 0) else None
     if rank == 0:
         line = {"metric": "body-steps/s", "value": value, "unit": "body-steps/s", "n_gpus": world_size,
                 "steps": args.steps, "warmup": warmup, "ms_per_step": ms_max / args.steps,
@@ -370,6 +480,8 @@ def main():
                 "clocks": clocks,
                 "stages_ms": stage, "narrowphase_pairs_per_s": pairs_acc / (stage["narrowphase"] * 1e-3),
                 "host": {"nproc": os.cpu_count()}}
+        if c3:
+            line["c3_narrowphase"] = c3
         print(json.dumps(line), flush=True)
     world.close()
     if world_size > 1:

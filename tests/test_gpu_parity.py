@@ -325,3 +325,59 @@ def test_capacity_overflow_is_reported(nb200, oracle):
         gw.stats()
     assert gw.stats(strict=False)["overflow"] & 1
     gw.close()
+
+
+def test_batched_independent_worlds(nb200, oracle):
+    """Config C4 at reduced size: many independent worlds in one device world (world_id): bodies of
+    different worlds never pair up, and every world evolves exactly as if stepped alone by the oracle."""
+    from nans_projekat_b200 import scenes
+    n_worlds, cpw, spw = 12, 10, 4
+    s = scenes.batched_worlds(n_worlds=n_worlds, cubes_per=cpw, spheres_per=spw, seed=3)
+    s.pos[:, 1] -= 0.25
+    nc = s.n_cubes
+    whole = world_from_scene(oracle, s); whole.rebuild_vertices()
+    s.verts[:] = whole.verts; s.st_verts[:] = whole.st_verts
+    # one oracle world per independent world
+    subs = []
+    for wd in range(n_worlds):
+        rows = np.nonzero(s.world_id == wd)[0]
+        cu, sp = rows[rows < nc], rows[rows >= nc]
+        o = oracle.World(len(cu), len(sp), 1)
+        r = np.concatenate([cu, sp])
+        for f in ("pos", "vel", "force", "ang", "angvel", "torque", "scale"):
+            getattr(o, f)[:] = getattr(s, f)[r]
+        o.mass[:], o.moi[:], o.radius[:] = s.mass[r], s.moi[r], s.radius[r]
+        o.verts[:] = s.verts[cu]
+        for f in ("st_pos", "st_ang", "st_scale", "st_mass", "st_moi", "st_verts"):
+            getattr(o, f)[...] = getattr(s, f)
+        subs.append((r, cu, sp, o))
+    gw = nb200.World(s)
+    total = 0
+    for step in range(40):
+        gw.step(DT)
+        gc = gw.contacts()
+        d = gw.download()
+        assert gw.stats()["overflow"] == 0
+        for wd, (r, cu, sp, o) in enumerate(subs):
+            oc = o.step(DT, prefilter=False)
+            for f in ("pos", "vel", "ang", "angvel"):
+                assert_bit_equal(getattr(d, f)[r], getattr(o, f), f"step {step} world {wd} {f}")
+            assert_bit_equal(d.verts[cu], o.verts, f"step {step} world {wd} verts")
+            # this world's contacts out of the global list, re-indexed locally
+            cube_local = {int(g): i for i, g in enumerate(cu)}
+            sph_local = {int(g - nc): i for i, g in enumerate(sp)}
+            mine = []
+            for c in gc:
+                t, a, b = int(c["type"]), int(c["a"]), int(c["b"])
+                a_sph = t in (3, 4)
+                if (a_sph and a in sph_local) or (not a_sph and a in cube_local):
+                    cc = c.copy()
+                    cc["a"] = sph_local[a] if a_sph else cube_local[a]
+                    if t in (0,): cc["b"] = cube_local[b]
+                    elif t in (1, 3): cc["b"] = sph_local[b]
+                    mine.append(cc)
+            mine = np.array(mine, dtype=gc.dtype) if mine else np.zeros(0, gc.dtype)
+            assert mine.tobytes() == oc.tobytes(), f"step {step} world {wd}: contacts {len(mine)} vs {len(oc)}"
+            total += len(oc)
+    assert total > 1000
+    gw.close()
