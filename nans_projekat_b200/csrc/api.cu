@@ -426,7 +426,8 @@ static int snapshot_copy(WorldImpl *w, bool restore)
     DeviceWorld &d = w->d;
     NANS_CUDA(cudaSetDevice(w->device));
     float4 *rows[6] = {d.pos, d.vel, d.angvel, d.ang, d.force, d.torque};
-    const size_t nb = (size_t)d.nb, nc = (size_t)d.n_cubes;
+    // fixed layout (capacity strides): slab mode varies nb / n_cubes between snapshot and restore
+    const size_t nb = (size_t)w->cap_nb, nc = (size_t)(d.n_spheres ? d.n_cubes : w->cap_nb);
     for (int k = 0; k < 6 && nb; ++k) {
         float4 *snap = w->snap + k * nb;
         NANS_CUDA(cudaMemcpyAsync(restore ? rows[k] : snap, restore ? snap : rows[k], sizeof(float4) * nb,

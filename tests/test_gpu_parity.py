@@ -381,3 +381,42 @@ def test_batched_independent_worlds(nb200, oracle):
             total += len(oc)
     assert total > 1000
     gw.close()
+
+
+def test_c2_full_size_drop_scene(nb200, oracle):
+    """Config C2 at FULL size: 10 000 cubes dropped into the static box (floor + 4 wall slabs).
+    The GPU free-runs to a contact-rich state; from that identical state GPU and oracle are stepped
+    side by side (re-seeded each step): contact lists and body state bit-identical.  Plus size-independent
+    properties over the whole run: finite state, contact list strictly ordered, no capacity overflow."""
+    from nans_projekat_b200 import scenes
+    s = scenes.cube_drop(n=10000)
+    w = world_from_scene(oracle, s)
+    w.rebuild_vertices()
+    gw = nb200.World(scene_from_oracle_world(w))
+    max_contacts = 0
+    for step in range(150):
+        gw.step(DT)
+        if step % 25 == 24:
+            st = gw.stats()
+            assert st["overflow"] == 0
+            c = gw.contacts()
+            key = c["type"].astype(np.int64) * 0  # order: CC, CF, SF, CS, SS then (a, b)
+            seg = np.array([0, 3, 1, 4, 2])[c["type"]]
+            k = (seg.astype(np.int64) << 50) | (c["a"].astype(np.int64) << 25) | c["b"].astype(np.int64)
+            assert (np.diff(k) > 0).all(), "contact list must be strictly increasing in reference order"
+            max_contacts = max(max_contacts, len(c))
+    d = gw.download()
+    assert all(np.isfinite(getattr(d, f)).all() for f in ("pos", "vel", "ang", "angvel", "verts"))
+    assert max_contacts > 5000, "the drop never developed a contact-rich state"
+    for f in STATE:
+        getattr(w, f)[...] = getattr(d, f)
+    for step in range(4):
+        gw.upload(w, fields=STATE)
+        gw.step(DT)
+        oc = w.step(DT, prefilter=True)
+        gc = gw.contacts()
+        assert gc.tobytes() == oc.tobytes(), f"step {step}: contact list {len(gc)} vs {len(oc)}"
+        d = gw.download()
+        for f in ("pos", "vel", "ang", "angvel", "verts"):
+            assert_bit_equal(getattr(d, f), getattr(w, f), f"step {step} {f}")
+    gw.close()
