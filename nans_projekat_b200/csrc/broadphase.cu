@@ -282,23 +282,21 @@ __device__ __forceinline__ void for_each_partner(const DeviceWorld &w, const uin
     const uint32_t key = keys[t];
     const int cx = (int)compact_bits10(key >> 2), cy = (int)compact_bits10(key >> 1), cz = (int)compact_bits10(key);
     // the 27 neighbour keys are combinations of 3 x 3 pre-expanded coordinates (9 bit expansions, not 81)
-    uint32_t ex[3], ey[3], ez[3];
-#pragma unroll
-    for (int d = 0; d < 3; ++d) {
-        ex[d] = expand_bits10((uint32_t)(cx + d - 1)) << 2;
-        ey[d] = expand_bits10((uint32_t)(cy + d - 1)) << 1;
-        ez[d] = expand_bits10((uint32_t)(cz + d - 1));
-    }
-#pragma unroll
+    const uint32_t ex0 = expand_bits10((uint32_t)(cx - 1)) << 2, ex1 = expand_bits10((uint32_t)cx) << 2,
+                   ex2 = expand_bits10((uint32_t)(cx + 1)) << 2;
+    const uint32_t ey0 = expand_bits10((uint32_t)(cy - 1)) << 1, ey1 = expand_bits10((uint32_t)cy) << 1,
+                   ey2 = expand_bits10((uint32_t)(cy + 1)) << 1;
+    const uint32_t ez0 = expand_bits10((uint32_t)(cz - 1)), ez1 = expand_bits10((uint32_t)cz),
+                   ez2 = expand_bits10((uint32_t)(cz + 1));
     for (int dz = -1; dz <= 1; ++dz)
-#pragma unroll
         for (int dy = -1; dy <= 1; ++dy)
-#pragma unroll
             for (int dx = -1; dx <= 1; ++dx) {
                 const int nx = cx + dx, ny = cy + dy, nz = cz + dz;
                 if ((unsigned)nx > 1023u || (unsigned)ny > 1023u || (unsigned)nz > 1023u) continue;
+                const uint32_t nkey = (dx < 0 ? ex0 : dx == 0 ? ex1 : ex2) | (dy < 0 ? ey0 : dy == 0 ? ey1 : ey2) |
+                                      (dz < 0 ? ez0 : dz == 0 ? ez1 : ez2);
                 uint32_t s, e;
-                if (!cell_lookup(w, ex[dx + 1] | ey[dy + 1] | ez[dz + 1], s, e)) continue;
+                if (!cell_lookup(w, nkey, s, e)) continue;
                 for (uint32_t u = s; u < e; ++u) {
                     const float4 blo = __ldg(&w.sbox[2 * (size_t)u]), bhi = __ldg(&w.sbox[2 * (size_t)u + 1]);
                     const int brow = __float_as_int(blo.w);
