@@ -707,7 +707,7 @@ int nans_debug_solver_trace(nans_world *h, uint64_t *times, int32_t *levels, int
     WorldImpl *w = impl(h);
     NANS_CUDA(cudaSetDevice(w->device));
     NANS_CUDA(cudaStreamSynchronize(w->stream));
-    if (times) NANS_CUDA(cudaMemcpy(times, w->d.pair_out, sizeof(uint64_t) * cap, cudaMemcpyDeviceToHost));
+    if (times) NANS_CUDA(cudaMemcpy(times, w->d.pair_out, sizeof(uint64_t) * 4 * cap, cudaMemcpyDeviceToHost));   // 4 slots per contact
     if (levels) NANS_CUDA(cudaMemcpy(levels, w->d.frontier[1], sizeof(int32_t) * cap, cudaMemcpyDeviceToHost));
     return NANS_OK;
 }

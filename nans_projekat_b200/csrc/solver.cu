@@ -359,13 +359,20 @@ __global__ void __launch_bounds__(kFlowThreads) solve_dataflow_kernel(DeviceWorl
                 // run the contact in hand, then keep following the chain it unlocks (bounded, so the
                 // sibling lanes get back to polling their tickets)
                 for (int hop = 0; hop < max_hops && c >= 0; ++hop) {
-                    if (trace) {   // debug: wall-clock (ns) at which each contact starts
+                    const int c_now = c;
+                    if (trace) {   // debug: wall-clock (ns) at which each contact starts; 4 slots per contact
                         unsigned long long tns;
                         asm volatile("mov.u64 %0, %globaltimer;" : "=l"(tns));
-                        trace[c] = tns;
+                        trace[4 * (size_t)c] = tns;
+                        trace[4 * (size_t)c + 3] = (rows_a == kRowsUnknown) ? 0ull : 1ull;   // 0 = from the queue, 1 = chain
                     }
                     const int lv = __ldcg(&level[c]);
                     const NextRows nx = apply_prepared(w, c, rows_a, rows_b);
+                    if (trace) {
+                        unsigned long long tns;
+                        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(tns));
+                        trace[4 * (size_t)c_now + 1] = tns;
+                    }
                     ++processed;
                     max_level = max(max_level, lv);
                     if (nx.sa >= 0) atomicMax(&level[nx.sa], lv + 1);
@@ -381,6 +388,11 @@ __global__ void __launch_bounds__(kFlowThreads) solve_dataflow_kernel(DeviceWorl
                         if (nx.sb >= 0) ob = atom_add_acq_rel(&w.indeg[nx.sb], -1);
                     }
                     const bool ra = oa == 1, rb = ob == 1;
+                    if (trace) {
+                        unsigned long long tns;
+                        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(tns));
+                        trace[4 * (size_t)c_now + 2] = tns;
+                    }
                     // a successor we completed is run by this lane straight away (no queue round
                     // trip); if both became ready the second one goes to the queue
                     const bool push_b = ra && rb;

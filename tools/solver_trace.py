@@ -13,13 +13,18 @@ w = World(scenes.cube_pile(n_side=side, layers=layers, n=bodies, seed=7)); w.reb
 dt = np.float32(1 / 60.)
 for _ in range(settle): w.step(dt)
 ms = w.step_profiled(dt); st = w.stats(); n = st["n_contacts"]
-t = np.zeros(n, np.uint64); lv = np.zeros(n, np.int32)
-_lib.check(_lib.lib().nans_debug_solver_trace(w._h, t.ctypes.data, lv.ctypes.data, n))
-t = (t - t.min()).astype(np.float64) / 1e3
+t4 = np.zeros((n, 4), np.uint64); lv = np.zeros(n, np.int32)
+_lib.check(_lib.lib().nans_debug_solver_trace(w._h, t4.ctypes.data, lv.ctypes.data, n))
+t0 = t4[:, 0].min()
+t = (t4[:, 0] - t0).astype(np.float64) / 1e3
+apply_us = (t4[:, 1] - t4[:, 0]).astype(np.float64) / 1e3
+sync_us = (t4[:, 2] - t4[:, 1]).astype(np.float64) / 1e3
+chain = t4[:, 3] == 1
 print("stage ms", ms, "contacts", n, "levels", st["solver_levels"], "span us", t.max())
 c = w.contacts()
 print("type counts", np.bincount(c["type"], minlength=5))
 for L in sorted(set(lv.tolist()))[:200]:
     m = lv == L
     if L <= 20 or L % 10 == 0 or m.sum() > 5000:
-        print(f"level {L:3d} n={m.sum():7d} start min/med/max us = {t[m].min():8.1f} {np.median(t[m]):8.1f} {t[m].max():8.1f}  types {np.bincount(c['type'][m], minlength=5)}")
+        print(f"level {L:3d} n={m.sum():7d} start min/med/max us = {t[m].min():8.1f} {np.median(t[m]):8.1f} {t[m].max():8.1f}"
+              f" | apply med {np.median(apply_us[m]):5.2f} sync med {np.median(sync_us[m]):5.2f} chained {chain[m].mean()*100:3.0f}%")
