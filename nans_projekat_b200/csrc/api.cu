@@ -189,6 +189,8 @@ static inline WorldImpl *impl(nans_world *w) { return reinterpret_cast<WorldImpl
 
 using namespace nans;
 
+static void graph_invalidate(WorldImpl *w);
+
 extern "C" {
 
 const char *nans_last_error(void) { return g_err; }
@@ -263,6 +265,7 @@ void nans_world_destroy(nans_world *h)
     WorldImpl *w = impl(h);
     cudaSetDevice(w->device);
     cudaStreamSynchronize(w->stream);
+    if (w->graph_exec) cudaGraphExecDestroy(w->graph_exec);
     if (w->owns_arena) cudaFree(w->arena);
     if (w->owns_stream) cudaStreamDestroy(w->stream);
     if (w->h_counters) cudaFreeHost(w->h_counters);
@@ -351,6 +354,7 @@ int nans_world_upload(nans_world *h, const nans_scene_view *sc)
         if (cell > d.cell_size || d.cell_size == 2.0f) d.cell_size = fmaxf(cell, 0.25f);
     }
     w->have_contacts = false;
+    if (sc->scale || sc->radius || sc->world_id) graph_invalidate(w);   // launch parameters changed
     NANS_CUDA(cudaStreamSynchronize(s));
     return NANS_OK;
 }
@@ -451,6 +455,7 @@ int nans_world_set_partition(nans_world *h, int32_t n_owned, int32_t n_ghosts)
     if (w->d.n_spheres != 0) return fail(NANS_ERR_ARG, "slab mode supports cube-only worlds");
     if (n_owned < 0 || n_ghosts < 0 || n_owned + n_ghosts > w->cap_nb)
         return fail(NANS_ERR_CAPACITY, "nans_world_set_partition: owned + ghosts exceed the world's capacity");
+    if (w->d.n_owned != n_owned || w->d.nb != n_owned + n_ghosts) graph_invalidate(w);
     w->d.n_owned = n_owned;
     w->d.nb = n_owned + n_ghosts;
     w->d.n_cubes = w->d.nb;
@@ -559,7 +564,7 @@ int nans_rebuild_vertices(nans_world *h)
     return launch_integrate_velocities(w, 0.0f);   // Position += 0*V is exact for finite V; rebuilds every Model
 }
 
-int nans_step(nans_world *h, float dt)
+static int step_eager(nans_world *h, float dt)
 {
     int rc = nans_integrate_forces(h, dt);
     if (rc) return rc;
@@ -568,6 +573,63 @@ int nans_step(nans_world *h, float dt)
     rc = nans_solve_constraints(h, dt);
     if (rc) return rc;
     return nans_integrate_velocities(h, dt);
+}
+
+static void graph_invalidate(WorldImpl *w)
+{
+    if (w->graph_exec) { cudaGraphExecDestroy(w->graph_exec); w->graph_exec = nullptr; }
+    if (w->graph_state > 0) w->graph_state = 0;
+}
+
+// The step is ~46 launches whose parameters do not change from frame to frame (all sizes that vary
+// live in device memory), so it is captured once into a CUDA graph and replayed: one launch per
+// frame instead of 46.  First step with a given dt runs eagerly (it also warms the static launch
+// configuration caches), the second is captured.  NANS_GRAPH=0 disables.
+int nans_step(nans_world *h, float dt)
+{
+    if (!h) return fail(NANS_ERR_ARG, "null world");
+    WorldImpl *w = impl(h);
+    static int enabled = -1;
+    if (enabled < 0) { const char *e = getenv("NANS_GRAPH"); enabled = (e && atoi(e) == 0) ? 0 : 1; }
+    if (!enabled || w->graph_state < 0 || w->d.nb == 0) return step_eager(h, dt);
+    NANS_CUDA(cudaSetDevice(w->device));
+    if (w->graph_state == 2 && w->graph_dt == dt) {
+        NANS_CUDA(cudaGraphLaunch(w->graph_exec, w->stream));
+        g_launches += w->graph_launches;
+        w->have_contacts = true;
+        return NANS_OK;
+    }
+    if (w->graph_state == 1 && w->graph_dt == dt) {
+        const unsigned long long before = g_launches;
+        cudaGraph_t graph = nullptr;
+        if (cudaStreamBeginCapture(w->stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+            cudaGetLastError();
+            w->graph_state = -1;
+            return step_eager(h, dt);
+        }
+        const int rc = step_eager(h, dt);
+        const cudaError_t ee = cudaStreamEndCapture(w->stream, &graph);
+        if (rc || ee != cudaSuccess || !graph ||
+            cudaGraphInstantiate(&w->graph_exec, graph, 0) != cudaSuccess) {
+            cudaGetLastError();
+            if (graph) cudaGraphDestroy(graph);
+            w->graph_exec = nullptr;
+            w->graph_state = -1;            // capture not possible here: stay eager
+            g_launches = before;
+            return step_eager(h, dt);
+        }
+        cudaGraphDestroy(graph);
+        w->graph_launches = (unsigned)(g_launches - before);
+        g_launches = before;
+        w->graph_state = 2;
+        NANS_CUDA(cudaGraphLaunch(w->graph_exec, w->stream));
+        g_launches += w->graph_launches;
+        return NANS_OK;
+    }
+    graph_invalidate(w);
+    w->graph_dt = dt;
+    w->graph_state = 1;
+    return step_eager(h, dt);
 }
 
 // One step with a CUDA event between every stage (on the world's stream); stage_ms[8]:

@@ -96,6 +96,12 @@ struct World {
     cudaStream_t stream;
     bool owns_stream;
     bool have_contacts;
+    // whole-step CUDA graph (captured on the 2nd step with an unchanged dt; any change of the launch
+    // parameters -- body counts, cell size, world ids -- invalidates it)
+    cudaGraphExec_t graph_exec;
+    float graph_dt;
+    int graph_state;            // 0 none, 1 one eager step seen with graph_dt, 2 captured, -1 disabled
+    unsigned graph_launches;    // kernels inside the captured step
     int device;
     int coop_blocks_per_sm;
     int32_t *h_counters;   // pinned mirror of Counters
