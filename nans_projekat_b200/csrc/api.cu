@@ -189,9 +189,9 @@ static inline WorldImpl *impl(nans_world *w) { return reinterpret_cast<WorldImpl
 
 using namespace nans;
 
-static void graph_invalidate(WorldImpl *w);
-
 extern "C" {
+
+static void graph_invalidate(WorldImpl *w);
 
 const char *nans_last_error(void) { return g_err; }
 
