@@ -45,6 +45,8 @@ def parse():
     ap.add_argument("--cpu-bodies", type=int, default=2048, help="size of the CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--workload", default="pile", choices=["pile", "drop10k", "worlds4096"],
+                    help="pile = 1M-cube pile (BASELINE metric; default); drop10k = config C2; worlds4096 = config C4")
     ap.add_argument("--mode", default="worlds", choices=["worlds", "slab"],
                     help="N>1: 'worlds' = one independent world per GPU (weak scaling, no collective; default); "
                          "'slab' = ONE world split by body-index slabs with NCCL halo exchange (strong scaling)")
@@ -104,6 +106,17 @@ def build_pile(bodies, side, seed):
     from nans_projekat_b200 import scenes
     layers = max(1, (bodies + side * side - 1) // (side * side))
     return scenes.cube_pile(n_side=side, layers=layers, n=bodies, seed=seed), layers
+
+
+def build_workload(args, seed):
+    """(scene, layers, name): the scene the step is timed on."""
+    from nans_projekat_b200 import scenes
+    if args.workload == "drop10k":      # config C2: 10 000 cubes dropped into the static box
+        return scenes.cube_drop(n=10000, seed=seed), 21, "cube_drop_10k (config C2)"
+    if args.workload == "worlds4096":   # config C4: 4096 independent worlds x (48 cubes + 16 spheres)
+        return scenes.batched_worlds(4096, 48, 16, seed=seed), 3, "batched_worlds_4096x64 (config C4)"
+    scene, layers = build_pile(args.bodies, args.side, seed)
+    return scene, layers, ("cube_pile_1M" if scene.n_cubes == 1_000_000 else f"cube_pile_{scene.n_cubes}")
 
 
 # --------------------------------------------------------------------------------------- CPU legs
@@ -339,8 +352,8 @@ def main():
             dist.barrier()
 
     warmup = max(args.warmup, 3)
-    scene, layers = build_pile(args.bodies, args.side, seed=7 + rank)
-    nb = scene.n_cubes
+    scene, layers, workload_name = build_workload(args, seed=7 + rank)
+    nb = scene.nb
     stream = torch.cuda.Stream()
     world = World(scene, device=local, stream=stream.cuda_stream)
     world.rebuild_vertices()
@@ -438,7 +451,7 @@ def main():
         def pinned(shape):
             return torch.zeros(shape, dtype=torch.float32).pin_memory().numpy()
         io = Scene.__new__(Scene)
-        io.n_cubes, io.n_spheres, io.n_statics, io.world_id = scene.n_cubes, 0, scene.n_statics, None
+        io.n_cubes, io.n_spheres, io.n_statics, io.world_id = scene.n_cubes, scene.n_spheres, scene.n_statics, None
         io.force, io.torque, io.pos, io.ang = pinned((nb, 3)), pinned((nb, 3)), pinned((nb, 3)), pinned((nb, 3))
 
         def e2e_step():
@@ -460,7 +473,7 @@ def main():
         assert np.isfinite(io.pos).all(), "non-finite positions after the e2e loop"
 
     cpu = None
-    if rank == 0 and world_size == 1 and not args.no_cpu_baseline:
+    if rank == 0 and world_size == 1 and not args.no_cpu_baseline and args.workload == "pile":
         state = prepared.copy()
         for f in ("scale", "mass", "moi", "st_pos", "st_ang", "st_scale", "st_mass", "st_moi"):
             getattr(state, f)[...] = getattr(scene, f)
@@ -475,7 +488,7 @@ def main():
                 "steps": args.steps, "warmup": warmup, "ms_per_step": ms_max / args.steps,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
                 "data": "synthetic",
-                "config": {"workload": "cube_pile_1M" if nb == 1_000_000 else f"cube_pile_{nb}",
+                "config": {"workload": workload_name,
                            "bodies_per_world": nb, "worlds": world_size, "footprint": f"{args.side}x{args.side}",
                            "layers": layers, "spacing": 1.02, "dt": float(DT), "settle_steps": args.settle,
                            "parallelism": "1 world per GPU, no collective" if world_size > 1 else "1 world on 1 GPU",

@@ -1,0 +1,33 @@
+"""Small run for compute-sanitizer (memcheck / racecheck / initcheck): every kernel of the step on a
+mixed world (cubes + spheres + statics), the stand-alone narrowphase, snapshot/restore, transfers."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+from nans_projekat_b200 import scenes
+from nans_projekat_b200.world import World, check_collision
+
+rng = np.random.default_rng(5)
+s = scenes.Scene(300, 60, 3)
+p = rng.uniform(0, 6, (360, 3)); p[:, 1] = rng.uniform(0.3, 4.0, 360)
+for i in range(300):
+    s.set_cube(i, p[i], ang=rng.uniform(-180, 180, 3))
+for j in range(60):
+    s.set_sphere(j, p[300 + j], radius=float(rng.uniform(0.2, 0.5)))
+s.set_static(0, (3, -0.5, 3), (100.0, 1.0, 100.0))
+s.set_static(1, (-0.6, 2.0, 3), (1.0, 8.0, 20.0), size_for_moi=20)
+s.set_static(2, (6.6, 2.0, 3), (1.0, 8.0, 20.0), size_for_moi=20)
+w = World(s)
+w.rebuild_vertices()
+dt = np.float32(1 / 60.)
+w.snapshot()
+for k in range(12):
+    w.step(dt)          # eager, then captured graph, then replays
+w.restore()
+for k in range(3):
+    w.step_profiled(dt)
+st = w.stats()
+c = w.contacts(); a, b = w.pairs(); d = w.download()
+q = scenes.narrowphase_pairs(2048, seed=3)
+r = check_collision(q["type"], q["pos_a"], q["verts_a"], q["rad_a"], q["pos_b"], q["verts_b"], q["rad_b"])
+print("sanitize run ok:", st, "contacts", len(c), "pairs", len(a), "hits", int(r["hit"].sum()))
+w.close()
