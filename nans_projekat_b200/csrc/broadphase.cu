@@ -8,11 +8,11 @@
 //   aabb_kernel          AABB per body (8 vertices / centre +- radius) + this step's largest extent
 //   key_kernel           30-bit Morton key of the cell (edge = largest extent) holding the AABB centre
 //   radix sort           4 x 8-bit LSD passes (histogram -> scan -> stable scatter), key+row payload
-//   gather_sorted_kernel AABBs permuted into Morton order (neighbour scans read contiguous ranges)
-//   cell_table_kernel    open-addressing hash: cell key -> [start, end) in the sorted order
-//   pair_count_kernel    per body, 27-cell scan, counts per (type, body)
+//   gather_sorted_kernel AABBs permuted into Morton order as 32-byte records (neighbour scans read
+//                        contiguous ranges) + open-addressing hash table cell key -> [start, end)
+//   pair_count_kernel    per body ONE 27-cell scan: counts per (type, body) + partners parked in slots
 //   (exclusive scan)     offsets in reference order
-//   pair_emit_kernel     same scan, writes partners, sorts each short run ascending
+//   pair_emit_kernel     moves the parked partners to their offsets, sorts each short run ascending
 //
 // All kernels are HBM/L2-bound integer + compare work; see DESIGN.md §4 for bytes per body.
 #include "world.cuh"

@@ -92,12 +92,6 @@ __device__ __forceinline__ vec3 support_of(const NpShapes &S, int side, vec3 d, 
         return box_support(S, side, d, rec.idx);
     }
 }
-template <bool SPHERE>
-__device__ __forceinline__ vec3 support_point(const NpShapes &S, int side, const SupRec<SPHERE> &rec)
-{
-    if constexpr (SPHERE) return rec.v; else return S.vertex(side, rec.idx);
-}
-
 // CalculateSupport, code/nans.cpp:464-519
 template <bool AS, bool BS>
 __device__ __forceinline__ GjkVertex<AS, BS> calc_support(const NpShapes &S, vec3 d)

@@ -326,7 +326,7 @@ __device__ __forceinline__ int atom_add_acq_rel(int *p, int v)
 // stores (RMW chain on the same counter) and either runs the successor itself or hands it over
 // through a release store to the queue slot, which the ticket holder reads with an acquire load.
 __global__ void __launch_bounds__(kFlowThreads) solve_dataflow_kernel(DeviceWorld w, unsigned long long *trace,
-                                                                      int max_hops, int atomic_mode, int sleep_ns)
+                                                                      int max_hops, int atomic_mode, int sleep_ns, int track_levels)
 {
     const int n = w.counters->n_contacts;
     const int lane = threadIdx.x & 31;
@@ -366,7 +366,7 @@ __global__ void __launch_bounds__(kFlowThreads) solve_dataflow_kernel(DeviceWorl
                         trace[4 * (size_t)c] = tns;
                         trace[4 * (size_t)c + 3] = (rows_a == kRowsUnknown) ? 0ull : 1ull;   // 0 = from the queue, 1 = chain
                     }
-                    const int lv = __ldcg(&level[c]);
+                    const int lv = track_levels ? __ldcg(&level[c]) : 0;
                     const NextRows nx = apply_prepared(w, c, rows_a, rows_b);
                     if (trace) {
                         unsigned long long tns;
@@ -375,8 +375,10 @@ __global__ void __launch_bounds__(kFlowThreads) solve_dataflow_kernel(DeviceWorl
                     }
                     ++processed;
                     max_level = max(max_level, lv);
-                    if (nx.sa >= 0) atomicMax(&level[nx.sa], lv + 1);
-                    if (nx.sb >= 0) atomicMax(&level[nx.sb], lv + 1);
+                    if (track_levels) {   // statistic only (DAG depth); two more RMWs to drain before the fence
+                        if (nx.sa >= 0) atomicMax(&level[nx.sa], lv + 1);
+                        if (nx.sb >= 0) atomicMax(&level[nx.sb], lv + 1);
+                    }
                     int oa = 0, ob = 0;
                     if (atomic_mode == 0) {            // one release fence, two relaxed RMWs in flight together
                         fence_acq_rel();               // release: this contact's velocity stores
@@ -518,17 +520,18 @@ int launch_solver(World *w, float dt)
     static int trace_on = -1;
     if (trace_on < 0) trace_on = getenv("NANS_SOLVER_TRACE") ? 1 : 0;
     // debug trace reuses the narrowphase output block (idle during the solve)
-    static int hops = -1, amode = 0, sleep_ns = 32;
+    static int hops = -1, amode = 0, sleep_ns = 32, track_levels = 1;
     if (hops < 0) {   // tuning knobs (defaults chosen from the sweeps in profiles/)
         const char *e;
         hops = (e = getenv("NANS_FLOW_HOPS")) ? atoi(e) : 1;
         amode = (e = getenv("NANS_FLOW_ATOMICS")) ? atoi(e) : 0;
         sleep_ns = (e = getenv("NANS_FLOW_SLEEP")) ? atoi(e) : 32;
         if ((e = getenv("NANS_FLOW_BLOCKS"))) flow_blocks = sm_count * atoi(e);
+        track_levels = (e = getenv("NANS_SOLVER_LEVELS")) ? atoi(e) : 1;
         if (hops < 1) hops = 1;
     }
     solve_dataflow_kernel<<<flow_blocks, kFlowThreads, 0, s>>>(d, trace_on ? (unsigned long long *)d.pair_out : nullptr,
-                                                               hops, amode, sleep_ns);
+                                                               hops, amode, sleep_ns, track_levels | trace_on);
     NANS_LAUNCH_CHECK();
     return NANS_OK;
 }
