@@ -128,18 +128,14 @@ __global__ void __launch_bounds__(256) aabb_kernel(DeviceWorld w)
 // Morton cell key of the AABB centre.  The cell edge is this step's largest AABB extent (so that
 // AABB-overlapping bodies always sit in adjacent cells) — far tighter than the static bound (box
 // diagonal) while the bodies are near axis-aligned; the static bound is the fallback if it is not finite.
-__device__ __forceinline__ float step_cell_size(const DeviceWorld &w)
-{
-    float cell = __uint_as_float((unsigned int)w.counters->pad[2]) * 1.0001f + 1e-4f;
-    if (!isfinite(cell)) cell = w.cell_size;             // overflowed vertices: static bound (box diagonal)
-    return fmaxf(cell, 0.05f);
-}
-
 __global__ void __launch_bounds__(256) key_kernel(DeviceWorld w)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= w.nb) return;
-    const float inv_cell = 1.0f / step_cell_size(w);
+    float cell = __uint_as_float((unsigned int)w.counters->pad[2]) * 1.0001f + 1e-4f;
+    if (!isfinite(cell)) cell = w.cell_size;             // overflowed vertices: static bound (box diagonal)
+    cell = fmaxf(cell, 0.05f);
+    const float inv_cell = 1.0f / cell;
     const float4 lo = w.aabb_lo[i], hi = w.aabb_hi[i];
     int cx = cell_coord(0.5f * (lo.x + hi.x), inv_cell);
     int cy = cell_coord(0.5f * (lo.y + hi.y), inv_cell);
@@ -292,27 +288,9 @@ __device__ __forceinline__ void for_each_partner(const DeviceWorld &w, const uin
                    ey2 = expand_bits10((uint32_t)(cy + 1)) << 1;
     const uint32_t ez0 = expand_bits10((uint32_t)(cz - 1)), ez1 = expand_bits10((uint32_t)cz),
                    ez2 = expand_bits10((uint32_t)(cz + 1));
-    // A partner's centre lies within (own extent + largest extent) / 2 of this body's centre on every
-    // axis, so only the cells that interval touches need a visit (monotone cell_coord => conservative):
-    // on average ~17 of the 27 neighbours.  (Batched worlds remap x/z cells; they keep the full scan.)
-    int dlo[3] = {-1, -1, -1}, dhi[3] = {1, 1, 1};
-    if (!w.world_id) {
-        const float cell = step_cell_size(w), inv_cell = 1.0f / cell;
-        const float lo3[3] = {alo.x, alo.y, alo.z}, hi3[3] = {ahi.x, ahi.y, ahi.z};
-        const int c3[3] = {cx, cy, cz};
-#pragma unroll
-        for (int k = 0; k < 3; ++k) {
-            const float c = 0.5f * (lo3[k] + hi3[k]);
-            const float r = (0.5f * ((hi3[k] - lo3[k]) + cell)) * 1.001f + 1e-4f;
-            if (isfinite(c) && isfinite(r)) {
-                dlo[k] = max(-1, cell_coord(c - r, inv_cell) - c3[k]);
-                dhi[k] = min(1, cell_coord(c + r, inv_cell) - c3[k]);
-            }
-        }
-    }
-    for (int dz = dlo[2]; dz <= dhi[2]; ++dz)
-        for (int dy = dlo[1]; dy <= dhi[1]; ++dy)
-            for (int dx = dlo[0]; dx <= dhi[0]; ++dx) {
+    for (int dz = -1; dz <= 1; ++dz)
+        for (int dy = -1; dy <= 1; ++dy)
+            for (int dx = -1; dx <= 1; ++dx) {
                 const int nx = cx + dx, ny = cy + dy, nz = cz + dz;
                 if ((unsigned)nx > 1023u || (unsigned)ny > 1023u || (unsigned)nz > 1023u) continue;
                 const uint32_t nkey = (dx < 0 ? ex0 : dx == 0 ? ex1 : ex2) | (dy < 0 ? ey0 : dy == 0 ? ey1 : ey2) |
