@@ -104,6 +104,15 @@ int nans_world_add_force(nans_world *w, int32_t body_row, const float force[3], 
 int nans_world_set_body(nans_world *w, int32_t body_row, const float pos[3], const float vel[3],
                         const float angvel[3]);
 
+/* Pipelined host I/O for hosts that can take the poses one frame late (a renderer): the copies run on
+ * their own streams and overlap the step.  Host buffers should be pinned and must stay valid until the
+ * copy completes (upload: until the next nans_step has been issued and nans_world_wait(w, -1) or a later
+ * download ticket returned; download: until nans_world_wait on its ticket).  Fields: pos, vel, force, ang,
+ * angvel, torque.  The reference's frame is synchronous (code/sdl_nans.cpp:986); use the calls above for that. */
+int nans_world_upload_async(nans_world *w, const nans_scene_view *scene);
+int nans_world_download_async(nans_world *w, nans_scene_view *scene, int32_t *ticket);
+int nans_world_wait(nans_world *w, int32_t ticket);   /* ticket < 0: everything outstanding */
+
 /* device-to-device snapshot / restore of the dynamic state (pose, velocities, forces, vertices);
  * asynchronous on the world's stream.  The reference checkpoints implicitly: its whole world is one
  * host block that survives plugin reloads (code/sdl_nans.cpp:541-555). */

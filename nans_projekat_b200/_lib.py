@@ -36,7 +36,7 @@ class StepStats(C.Structure):
 # every symbol include/nans_b200.h declares
 EXPORTS = ("nans_world_create", "nans_world_destroy", "nans_world_arena_bytes", "nans_last_error",
            "nans_device_count", "nans_world_upload", "nans_world_download", "nans_world_add_force",
-           "nans_world_set_body", "nans_world_snapshot", "nans_world_restore", "nans_integrate_forces", "nans_detect_collisions",
+           "nans_world_set_body", "nans_world_upload_async", "nans_world_download_async", "nans_world_wait", "nans_world_snapshot", "nans_world_restore", "nans_integrate_forces", "nans_detect_collisions",
            "nans_solve_constraints", "nans_integrate_velocities", "nans_rebuild_vertices", "nans_step", "nans_step_profiled",
            "nans_synchronize", "nans_get_stats", "nans_get_contacts", "nans_get_pairs", "nans_set_contacts",
            "nans_check_collision_batch", "nans_check_collision_device", "nans_kernel_launches", "nans_debug_solver_trace", "nans_world_set_partition", "nans_world_bounds",
@@ -68,6 +68,9 @@ def lib():
     L.nans_world_destroy.restype = None
     for name in ("nans_world_upload", "nans_world_download"):
         getattr(L, name).argtypes = [C.c_void_p, C.POINTER(SceneView)]
+    L.nans_world_upload_async.argtypes = [C.c_void_p, C.POINTER(SceneView)]
+    L.nans_world_download_async.argtypes = [C.c_void_p, C.POINTER(SceneView), i32p]
+    L.nans_world_wait.argtypes = [C.c_void_p, C.c_int32]
     L.nans_world_add_force.argtypes = [C.c_void_p, C.c_int32, f32p, f32p]
     L.nans_world_set_body.argtypes = [C.c_void_p, C.c_int32, f32p, f32p, f32p]
     for name in ("nans_integrate_forces", "nans_solve_constraints", "nans_integrate_velocities", "nans_step"):

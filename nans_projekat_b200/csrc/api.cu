@@ -128,7 +128,16 @@ static Layout carve(const nans_world_desc &desc, char *base)
     return L;
 }
 
+struct IoPipe {               // pipelined host I/O: copies on their own streams, overlapping the step
+    bool init;
+    cudaStream_t up, down;
+    cudaEvent_t ev_up, ev_unpack, ev_pack, ev_down[8];
+    bool have_unpack, have_down;
+    int next_ticket;
+};
+
 struct WorldImpl : World {
+    IoPipe io;
     Staging st;
     SlabBufs slab;
     int32_t cap_nb;          // capacity of the body arrays (slab mode varies nb below it)
@@ -221,6 +230,7 @@ int nans_world_create(const nans_world_desc *desc, nans_world **out)
     NANS_CUDA(cudaSetDevice(desc->device));
     WorldImpl *w = new WorldImpl();
     memset(static_cast<World *>(w), 0, sizeof(World));
+    memset(&w->io, 0, sizeof(w->io));
     w->desc = *desc;
     w->device = desc->device;
     const size_t need = carve(*desc, nullptr).bytes;
@@ -266,6 +276,12 @@ void nans_world_destroy(nans_world *h)
     cudaSetDevice(w->device);
     cudaStreamSynchronize(w->stream);
     if (w->graph_exec) cudaGraphExecDestroy(w->graph_exec);
+    if (w->io.init) {
+        cudaStreamSynchronize(w->io.up); cudaStreamSynchronize(w->io.down);
+        cudaStreamDestroy(w->io.up); cudaStreamDestroy(w->io.down);
+        cudaEventDestroy(w->io.ev_up); cudaEventDestroy(w->io.ev_unpack); cudaEventDestroy(w->io.ev_pack);
+        for (auto &e : w->io.ev_down) cudaEventDestroy(e);
+    }
     if (w->owns_arena) cudaFree(w->arena);
     if (w->owns_stream) cudaStreamDestroy(w->stream);
     if (w->h_counters) cudaFreeHost(w->h_counters);
@@ -292,6 +308,7 @@ int nans_world_upload(nans_world *h, const nans_scene_view *sc)
     const int grid = div_up(nb > 0 ? nb : 1, 256);
     const float *vsrc[7] = {sc->pos, sc->vel, sc->force, sc->ang, sc->angvel, sc->torque, sc->scale};
     float4 *vdst[7] = {d.pos, d.vel, d.force, d.ang, d.angvel, d.torque, d.scale};
+    if (w->io.init) { NANS_CUDA(cudaStreamSynchronize(w->io.up)); NANS_CUDA(cudaStreamSynchronize(w->io.down)); }
     if (nb > 0) {
         for (int k = 0; k < 7; ++k) {
             if (!vsrc[k]) continue;
@@ -370,6 +387,7 @@ int nans_world_download(nans_world *h, nans_scene_view *sc)
     const int grid = div_up(nb > 0 ? nb : 1, 256);
     float *vdst[7] = {sc->pos, sc->vel, sc->force, sc->ang, sc->angvel, sc->torque, sc->scale};
     const float4 *vsrc[7] = {d.pos, d.vel, d.force, d.ang, d.angvel, d.torque, d.scale};
+    if (w->io.init) { NANS_CUDA(cudaStreamSynchronize(w->io.up)); NANS_CUDA(cudaStreamSynchronize(w->io.down)); }
     if (nb > 0) {
         for (int k = 0; k < 7; ++k) {
             if (!vdst[k]) continue;
@@ -391,6 +409,103 @@ int nans_world_download(nans_world *h, nans_scene_view *sc)
         NANS_CUDA(cudaMemcpyAsync(sc->st_verts, d.st_verts, sizeof(float) * 24 * (size_t)d.n_statics,
                                   cudaMemcpyDeviceToHost, s));
     NANS_CUDA(cudaStreamSynchronize(s));
+    return NANS_OK;
+}
+
+// ---- pipelined I/O ------------------------------------------------------------------------------
+// The reference's frame is synchronous (host writes forces, steps, reads poses).  For hosts that can
+// take the poses one frame late (a renderer), the copies can ride on separate streams and overlap the
+// step: H2D of frame k+1's inputs and D2H of frame k's poses both run while frame k+1 computes.
+static int io_init(WorldImpl *w)
+{
+    if (w->io.init) return NANS_OK;
+    NANS_CUDA(cudaStreamCreateWithFlags(&w->io.up, cudaStreamNonBlocking));
+    NANS_CUDA(cudaStreamCreateWithFlags(&w->io.down, cudaStreamNonBlocking));
+    NANS_CUDA(cudaEventCreateWithFlags(&w->io.ev_up, cudaEventDisableTiming));
+    NANS_CUDA(cudaEventCreateWithFlags(&w->io.ev_unpack, cudaEventDisableTiming));
+    NANS_CUDA(cudaEventCreateWithFlags(&w->io.ev_pack, cudaEventDisableTiming));
+    for (auto &e : w->io.ev_down) NANS_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    w->io.have_unpack = w->io.have_down = false;
+    w->io.next_ticket = 0;
+    w->io.init = true;
+    return NANS_OK;
+}
+
+int nans_world_upload_async(nans_world *h, const nans_scene_view *sc)
+{
+    if (!h || !sc) return fail(NANS_ERR_ARG, "null argument");
+    WorldImpl *w = impl(h);
+    DeviceWorld &d = w->d;
+    NANS_CUDA(cudaSetDevice(w->device));
+    int rc = io_init(w);
+    if (rc) return rc;
+    const int nb = d.nb;
+    if (nb == 0) return NANS_OK;
+    const float *vsrc[6] = {sc->pos, sc->vel, sc->force, sc->ang, sc->angvel, sc->torque};
+    float4 *vdst[6] = {d.pos, d.vel, d.force, d.ang, d.angvel, d.torque};
+    // the staging slots are free once the previous unpack ran and the previous D2H has read them
+    if (w->io.have_unpack) NANS_CUDA(cudaStreamWaitEvent(w->io.up, w->io.ev_unpack, 0));
+    if (w->io.have_down) NANS_CUDA(cudaStreamWaitEvent(w->io.up, w->io.ev_down[(w->io.next_ticket + 7) % 8], 0));
+    for (int k = 0; k < 6; ++k)
+        if (vsrc[k])
+            NANS_CUDA(cudaMemcpyAsync(w->st.vec[k], vsrc[k], sizeof(float) * 3 * (size_t)nb, cudaMemcpyHostToDevice, w->io.up));
+    NANS_CUDA(cudaEventRecord(w->io.ev_up, w->io.up));
+    NANS_CUDA(cudaStreamWaitEvent(w->stream, w->io.ev_up, 0));
+    const int grid = div_up(nb, 256);
+    for (int k = 0; k < 6; ++k)
+        if (vsrc[k]) {
+            unpack_vec3_kernel<<<grid, 256, 0, w->stream>>>(w->st.vec[k], vdst[k], nb);
+            NANS_LAUNCH_CHECK();
+        }
+    NANS_CUDA(cudaEventRecord(w->io.ev_unpack, w->stream));
+    w->io.have_unpack = true;
+    return NANS_OK;
+}
+
+int nans_world_download_async(nans_world *h, nans_scene_view *sc, int32_t *ticket)
+{
+    if (!h || !sc || !ticket) return fail(NANS_ERR_ARG, "null argument");
+    WorldImpl *w = impl(h);
+    DeviceWorld &d = w->d;
+    NANS_CUDA(cudaSetDevice(w->device));
+    int rc = io_init(w);
+    if (rc) return rc;
+    const int nb = d.nb;
+    float *vdst[6] = {sc->pos, sc->vel, sc->force, sc->ang, sc->angvel, sc->torque};
+    const float4 *vsrc[6] = {d.pos, d.vel, d.force, d.ang, d.angvel, d.torque};
+    const int t = w->io.next_ticket;
+    // the previous D2H must have drained the staging slots before they are packed again
+    if (w->io.have_down) NANS_CUDA(cudaStreamWaitEvent(w->stream, w->io.ev_down[(t + 7) % 8], 0));
+    const int grid = div_up(nb > 0 ? nb : 1, 256);
+    for (int k = 0; k < 6 && nb > 0; ++k)
+        if (vdst[k]) {
+            pack_vec3_kernel<<<grid, 256, 0, w->stream>>>(vsrc[k], w->st.vec[k], nb);
+            NANS_LAUNCH_CHECK();
+        }
+    NANS_CUDA(cudaEventRecord(w->io.ev_pack, w->stream));
+    NANS_CUDA(cudaStreamWaitEvent(w->io.down, w->io.ev_pack, 0));
+    for (int k = 0; k < 6 && nb > 0; ++k)
+        if (vdst[k])
+            NANS_CUDA(cudaMemcpyAsync(vdst[k], w->st.vec[k], sizeof(float) * 3 * (size_t)nb, cudaMemcpyDeviceToHost, w->io.down));
+    NANS_CUDA(cudaEventRecord(w->io.ev_down[t % 8], w->io.down));
+    w->io.have_down = true;
+    w->io.next_ticket = t + 1;
+    *ticket = t;
+    return NANS_OK;
+}
+
+int nans_world_wait(nans_world *h, int32_t ticket)
+{
+    if (!h) return fail(NANS_ERR_ARG, "null world");
+    WorldImpl *w = impl(h);
+    NANS_CUDA(cudaSetDevice(w->device));
+    if (!w->io.init || ticket < 0) {
+        if (w->io.init) { NANS_CUDA(cudaStreamSynchronize(w->io.up)); NANS_CUDA(cudaStreamSynchronize(w->io.down)); }
+        NANS_CUDA(cudaStreamSynchronize(w->stream));
+        return NANS_OK;
+    }
+    if (ticket >= w->io.next_ticket || ticket < w->io.next_ticket - 8) return fail(NANS_ERR_ARG, "nans_world_wait: stale or unknown ticket");
+    NANS_CUDA(cudaEventSynchronize(w->io.ev_down[ticket % 8]));
     return NANS_OK;
 }
 

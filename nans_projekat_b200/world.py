@@ -95,6 +95,22 @@ class World:
         v = _view(scene, fields)
         _lib.check(_lib.lib().nans_world_download(self._h, C.byref(v)))
 
+    # pipelined I/O (poses one frame late): copies overlap the step on their own streams
+    def upload_async(self, scene, fields=("force", "torque")):
+        v = _view(scene, fields)
+        self._pending_views = getattr(self, "_pending_views", [])[-4:] + [v]   # keep the host arrays alive
+        _lib.check(_lib.lib().nans_world_upload_async(self._h, C.byref(v)))
+
+    def download_async(self, scene, fields=("pos", "ang")) -> int:
+        v = _view(scene, fields)
+        self._pending_views = getattr(self, "_pending_views", [])[-4:] + [v]
+        t = C.c_int32(0)
+        _lib.check(_lib.lib().nans_world_download_async(self._h, C.byref(v), C.byref(t)))
+        return t.value
+
+    def wait(self, ticket: int = -1):
+        _lib.check(_lib.lib().nans_world_wait(self._h, ticket))
+
     def add_force(self, body_row: int, force=(0, 0, 0), torque=(0, 0, 0)):
         f = np.asarray(force, np.float32); t = np.asarray(torque, np.float32)
         _lib.check(_lib.lib().nans_world_add_force(self._h, body_row, _fp(f), _fp(t)))
