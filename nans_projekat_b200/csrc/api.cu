@@ -46,6 +46,7 @@ static uint32_t pow2_at_least(uint32_t v)
 
 struct Staging {            // per-field upload/download slots (device), carved from the same arena
     float *vec[7];          // pos, vel, force, ang, angvel, torque, scale : [nb][3]
+    float *dvec[6];         // separate slots for the pipelined downloads (so H2D and D2H never share one)
     float *scal[3];         // mass, moi, radius : [nb]
     float *verts;           // [n_cubes][24]
     int32_t *wid;           // [nb]
@@ -119,6 +120,7 @@ static Layout carve(const nans_world_desc &desc, char *base)
     d.scan_block = b.take<uint32_t>((size_t)scan_scratch_elems((int)scan_n) + 8);
     d.counters = b.take<Counters>(1);
     for (int k = 0; k < 7; ++k) L.st.vec[k] = b.take<float>(3 * nb);
+    for (int k = 0; k < 6; ++k) L.st.dvec[k] = b.take<float>(3 * nb);
     for (int k = 0; k < 3; ++k) L.st.scal[k] = b.take<float>(nb);
     L.st.verts = b.take<float>(24 * nc);
     L.st.wid = b.take<int32_t>(nb);
@@ -443,9 +445,8 @@ int nans_world_upload_async(nans_world *h, const nans_scene_view *sc)
     if (nb == 0) return NANS_OK;
     const float *vsrc[6] = {sc->pos, sc->vel, sc->force, sc->ang, sc->angvel, sc->torque};
     float4 *vdst[6] = {d.pos, d.vel, d.force, d.ang, d.angvel, d.torque};
-    // the staging slots are free once the previous unpack ran and the previous D2H has read them
+    // the upload slots are free once the previous unpack has run (downloads use their own slots)
     if (w->io.have_unpack) NANS_CUDA(cudaStreamWaitEvent(w->io.up, w->io.ev_unpack, 0));
-    if (w->io.have_down) NANS_CUDA(cudaStreamWaitEvent(w->io.up, w->io.ev_down[(w->io.next_ticket + 7) % 8], 0));
     for (int k = 0; k < 6; ++k)
         if (vsrc[k])
             NANS_CUDA(cudaMemcpyAsync(w->st.vec[k], vsrc[k], sizeof(float) * 3 * (size_t)nb, cudaMemcpyHostToDevice, w->io.up));
@@ -479,14 +480,14 @@ int nans_world_download_async(nans_world *h, nans_scene_view *sc, int32_t *ticke
     const int grid = div_up(nb > 0 ? nb : 1, 256);
     for (int k = 0; k < 6 && nb > 0; ++k)
         if (vdst[k]) {
-            pack_vec3_kernel<<<grid, 256, 0, w->stream>>>(vsrc[k], w->st.vec[k], nb);
+            pack_vec3_kernel<<<grid, 256, 0, w->stream>>>(vsrc[k], w->st.dvec[k], nb);
             NANS_LAUNCH_CHECK();
         }
     NANS_CUDA(cudaEventRecord(w->io.ev_pack, w->stream));
     NANS_CUDA(cudaStreamWaitEvent(w->io.down, w->io.ev_pack, 0));
     for (int k = 0; k < 6 && nb > 0; ++k)
         if (vdst[k])
-            NANS_CUDA(cudaMemcpyAsync(vdst[k], w->st.vec[k], sizeof(float) * 3 * (size_t)nb, cudaMemcpyDeviceToHost, w->io.down));
+            NANS_CUDA(cudaMemcpyAsync(vdst[k], w->st.dvec[k], sizeof(float) * 3 * (size_t)nb, cudaMemcpyDeviceToHost, w->io.down));
     NANS_CUDA(cudaEventRecord(w->io.ev_down[t % 8], w->io.down));
     w->io.have_down = true;
     w->io.next_ticket = t + 1;
