@@ -461,3 +461,34 @@ def test_pipelined_io_matches_synchronous_io(nb200, oracle):
     for fld in ("pos", "vel", "ang", "angvel", "verts"):
         assert_bit_equal(getattr(d, fld), getattr(base, fld), f"restore {fld}")
     ga.close(); gb.close()
+
+
+def test_c4_full_size_batched_worlds_properties(nb200):
+    """Config C4 at FULL size (4096 worlds x 64 bodies = 262 144 bodies in one device world):
+    size-independent properties — no contact ever joins two different worlds, the list stays in
+    reference order, the state stays finite, and an identical second world reproduces it bit for bit."""
+    from nans_projekat_b200 import scenes
+    s = scenes.batched_worlds(n_worlds=4096, cubes_per=48, spheres_per=16, seed=1)
+    s.pos[:, 1] -= 0.25
+    nc = s.n_cubes
+    ga, gb = nb200.World(s), nb200.World(s)
+    ga.rebuild_vertices(); gb.rebuild_vertices()
+    for step in range(30):
+        ga.step(DT); gb.step(DT)
+    assert ga.stats()["overflow"] == 0
+    c = ga.contacts()
+    assert len(c) > 100_000
+    wid = s.world_id
+    a_row = np.where(np.isin(c["type"], (3, 4)), c["a"] + nc, c["a"])
+    dyn = np.isin(c["type"], (0, 1, 3))
+    b_row = np.where(np.isin(c["type"], (1, 3)), c["b"] + nc, c["b"])
+    assert (wid[a_row[dyn]] == wid[b_row[dyn]]).all(), "a contact joins two independent worlds"
+    seg = np.array([0, 3, 1, 4, 2])[c["type"]]
+    k = (seg.astype(np.int64) << 50) | (c["a"].astype(np.int64) << 25) | c["b"].astype(np.int64)
+    assert (np.diff(k) > 0).all()
+    da, db = ga.download(), gb.download()
+    for f in ("pos", "vel", "ang", "angvel", "verts"):
+        assert np.isfinite(getattr(da, f)).all()
+        assert_bit_equal(getattr(da, f), getattr(db, f), f"determinism {f}")
+    assert gb.contacts().tobytes() == c.tobytes()
+    ga.close(); gb.close()
