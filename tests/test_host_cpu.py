@@ -79,3 +79,11 @@ def test_scene_builders():
     assert p.n_cubes == 1000
     b = scenes.batched_worlds(n_worlds=4, cubes_per=6, spheres_per=2)
     assert b.world_id.max() == 3 and b.n_cubes == 24 and b.n_spheres == 8
+
+
+def test_headers_are_plain_c(tmp_path):
+    """The drop-in boundary is a C ABI: both headers must compile as C11 (no C++/torch types)."""
+    for h in ("nans_b200.h", "nans_plugin.h"):
+        src = tmp_path / (h + ".c")
+        src.write_text(f'#include "{os.path.join(ROOT, "include", h)}"\nint main(void) {{ return 0; }}\n')
+        subprocess.check_call(["gcc", "-std=c11", "-Wall", "-Werror", "-fsyntax-only", str(src)])
