@@ -122,7 +122,7 @@ class SlabWorld:
 class CudaEngine:
     """libnans_b200.so as the slab engine: everything stays in device memory."""
 
-    def __init__(self, scene: Scene, rank: int, world_size: int, device: int, ghost_frac: float = 0.6):
+    def __init__(self, scene: Scene, rank: int, world_size: int, device: int, ghost_frac: float = 1.25):
         import torch
         from . import _lib
         from .world import World
@@ -130,6 +130,8 @@ class CudaEngine:
         self.ranges = partition(scene.n_cubes, world_size)
         self.lo, self.hi = self.ranges[rank]
         self.n_owned = self.hi - self.lo
+        # ghosts are selected by the lower rank's bounding box, so one stray body can pull in a whole
+        # extra layer: leave room for more than a slab's worth
         self.ghost_cap = int(max(1024, ghost_frac * max(self.n_owned, 1)))
         self.device = torch.device("cuda", device)
         self.stream = torch.cuda.Stream(device=self.device)
