@@ -15,7 +15,10 @@
 //     computed once at face creation: |d| is the scan distance, the flipped normal is
 //     (d < 0 ? -n : n) = PushTriangle's stored N (:316-320);
 //   * std::vector<edge>/<triangle> erase/push_back order is preserved exactly (the closest-face
-//     tie-break is "first minimum", so face order is observable).
+//     tie-break is "first minimum", so face order is observable);
+//   * the horizon's by-value edge cancellation compares precomputed vertex equivalence classes, the
+//     closest face is tracked while the face list is rebuilt, and visible faces are listed first and
+//     turned into edges afterwards (keeps the warp converged; profiles/README.md).
 #pragma once
 #include "nans_math.cuh"
 #include "world.cuh"
@@ -181,21 +184,38 @@ __device__ __forceinline__ int evolve_simplex(const NpShapes &S, GjkVertex<AS, B
 }
 
 // ---- EPA --------------------------------------------------------------------------------------
-struct EpaArena {                        // per-thread (local memory; only the touched part costs traffic)
+// Per-thread arena (local memory; only the touched part costs traffic).  A face record is two float4:
+// (unflipped unit normal n, d = dot(n, A.P)) and (A.P, packed vertex indices a | b<<8 | c<<16), so
+// the visibility test of a face needs no dependent load.
+struct EpaArena {
     vec3 P[kEpaMaxVerts];
-    vec3 SA[kEpaMaxVerts], SB[kEpaMaxVerts];   // sphere sides only
+    vec3 SA[kEpaMaxVerts], SB[kEpaMaxVerts];    // sphere sides only
     uint8_t ia[kEpaMaxVerts], ib[kEpaMaxVerts]; // box sides only
-    float4 fnd[kEpaMaxFaces];            // unflipped unit normal, d = dot(n, A.P)
-    uint32_t fidx[kEpaMaxFaces];         // a | b<<8 | c<<16
-    uint16_t edge[kEpaMaxEdges];         // a | b<<8
+    uint8_t cid[kEpaMaxVerts];                  // lowest vertex index with an equal P (kCidNaN: equal to nothing)
+    float4 fnd[kEpaMaxFaces];
+    float4 fpa[kEpaMaxFaces];
+    uint32_t vis[kEpaMaxFaces];                 // packed indices of the faces dissolved this iteration
+    uint32_t edge[kEpaMaxEdges];                // a | b<<8 | cid[a]<<16 | cid[b]<<24
 };
+constexpr int kCidNaN = 254;
 
+// The reference's edge cancels an opposite-winding edge BY VALUE of P (code/nans.h:251-254).  Float
+// equality is an equivalence on non-NaN vectors (+0 == -0 included), so every vertex gets the lowest
+// index of its class once, when it is stored, and the edge compares become one integer compare.
 template <bool AS, bool BS>
 __device__ __forceinline__ void epa_store_vertex(EpaArena &E, int i, const GjkVertex<AS, BS> &v)
 {
     E.P[i] = v.P;
     if constexpr (AS) E.SA[i] = v.a.v; else E.ia[i] = (uint8_t)v.a.idx;
     if constexpr (BS) E.SB[i] = v.b.v; else E.ib[i] = (uint8_t)v.b.idx;
+    int c = i;
+    if (!equal(v.P, v.P)) {
+        c = kCidNaN;
+    } else {
+        for (int j = 0; j < i; ++j)
+            if (equal(E.P[j], v.P)) { c = j; break; }
+    }
+    E.cid[i] = (uint8_t)c;
 }
 template <bool AS> __device__ __forceinline__ vec3 epa_sup_a(const EpaArena &E, const NpShapes &S, int i)
 {
@@ -206,14 +226,22 @@ template <bool BS> __device__ __forceinline__ vec3 epa_sup_b(const EpaArena &E, 
     if constexpr (BS) return E.SB[i]; else return S.vertex(1, E.ib[i]);
 }
 
-__device__ __forceinline__ void epa_push_face(EpaArena &E, int &nf, int a, int b, int c)
+// closest face = FIRST strict minimum of |d| in face order (:807-822).  The reference rescans every
+// iteration; here the minimum is carried along while the face list is rebuilt in the same order.
+__device__ __forceinline__ void epa_track_min(float d, int slot, float &cur, int &ci)
 {
-    // PushTriangle, code/nans.cpp:293-322 (flip folded into the sign of d)
-    const vec3 pa = E.P[a];
+    const float dist = fabsf(d);
+    if (slot == 0 || dist < cur) { cur = dist; ci = slot; }
+}
+
+__device__ __forceinline__ void epa_push_face(EpaArena &E, int &nf, int a, int b, int c, vec3 pa, float &cur, int &ci)
+{
+    // PushTriangle, code/nans.cpp:293-322 (flip folded into the sign of d); pa == E.P[a]
     const vec3 n = normalize(cross(E.P[b] - pa, E.P[c] - pa));
     const float d = dot(pa, n);
     E.fnd[nf] = make_float4(n.x, n.y, n.z, d);
-    E.fidx[nf] = (uint32_t)a | ((uint32_t)b << 8) | ((uint32_t)c << 16);
+    E.fpa[nf] = make_float4(pa.x, pa.y, pa.z, __uint_as_float((uint32_t)a | ((uint32_t)b << 8) | ((uint32_t)c << 16)));
+    epa_track_min(d, nf, cur, ci);
     ++nf;
 }
 __device__ __forceinline__ vec3 face_normal_flipped(const float4 &nd)
@@ -222,20 +250,22 @@ __device__ __forceinline__ vec3 face_normal_flipped(const float4 &nd)
     return nd.w < 0.0f ? n * -1.0f : n;
 }
 
-// PushEdge, code/nans.cpp:233-266: cancel an opposite-winding edge BY VALUE of P (code/nans.h:251-254)
+// PushEdge, code/nans.cpp:233-266: an opposite-winding edge already in the list is erased (order of
+// the rest kept), otherwise the edge is appended
 __device__ __forceinline__ void epa_push_edge(EpaArena &E, int &ne, int a, int b, int &ovf)
 {
-    const vec3 pa = E.P[a], pb = E.P[b];
-    for (int i = 0; i < ne; ++i) {
-        const int ea = E.edge[i] & 255, eb = E.edge[i] >> 8;
-        if (equal(E.P[ea], pb) && equal(E.P[eb], pa)) {
-            for (int k = i; k < ne - 1; ++k) E.edge[k] = E.edge[k + 1];
-            --ne;
-            return;
-        }
+    const uint32_t ca = E.cid[a], cb = E.cid[b];
+    // a NaN vertex equals nothing, itself included: its id on the probing side never matches a stored one
+    const uint32_t want = (cb == kCidNaN ? 255u : cb) | ((ca == kCidNaN ? 255u : ca) << 8);
+    int i = 0;
+    while (i < ne && (E.edge[i] >> 16) != want) ++i;
+    if (i < ne) {
+        for (int k = i; k < ne - 1; ++k) E.edge[k] = E.edge[k + 1];
+        --ne;
+        return;
     }
     if (ne >= kEpaMaxEdges) { ovf |= OVF_EPA_EDGES; return; }
-    E.edge[ne++] = (uint16_t)(a | (b << 8));
+    E.edge[ne++] = (uint32_t)a | ((uint32_t)b << 8) | (ca << 16) | (cb << 24);
 }
 
 // ResolveCollision, code/nans.cpp:788-904.  Returns the bool32 result; fills PointA/PointB/N.
@@ -245,30 +275,25 @@ __device__ __forceinline__ int epa_resolve(const NpShapes &S, const GjkVertex<AS
 {
 #pragma unroll
     for (int k = 0; k < 4; ++k) epa_store_vertex<AS, BS>(E, k, s[k]);
-    int nv = 4, nf = 0, ne = 0;
-    epa_push_face(E, nf, 0, 1, 2);  // ABC
-    epa_push_face(E, nf, 0, 2, 3);  // ACD
-    epa_push_face(E, nf, 0, 3, 1);  // ADB
-    epa_push_face(E, nf, 1, 3, 2);  // BDC
+    int nv = 4, nf = 0, ne = 0, ci = 0;
+    float cur = 0.f;
+    epa_push_face(E, nf, 0, 1, 2, s[0].P, cur, ci);  // ABC
+    epa_push_face(E, nf, 0, 2, 3, s[0].P, cur, ci);  // ACD
+    epa_push_face(E, nf, 0, 3, 1, s[0].P, cur, ci);  // ADB
+    epa_push_face(E, nf, 1, 3, 2, s[1].P, cur, ci);  // BDC
     int it = 0;
     while (it++ <= 64) {            // MAX_EPA_ITERATIONS, code/nans.h:56
         max_faces = max(max_faces, nf);
-        // closest face: first strict minimum of |d| (:807-822)
-        float cur = fabsf(E.fnd[0].w);
-        int ci = 0;
-        for (int i = 1; i < nf; ++i) {
-            const float dist = fabsf(E.fnd[i].w);
-            if (dist < cur) { cur = dist; ci = i; }
-        }
         const float4 cnd = E.fnd[ci];
         const vec3 N = face_normal_flipped(cnd);
         const GjkVertex<AS, BS> ns = calc_support<AS, BS>(S, N);
         if (fsub(dot(N, ns.P), cur) < 0.001f) {   // MAX_EPA_ERROR, code/nans.h:55
-            const uint32_t f = E.fidx[ci];
+            const float4 cpa = E.fpa[ci];
+            const uint32_t f = __float_as_uint(cpa.w);
             const int a = f & 255, b = (f >> 8) & 255, c = (f >> 16) & 255;
             // Barycentric, code/nans.cpp:772-785
             const vec3 Pp = N * cur;
-            const vec3 A0 = E.P[a];
+            const vec3 A0 = V3(cpa);
             const vec3 v0 = E.P[b] - A0, v1 = E.P[c] - A0, v2 = Pp - A0;
             const float d00 = dot(v0, v0), d01 = dot(v0, v1), d11 = dot(v1, v1);
             const float d20 = dot(v2, v0), d21 = dot(v2, v1);
@@ -285,26 +310,37 @@ __device__ __forceinline__ int epa_resolve(const NpShapes &S, const GjkVertex<AS
         }
         if (nv >= kEpaMaxVerts) { ovf |= OVF_EPA_FACES; return 0; }
         epa_store_vertex<AS, BS>(E, nv, ns);
-        // dissolve every face the new point can see (:869-891); survivors keep their order
-        int keep = 0;
+        // dissolve every face the new point can see (:869-891); survivors keep their order.  The
+        // dissolved faces are only LISTED here; their edges are pushed in a second loop, so the warp
+        // stays converged over the face scan.
+        int keep = 0, nvis = 0;
         for (int i = 0; i < nf; ++i) {
             const float4 nd = E.fnd[i];
-            const uint32_t f = E.fidx[i];
-            const int a = f & 255, b = (f >> 8) & 255, c = (f >> 16) & 255;
-            const vec3 tmp = ns.P - E.P[a];
+            const float4 pa = E.fpa[i];
+            const vec3 tmp = ns.P - V3(pa);
             if (dot(face_normal_flipped(nd), tmp) > 0.0f) {
-                epa_push_edge(E, ne, a, b, ovf);
-                epa_push_edge(E, ne, b, c, ovf);
-                epa_push_edge(E, ne, c, a, ovf);
+                E.vis[nvis++] = __float_as_uint(pa.w);
             } else {
-                if (keep != i) { E.fnd[keep] = nd; E.fidx[keep] = f; }
+                if (keep != i) { E.fnd[keep] = nd; E.fpa[keep] = pa; }
+                epa_track_min(nd.w, keep, cur, ci);
                 ++keep;
             }
         }
         nf = keep;
+        for (int j = 0; j < nvis; ++j) {
+            uint32_t f = E.vis[j];
+#pragma unroll 1
+            for (int k = 0; k < 3; ++k) {           // AB, BC, CA
+                epa_push_edge(E, ne, f & 255, (f >> 8) & 255, ovf);
+                f = (f >> 8) | ((f & 255) << 16);
+            }
+        }
         // one new face per horizon edge, in edge-list order (:894-901)
         if (nf + ne > kEpaMaxFaces) { ovf |= OVF_EPA_FACES; return 0; }
-        for (int i = 0; i < ne; ++i) epa_push_face(E, nf, nv, E.edge[i] & 255, E.edge[i] >> 8);
+        for (int i = 0; i < ne; ++i) {
+            const uint32_t ed = E.edge[i];
+            epa_push_face(E, nf, nv, ed & 255, (ed >> 8) & 255, ns.P, cur, ci);
+        }
         ne = 0;
         ++nv;
     }
