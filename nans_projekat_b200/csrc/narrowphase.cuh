@@ -31,7 +31,16 @@ enum { kNoIntersection = 0, kFoundIntersection = 1, kStillEvolving = 2 };  // ev
 #define NANS_NP_THREADS 128
 #endif
 constexpr int kNpThreads = NANS_NP_THREADS;
-constexpr int kNoVertex = 8;   // box support when every compare failed (NaN direction): vec3(0)
+constexpr int kNoVertex = 8;
+#ifndef NANS_NP_OPT_A
+#define NANS_NP_OPT_A 1   // support scan keeps (best, index) only: -2 %
+#endif
+#ifndef NANS_NP_OPT_B
+#define NANS_NP_OPT_B 1   // face scan loads the next record ahead: -1 %
+#endif
+#ifndef NANS_NP_OPT_C
+#define NANS_NP_OPT_C 0   // equivalence-class scan without early exit: +4 % (worse)
+#endif   // box support when every compare failed (NaN direction): vec3(0)
 
 // Both shapes' box vertices, transposed: g_np_verts[(24*side + 3*k + r) * kNpThreads + tid].
 // File-scope __shared__ so every access compiles to LDS/STS (a pointer carried through the call
@@ -56,9 +65,19 @@ struct NpShapes {
 __device__ __forceinline__ vec3 box_support(const NpShapes &S, int side, vec3 d, int &idx)
 {
     float best = -FLT_MAX;
-    vec3 res = V3(0.f, 0.f, 0.f);
     idx = kNoVertex;
     const float *p = g_np_verts + 24 * side * kNpThreads + threadIdx.x;
+#if NANS_NP_OPT_A
+    // keep only (best, index) while scanning; fetch the winner afterwards
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const vec3 c = V3(p[(3 * k) * kNpThreads], p[(3 * k + 1) * kNpThreads], p[(3 * k + 2) * kNpThreads]);
+        const float dist = dot(c, d);
+        if (dist > best) { best = dist; idx = k; }
+    }
+    return S.vertex(side, idx);
+#else
+    vec3 res = V3(0.f, 0.f, 0.f);
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
         const vec3 c = V3(p[(3 * k) * kNpThreads], p[(3 * k + 1) * kNpThreads], p[(3 * k + 2) * kNpThreads]);
@@ -66,6 +85,7 @@ __device__ __forceinline__ vec3 box_support(const NpShapes &S, int side, vec3 d,
         if (dist > best) { best = dist; res = c; idx = k; }
     }
     return res;
+#endif
 }
 // GetSphereSupport, code/nans.cpp:433-438
 __device__ __forceinline__ vec3 sphere_support(vec3 pos, float radius, vec3 d)
@@ -212,8 +232,13 @@ __device__ __forceinline__ void epa_store_vertex(EpaArena &E, int i, const GjkVe
     if (!equal(v.P, v.P)) {
         c = kCidNaN;
     } else {
+#if NANS_NP_OPT_C
+        for (int j = i - 1; j >= 0; --j)          // no early exit: independent loads
+            if (equal(E.P[j], v.P)) c = j;
+#else
         for (int j = 0; j < i; ++j)
             if (equal(E.P[j], v.P)) { c = j; break; }
+#endif
     }
     E.cid[i] = (uint8_t)c;
 }
@@ -314,9 +339,17 @@ __device__ __forceinline__ int epa_resolve(const NpShapes &S, const GjkVertex<AS
         // dissolved faces are only LISTED here; their edges are pushed in a second loop, so the warp
         // stays converged over the face scan.
         int keep = 0, nvis = 0;
+#if NANS_NP_OPT_B
+        float4 nd_next = E.fnd[0], pa_next = E.fpa[0];
+#endif
         for (int i = 0; i < nf; ++i) {
+#if NANS_NP_OPT_B
+            const float4 nd = nd_next, pa = pa_next;
+            if (i + 1 < nf) { nd_next = E.fnd[i + 1]; pa_next = E.fpa[i + 1]; }   // before the stores below: in flight during the test
+#else
             const float4 nd = E.fnd[i];
             const float4 pa = E.fpa[i];
+#endif
             const vec3 tmp = ns.P - V3(pa);
             if (dot(face_normal_flipped(nd), tmp) > 0.0f) {
                 E.vis[nvis++] = __float_as_uint(pa.w);
