@@ -321,7 +321,10 @@ __device__ __forceinline__ void for_each_partner(const DeviceWorld &w, const uin
 // them to their scanned offsets; a body with more partners than slots (crowded cell) is rescanned.
 constexpr int kPairSlots = 24;
 
-__global__ void __launch_bounds__(128) pair_count_kernel(DeviceWorld w, const uint32_t *__restrict__ keys)
+#ifndef NANS_PC_MINBLOCKS
+#define NANS_PC_MINBLOCKS 12   // 40 registers: 1536 threads/SM hide the probe latency best (sweep: 1/10/12/16 -> 0.69/0.66/0.64/0.71 ms)
+#endif
+__global__ void __launch_bounds__(128, NANS_PC_MINBLOCKS) pair_count_kernel(DeviceWorld w, const uint32_t *__restrict__ keys)
 {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= w.nb) return;

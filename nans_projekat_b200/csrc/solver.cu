@@ -64,7 +64,9 @@ __global__ void __launch_bounds__(256) incidence_fill_kernel(DeviceWorld w)
 }
 
 // one thread per body: order its incident contacts by list position, link successors
-__global__ void __launch_bounds__(256) schedule_kernel(DeviceWorld w)
+// versioned != 0: succ_a / succ_b receive the contact's POSITION in the body's sequence instead (the
+// number of earlier contacts touching that body = the row version the contact waits for)
+__global__ void __launch_bounds__(256) schedule_kernel(DeviceWorld w, int versioned)
 {
     const int body = blockIdx.x * blockDim.x + threadIdx.x;
     if (body >= w.nb) return;
@@ -79,9 +81,9 @@ __global__ void __launch_bounds__(256) schedule_kernel(DeviceWorld w)
     }
     for (int k = 0; k < n; ++k) {
         const int c = l[k];
-        const int next = (k + 1 < n) ? l[k + 1] : -1;
+        const int next = versioned ? k : ((k + 1 < n) ? l[k + 1] : -1);
         if (w.c_a[c] == body) w.succ_a[c] = next; else w.succ_b[c] = next;
-        if (k > 0) atomicAdd(&w.indeg[c], 1);
+        if (k > 0 && !versioned) atomicAdd(&w.indeg[c], 1);
     }
 }
 
@@ -119,7 +121,7 @@ __global__ void __launch_bounds__(256) seed_kernel(DeviceWorld w)
 // The arithmetic (operations, order, roundings) is exactly that of the single function.
 constexpr int kRecQuads = 11;   // float4 per contact record
 
-__global__ void __launch_bounds__(256) contact_prep_kernel(DeviceWorld w, float dt)
+__global__ void __launch_bounds__(256) contact_prep_kernel(DeviceWorld w, float dt, int versioned)
 {
     const int n = w.counters->n_contacts;
     const int stride = gridDim.x * blockDim.x;
@@ -171,6 +173,7 @@ __global__ void __launch_bounds__(256) contact_prep_kernel(DeviceWorld w, float 
         r[8] = make_float4(R2T2.x, R2T2.y, R2T2.z, 0.f);
         const int sa = w.succ_a[c], sb = w.succ_b[c];
         r[9] = make_float4(__int_as_float(ia), __int_as_float(ib), __int_as_float(sa), __int_as_float(sb));
+        if (versioned) continue;        // (ia, ib, position on A, position on B) is all the versioned solver needs
         // body rows of the successors, so that whoever runs a successor can issue its record loads and
         // its velocity loads in ONE round trip instead of two
         const int none = 0x7fffffff;
@@ -181,42 +184,16 @@ __global__ void __launch_bounds__(256) contact_prep_kernel(DeviceWorld w, float 
     }
 }
 
-// the velocity-dependent part.  rows = (ia, ib) if the caller already knows the body rows (chain
-// following), else kRowsUnknown; returns the successor links and the successors' body rows.
-constexpr int kRowsUnknown = 0x7fffffff;
-struct NextRows { int sa, sb, sa_ia, sa_ib, sb_ia, sb_ib; };
-
-__device__ __forceinline__ NextRows apply_prepared(const DeviceWorld &w, int c, int known_ia, int known_ib)
+// The velocity-dependent part of Constraint (code/nans.cpp:1158-1328) on the prepared record q[0..8]:
+// relative velocities, the 70-iteration accumulation, the impulses.  has_b == false: body B is the
+// Floor (V = W = 0, never written, :1278-1289).
+__device__ __forceinline__ void constraint_apply(const float4 (&q)[kRecQuads], vec3 &V1, vec3 &W1, vec3 &V2, vec3 &W2,
+                                                 bool has_b)
 {
-    const float4 *r = w.crec + (size_t)kRecQuads * c;
-    float4 q[kRecQuads];
-#pragma unroll
-    for (int k = 0; k < kRecQuads; ++k) q[k] = __ldcg(r + k);
-    int ia = known_ia, ib = known_ib;
-    if (ia == kRowsUnknown) { ia = __float_as_int(q[9].x); ib = __float_as_int(q[9].y); }   // second round trip
-    float4 va4 = __ldcg(&w.vel[ia]), wa4 = __ldcg(&w.angvel[ia]);
-    float4 vb4 = make_float4(0, 0, 0, 0), wb4 = make_float4(0, 0, 0, 0);
-    if (ib >= 0) { vb4 = __ldcg(&w.vel[ib]); wb4 = __ldcg(&w.angvel[ib]); }
-    NextRows nx;
-    nx.sa = __float_as_int(q[9].z); nx.sb = __float_as_int(q[9].w);
-    nx.sa_ia = __float_as_int(q[10].x); nx.sa_ib = __float_as_int(q[10].y);
-    nx.sb_ia = __float_as_int(q[10].z); nx.sb_ib = __float_as_int(q[10].w);
-    // the successors' records will be wanted next: pull them towards L2 while this contact computes
-    if (nx.sa >= 0) {
-        const char *p = (const char *)(w.crec + (size_t)kRecQuads * nx.sa);
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(p + 128));
-    }
-    if (nx.sb >= 0) {
-        const char *p = (const char *)(w.crec + (size_t)kRecQuads * nx.sb);
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(p + 128));
-    }
     const vec3 N = V3(q[0]), T1 = V3(q[1]), T2 = V3(q[2]);
     const float JMJn = q[0].w, JMJt1 = q[1].w, JMJt2 = q[2].w;
     const vec3 RN1 = V3(q[3]), RN2 = V3(q[4]), R1T1 = V3(q[5]), R2T1 = V3(q[6]), R1T2 = V3(q[7]), R2T2 = V3(q[8]);
     const float invM1 = q[3].w, invM2 = q[4].w, invI1 = q[5].w, invI2 = q[6].w, Bd = q[7].w;
-    vec3 V1 = V3(va4), W1 = V3(wa4), V2 = V3(vb4), W2 = V3(wb4);   // the Floor: V = W = 0 (:1278-1289)
     const vec3 dVn = ((V1 + cross(W1, N)) - V2) - cross(W2, N);
     const float JdVn = dot(dVn, N);
     const float B = fadd(Bd, fmul(0.1f, JdVn));                        // + Cr * JdVn
@@ -276,12 +253,49 @@ __device__ __forceinline__ NextRows apply_prepared(const DeviceWorld &w, int c, 
     V1 = V1 + invM1 * LI;     W1 = W1 + invI1 * AI1;
     V1 = V1 + invM1 * LIT1;   W1 = W1 + invI1 * AI1T1;
     V1 = V1 + invM1 * LIT2;   W1 = W1 + invI1 * AI1T2;
-    __stcg(&w.vel[ia], make_float4(V1.x, V1.y, V1.z, va4.w));
-    __stcg(&w.angvel[ia], make_float4(W1.x, W1.y, W1.z, wa4.w));
-    if (ib >= 0) {
+    if (has_b) {
         V2 = V2 - invM2 * LI;     W2 = W2 - invI2 * AI2;
         V2 = V2 - invM2 * LIT1;   W2 = W2 - invI2 * AI2T1;
         V2 = V2 - invM2 * LIT2;   W2 = W2 - invI2 * AI2T2;
+    }
+}
+
+// the velocity-dependent part.  rows = (ia, ib) if the caller already knows the body rows (chain
+// following), else kRowsUnknown; returns the successor links and the successors' body rows.
+constexpr int kRowsUnknown = 0x7fffffff;
+struct NextRows { int sa, sb, sa_ia, sa_ib, sb_ia, sb_ib; };
+
+__device__ __forceinline__ NextRows apply_prepared(const DeviceWorld &w, int c, int known_ia, int known_ib)
+{
+    const float4 *r = w.crec + (size_t)kRecQuads * c;
+    float4 q[kRecQuads];
+#pragma unroll
+    for (int k = 0; k < kRecQuads; ++k) q[k] = __ldcg(r + k);
+    int ia = known_ia, ib = known_ib;
+    if (ia == kRowsUnknown) { ia = __float_as_int(q[9].x); ib = __float_as_int(q[9].y); }   // second round trip
+    float4 va4 = __ldcg(&w.vel[ia]), wa4 = __ldcg(&w.angvel[ia]);
+    float4 vb4 = make_float4(0, 0, 0, 0), wb4 = make_float4(0, 0, 0, 0);
+    if (ib >= 0) { vb4 = __ldcg(&w.vel[ib]); wb4 = __ldcg(&w.angvel[ib]); }
+    NextRows nx;
+    nx.sa = __float_as_int(q[9].z); nx.sb = __float_as_int(q[9].w);
+    nx.sa_ia = __float_as_int(q[10].x); nx.sa_ib = __float_as_int(q[10].y);
+    nx.sb_ia = __float_as_int(q[10].z); nx.sb_ib = __float_as_int(q[10].w);
+    // the successors' records will be wanted next: pull them towards L2 while this contact computes
+    if (nx.sa >= 0) {
+        const char *p = (const char *)(w.crec + (size_t)kRecQuads * nx.sa);
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(p + 128));
+    }
+    if (nx.sb >= 0) {
+        const char *p = (const char *)(w.crec + (size_t)kRecQuads * nx.sb);
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(p + 128));
+    }
+    vec3 V1 = V3(va4), W1 = V3(wa4), V2 = V3(vb4), W2 = V3(wb4);   // the Floor: V = W = 0 (:1278-1289)
+    constraint_apply(q, V1, W1, V2, W2, ib >= 0);
+    __stcg(&w.vel[ia], make_float4(V1.x, V1.y, V1.z, va4.w));
+    __stcg(&w.angvel[ia], make_float4(W1.x, W1.y, W1.z, wa4.w));
+    if (ib >= 0) {
         __stcg(&w.vel[ib], make_float4(V2.x, V2.y, V2.z, vb4.w));
         __stcg(&w.angvel[ib], make_float4(W2.x, W2.y, W2.z, wb4.w));
     }
@@ -433,6 +447,118 @@ __global__ void __launch_bounds__(kFlowThreads) solve_dataflow_kernel(DeviceWorl
     if (lane == 0 && max_level) atomicMax(&w.counters->solver_levels, max_level);
 }
 
+// ---- v3: versioned body rows (default) ----------------------------------------------------------
+// The dependency of a contact on its predecessors is carried by the DATA it needs: during the solve
+// every body's velocity lives in a 16-byte row (V.xyz, version) and its angular velocity in a second
+// row (W.xyz, version | level << 20), where version = number of contacts applied to that body so
+// far.  Contact c waits until both of its bodies show the versions it was scheduled for (its
+// position in each body's contact sequence), applies itself and stores the rows with version + 1.
+// A row is one aligned 128-bit access, so value and version arrive together: no fences, no in-degree
+// atomics, no ready queue; the hop from a contact to its successor is one L2 store -> poll.
+//
+// Warps take contacts in LIST order, 32 at a time.  Progress: every contact a lane waits for is
+// earlier in the list, so its ticket is already held by a running warp; by induction the earliest
+// unfinished contact is always runnable.  (A spin cap turns any violation into an error.)
+constexpr int kVerThreads = 256;
+constexpr int kVerMask = 0xfffff;   // version bits kept in the angular row (the rest carries the DAG level)
+
+__device__ __forceinline__ float4 ld_row(const float4 *p)
+{
+    float4 v;
+    asm volatile("ld.relaxed.gpu.global.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_row(float4 *p, vec3 v, int tag)
+{
+    asm volatile("st.relaxed.gpu.global.v4.f32 [%0], {%1, %2, %3, %4};"
+                 :: "l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(__int_as_float(tag)) : "memory");
+}
+
+// rows for the solve: (vel.xyz, 0) and (angvel.xyz, 0).  They borrow the AABB arrays, which are dead
+// between detection and the next step's broadphase.
+__global__ void __launch_bounds__(256) ver_seed_kernel(DeviceWorld w)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= w.nb) return;
+    float4 v = w.vel[i], a = w.angvel[i];
+    v.w = 0.f; a.w = 0.f;
+    w.aabb_lo[i] = v;
+    w.aabb_hi[i] = a;
+}
+__global__ void __launch_bounds__(256) ver_finish_kernel(DeviceWorld w)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= w.nb) return;
+    const float4 v = w.aabb_lo[i], a = w.aabb_hi[i];
+    if (__float_as_int(v.w) == 0) return;            // untouched by any contact
+    float4 *pv = &w.vel[i], *pa = &w.angvel[i];
+    pv->x = v.x; pv->y = v.y; pv->z = v.z;          // .w keeps 1/Mass, 1/MOI
+    pa->x = a.x; pa->y = a.y; pa->z = a.z;
+}
+
+__global__ void __launch_bounds__(kVerThreads) solve_versioned_kernel(DeviceWorld w, int sleep_ns)
+{
+    const int n = w.counters->n_contacts;
+    const int lane = threadIdx.x & 31;
+    int *head = &w.counters->frontier_n[0];
+    volatile int *abort_flag = &w.counters->pad[1];
+    float4 *sv = w.aabb_lo, *sw = w.aabb_hi;
+    int max_level = 0;
+    while (true) {
+        int base = 0;
+        if (lane == 0) base = atomicAdd(head, 32);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (base >= n) break;
+        const int c = base + lane;
+        bool pending = c < n;
+        float4 q[kRecQuads];
+        int ia = 0, ib = -1, ea = 0, eb = 0;
+        if (pending) {
+            const float4 *r = w.crec + (size_t)kRecQuads * c;
+#pragma unroll
+            for (int k = 0; k < 10; ++k) q[k] = __ldg(r + k);
+            ia = __float_as_int(q[9].x); ib = __float_as_int(q[9].y);
+            ea = __float_as_int(q[9].z); eb = __float_as_int(q[9].w);
+        }
+        int spins = 0;
+        while (__any_sync(0xffffffffu, pending)) {
+            bool fired = false;
+            if (pending) {
+                const float4 va = ld_row(sv + ia), wa = ld_row(sw + ia);
+                float4 vb = make_float4(0, 0, 0, 0), wb = make_float4(0, 0, 0, 0);
+                bool ok = __float_as_int(va.w) == ea && (__float_as_int(wa.w) & kVerMask) == (ea & kVerMask);
+                if (ib >= 0) {
+                    vb = ld_row(sv + ib); wb = ld_row(sw + ib);
+                    ok = ok && __float_as_int(vb.w) == eb && (__float_as_int(wb.w) & kVerMask) == (eb & kVerMask);
+                }
+                if (ok) {
+                    vec3 V1 = V3(va), W1 = V3(wa), V2 = V3(vb), W2 = V3(wb);   // the Floor: V = W = 0
+                    constraint_apply(q, V1, W1, V2, W2, ib >= 0);
+                    int lv = __float_as_int(wa.w) >> 20;
+                    if (ib >= 0) lv = max(lv, __float_as_int(wb.w) >> 20);
+                    const int lv1 = min(lv + 1, 4095) << 20;
+                    max_level = max(max_level, lv + 1);
+                    st_row(sv + ia, V1, ea + 1);
+                    st_row(sw + ia, W1, ((ea + 1) & kVerMask) | lv1);
+                    if (ib >= 0) {
+                        st_row(sv + ib, V2, eb + 1);
+                        st_row(sw + ib, W2, ((eb + 1) & kVerMask) | lv1);
+                    }
+                    pending = false;
+                    fired = true;
+                }
+            }
+            if (!__any_sync(0xffffffffu, fired)) {
+                if (++spins > kSpinCap || *abort_flag) { *abort_flag = 1; return; }
+                if (sleep_ns) __nanosleep(sleep_ns);
+            }
+        }
+    }
+    max_level = __reduce_max_sync(0xffffffffu, max_level);
+    if (lane == 0 && max_level) atomicMax(&w.counters->solver_levels, max_level);
+}
+
 // ---- v1: level-synchronous execution (kept for A/B, NANS_SOLVER=levels) -----------------------
 constexpr int kSolveThreads = 256;
 
@@ -475,8 +601,8 @@ int launch_solver(World *w, float dt)
     cudaStream_t s = w->stream;
     static int mode = -1, sm_count = 0;
     if (mode < 0) {
-        const char *e = getenv("NANS_SOLVER");
-        mode = (e && !strcmp(e, "levels")) ? 1 : 0;
+        const char *e = getenv("NANS_SOLVER");   // versioned (default) | flow | levels
+        mode = (e && !strcmp(e, "levels")) ? 1 : (e && !strcmp(e, "flow")) ? 0 : 2;
         cudaDeviceProp prop;
         NANS_CUDA(cudaGetDeviceProperties(&prop, w->device));
         sm_count = prop.multiProcessorCount;
@@ -491,9 +617,9 @@ int launch_solver(World *w, float dt)
     if (rc) return rc;
     incidence_fill_kernel<<<grid, 256, 0, s>>>(d);
     NANS_LAUNCH_CHECK();
-    schedule_kernel<<<div_up(d.nb, 256), 256, 0, s>>>(d);
+    schedule_kernel<<<div_up(d.nb, 256), 256, 0, s>>>(d, mode == 2);
     NANS_LAUNCH_CHECK();
-    contact_prep_kernel<<<grid, 256, 0, s>>>(d, dt);
+    contact_prep_kernel<<<grid, 256, 0, s>>>(d, dt, mode == 2);
     NANS_LAUNCH_CHECK();
 
     if (mode == 1) {
@@ -506,6 +632,25 @@ int launch_solver(World *w, float dt)
         NANS_CUDA(cudaLaunchCooperativeKernel((void *)solve_levels_kernel, dim3(sm_count * w->coop_blocks_per_sm),
                                               dim3(kSolveThreads), args, 0, s));
         ++g_launches;
+        return NANS_OK;
+    }
+    if (mode == 2) {
+        static int ver_blocks = 0, ver_sleep = 0;
+        if (!ver_blocks) {
+            int per_sm = 0;
+            NANS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, solve_versioned_kernel, kVerThreads, 0));
+            const char *e;
+            int want = (e = getenv("NANS_VER_BLOCKS")) ? atoi(e) : 2;
+            if (want < 1) want = 1;
+            ver_blocks = sm_count * (want < per_sm ? want : per_sm);   // every CTA must be resident (spinning lanes)
+            ver_sleep = (e = getenv("NANS_VER_SLEEP")) ? atoi(e) : 0;
+        }
+        ver_seed_kernel<<<div_up(d.nb, 256), 256, 0, s>>>(d);
+        NANS_LAUNCH_CHECK();
+        solve_versioned_kernel<<<ver_blocks, kVerThreads, 0, s>>>(d, ver_sleep);
+        NANS_LAUNCH_CHECK();
+        ver_finish_kernel<<<div_up(d.nb, 256), 256, 0, s>>>(d);
+        NANS_LAUNCH_CHECK();
         return NANS_OK;
     }
     seed_kernel<<<grid, 256, 0, s>>>(d);
