@@ -36,7 +36,7 @@ namespace cg = cooperative_groups;
 
 namespace nans {
 
-__global__ void __launch_bounds__(256) incidence_count_kernel(DeviceWorld w)
+__global__ void __launch_bounds__(256) incidence_count_kernel(DeviceWorld w, int versioned)
 {
     const int n = w.counters->n_contacts;
     const int stride = gridDim.x * blockDim.x;
@@ -44,7 +44,8 @@ __global__ void __launch_bounds__(256) incidence_count_kernel(DeviceWorld w)
         atomicAdd(&w.deg[w.c_a[c]], 1u);
         const int b = w.c_b[c];
         if (b >= 0) atomicAdd(&w.deg[b], 1u);
-        w.indeg[c] = 0;
+        // dataflow: in-degree (filled by schedule_kernel); versioned: 1 where a run of contacts on the same body A starts
+        w.indeg[c] = (versioned && (c == 0 || w.c_a[c - 1] != w.c_a[c])) ? 1 : 0;
         w.succ_a[c] = -1;
         w.succ_b[c] = -1;
         w.frontier[0][c] = -1;   // ready queue: empty slots
@@ -121,59 +122,69 @@ __global__ void __launch_bounds__(256) seed_kernel(DeviceWorld w)
 // The arithmetic (operations, order, roundings) is exactly that of the single function.
 constexpr int kRecQuads = 11;   // float4 per contact record
 
-__global__ void __launch_bounds__(256) contact_prep_kernel(DeviceWorld w, float dt, int versioned)
+// q[0..8] of contact c (everything that does not read velocities); returns the body rows
+__device__ __forceinline__ void constraint_prepare(const DeviceWorld &w, int c, float dt, float4 (&q)[kRecQuads], int &ia, int &ib)
+{
+    const float4 cpa = w.c_pa[c], cpb = w.c_pb[c];      // w lanes carry the body rows
+    ia = __float_as_int(cpa.w); ib = __float_as_int(cpb.w);
+    const vec3 posA = V3(w.pos[ia]);
+    const float invM1 = w.vel[ia].w, invI1 = w.angvel[ia].w;
+    vec3 posB;
+    float invM2, invI2;
+    if (ib >= 0) {
+        posB = V3(w.pos[ib]);
+        invM2 = w.vel[ib].w; invI2 = w.angvel[ib].w;
+    } else {
+        const int k = -ib - 1;                 // the Floor (:1065-1077)
+        const float4 sp = w.st_pos[k], sa = w.st_ang[k];
+        posB = V3(sp);
+        invM2 = sp.w; invI2 = sa.w;
+    }
+    vec3 N = normalize(V3(w.c_n[c]));
+    if (equal(N, V3(0.f, 0.f, 0.f))) N = normalize(posB - posA);   // :1115-1119
+    const vec3 R1 = V3(cpa) - posA;
+    const vec3 R2 = V3(cpb) - posB;
+    vec3 T1;
+    if (N.x >= 0.57735f) T1 = V3(N.y, -N.x, 0.0f); else T1 = V3(0.0f, N.z, -N.y);
+    const vec3 T2 = cross(N, T1);                                    // T1 is NOT normalised (:1133)
+    const float depth = dot((posA + R1) - (posB + R2), N);
+    const vec3 RN1 = cross(R1, N), RN2 = cross(R2, N);
+    float JMJn = fadd(invM1, invM2);
+    JMJn = fadd(JMJn, fsub(fmul(invI1, dot(RN1, RN1)), fmul(invI2, dot(-RN2, -RN2))));
+    JMJn = fdiv(1.0f, JMJn);
+    const vec3 R1T1 = cross(R1, T1), R2T1 = cross(R2, T1), R1T2 = cross(R1, T2), R2T2 = cross(R2, T2);
+    float JMJt1 = fadd(invM1, invM2);
+    JMJt1 = fadd(JMJt1, fsub(fmul(invI1, dot(R1T1, R1T1)), fmul(invI2, dot(-R2T1, -R2T1))));
+    JMJt1 = fdiv(1.0f, JMJt1);
+    float JMJt2 = fadd(invM1, invM2);
+    JMJt2 = fadd(JMJt2, fsub(fmul(invI1, dot(R1T2, R1T2)), fmul(invI2, dot(-R2T2, -R2T2))));
+    JMJt2 = fdiv(1.0f, JMJt2);
+    const float Bd = fmul(fdiv(-0.3f, dt), depth);                  // (-Beta / dt) * Depth (:1156)
+    q[0] = make_float4(N.x, N.y, N.z, JMJn);
+    q[1] = make_float4(T1.x, T1.y, T1.z, JMJt1);
+    q[2] = make_float4(T2.x, T2.y, T2.z, JMJt2);
+    q[3] = make_float4(RN1.x, RN1.y, RN1.z, invM1);
+    q[4] = make_float4(RN2.x, RN2.y, RN2.z, invM2);
+    q[5] = make_float4(R1T1.x, R1T1.y, R1T1.z, invI1);
+    q[6] = make_float4(R2T1.x, R2T1.y, R2T1.z, invI2);
+    q[7] = make_float4(R1T2.x, R1T2.y, R1T2.z, Bd);
+    q[8] = make_float4(R2T2.x, R2T2.y, R2T2.z, 0.f);
+}
+
+// dataflow / levels solvers: the records go to memory, with the successor links
+__global__ void __launch_bounds__(256) contact_prep_kernel(DeviceWorld w, float dt)
 {
     const int n = w.counters->n_contacts;
     const int stride = gridDim.x * blockDim.x;
     for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < n; c += stride) {
-        const float4 cpa = w.c_pa[c], cpb = w.c_pb[c];      // w lanes carry the body rows
-        const int ia = __float_as_int(cpa.w), ib = __float_as_int(cpb.w);
-        const vec3 posA = V3(w.pos[ia]);
-        const float invM1 = w.vel[ia].w, invI1 = w.angvel[ia].w;
-        vec3 posB;
-        float invM2, invI2;
-        if (ib >= 0) {
-            posB = V3(w.pos[ib]);
-            invM2 = w.vel[ib].w; invI2 = w.angvel[ib].w;
-        } else {
-            const int k = -ib - 1;                 // the Floor (:1065-1077)
-            const float4 sp = w.st_pos[k], sa = w.st_ang[k];
-            posB = V3(sp);
-            invM2 = sp.w; invI2 = sa.w;
-        }
-        vec3 N = normalize(V3(w.c_n[c]));
-        if (equal(N, V3(0.f, 0.f, 0.f))) N = normalize(posB - posA);   // :1115-1119
-        const vec3 R1 = V3(cpa) - posA;
-        const vec3 R2 = V3(cpb) - posB;
-        vec3 T1;
-        if (N.x >= 0.57735f) T1 = V3(N.y, -N.x, 0.0f); else T1 = V3(0.0f, N.z, -N.y);
-        const vec3 T2 = cross(N, T1);                                    // T1 is NOT normalised (:1133)
-        const float depth = dot((posA + R1) - (posB + R2), N);
-        const vec3 RN1 = cross(R1, N), RN2 = cross(R2, N);
-        float JMJn = fadd(invM1, invM2);
-        JMJn = fadd(JMJn, fsub(fmul(invI1, dot(RN1, RN1)), fmul(invI2, dot(-RN2, -RN2))));
-        JMJn = fdiv(1.0f, JMJn);
-        const vec3 R1T1 = cross(R1, T1), R2T1 = cross(R2, T1), R1T2 = cross(R1, T2), R2T2 = cross(R2, T2);
-        float JMJt1 = fadd(invM1, invM2);
-        JMJt1 = fadd(JMJt1, fsub(fmul(invI1, dot(R1T1, R1T1)), fmul(invI2, dot(-R2T1, -R2T1))));
-        JMJt1 = fdiv(1.0f, JMJt1);
-        float JMJt2 = fadd(invM1, invM2);
-        JMJt2 = fadd(JMJt2, fsub(fmul(invI1, dot(R1T2, R1T2)), fmul(invI2, dot(-R2T2, -R2T2))));
-        JMJt2 = fdiv(1.0f, JMJt2);
-        const float Bd = fmul(fdiv(-0.3f, dt), depth);                  // (-Beta / dt) * Depth (:1156)
+        float4 q[kRecQuads];
+        int ia, ib;
+        constraint_prepare(w, c, dt, q, ia, ib);
         float4 *r = w.crec + (size_t)kRecQuads * c;
-        r[0] = make_float4(N.x, N.y, N.z, JMJn);
-        r[1] = make_float4(T1.x, T1.y, T1.z, JMJt1);
-        r[2] = make_float4(T2.x, T2.y, T2.z, JMJt2);
-        r[3] = make_float4(RN1.x, RN1.y, RN1.z, invM1);
-        r[4] = make_float4(RN2.x, RN2.y, RN2.z, invM2);
-        r[5] = make_float4(R1T1.x, R1T1.y, R1T1.z, invI1);
-        r[6] = make_float4(R2T1.x, R2T1.y, R2T1.z, invI2);
-        r[7] = make_float4(R1T2.x, R1T2.y, R1T2.z, Bd);
-        r[8] = make_float4(R2T2.x, R2T2.y, R2T2.z, 0.f);
+#pragma unroll
+        for (int k = 0; k < 9; ++k) r[k] = q[k];
         const int sa = w.succ_a[c], sb = w.succ_b[c];
         r[9] = make_float4(__int_as_float(ia), __int_as_float(ib), __int_as_float(sa), __int_as_float(sb));
-        if (versioned) continue;        // (ia, ib, position on A, position on B) is all the versioned solver needs
         // body rows of the successors, so that whoever runs a successor can issue its record loads and
         // its velocity loads in ONE round trip instead of two
         const int none = 0x7fffffff;
@@ -497,56 +508,115 @@ __global__ void __launch_bounds__(256) ver_finish_kernel(DeviceWorld w)
     pa->x = a.x; pa->y = a.y; pa->z = a.z;
 }
 
-__global__ void __launch_bounds__(kVerThreads) solve_versioned_kernel(DeviceWorld w, int sleep_ns)
+__device__ __forceinline__ unsigned long long global_ns()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+
+// run r = contacts [run_start[r], run_start[r + 1]) = consecutive contacts with the same body A
+__global__ void __launch_bounds__(256) run_scatter_kernel(DeviceWorld w)
 {
     const int n = w.counters->n_contacts;
+    const int stride = gridDim.x * blockDim.x;
+    int32_t *run_start = w.frontier[0];
+    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < n; c += stride) {
+        const uint32_t r = w.pair_hit_scan[c];
+        if (w.indeg[c]) run_start[r] = c;
+        if (c == n - 1) w.counters->frontier_n[1] = (int)r + w.indeg[c];   // number of runs
+    }
+}
+
+// One lane per RUN: the lane keeps body A's velocity in registers along the run and only body B's
+// rows go through memory, and the lanes of a warp fire their j-th contacts together (a lane per
+// contact left ~8 of 32 lanes active per firing: the kernel was bound by issue slots).
+// trace (debug, NANS_SOLVER_TRACE=1): per contact {fire ns, stored ns, ticket ns, polls}; frontier[1] = DAG level
+__global__ void __launch_bounds__(kVerThreads) solve_versioned_kernel(DeviceWorld w, float dt, int sleep_ns, unsigned long long *trace)
+{
+    const int n = w.counters->n_contacts;
+    const int n_runs = w.counters->frontier_n[1];
     const int lane = threadIdx.x & 31;
     int *head = &w.counters->frontier_n[0];
     volatile int *abort_flag = &w.counters->pad[1];
+    const int32_t *run_start = w.frontier[0];
     float4 *sv = w.aabb_lo, *sw = w.aabb_hi;
     int max_level = 0;
     while (true) {
         int base = 0;
         if (lane == 0) base = atomicAdd(head, 32);
         base = __shfl_sync(0xffffffffu, base, 0);
-        if (base >= n) break;
-        const int c = base + lane;
-        bool pending = c < n;
-        float4 q[kRecQuads];
-        int ia = 0, ib = -1, ea = 0, eb = 0;
+        if (base >= n_runs) break;
+        const int r = base + lane;
+        bool pending = r < n_runs;
+        int c = 0, c_end = 0;
         if (pending) {
-            const float4 *r = w.crec + (size_t)kRecQuads * c;
-#pragma unroll
-            for (int k = 0; k < 10; ++k) q[k] = __ldg(r + k);
-            ia = __float_as_int(q[9].x); ib = __float_as_int(q[9].y);
-            ea = __float_as_int(q[9].z); eb = __float_as_int(q[9].w);
+            c = run_start[r];
+            c_end = (r + 1 < n_runs) ? run_start[r + 1] : n;
         }
+        float4 q[kRecQuads];
+        int ia = 0, ib = -1, ea = 0, eb = 0, lva = 0;
+        vec3 V1 = V3(0.f, 0.f, 0.f), W1 = V3(0.f, 0.f, 0.f);
+        bool loaded = false, have_a = false;
         int spins = 0;
+        unsigned long long t_ticket = 0;
+        if (trace) t_ticket = global_ns();
         while (__any_sync(0xffffffffu, pending)) {
             bool fired = false;
             if (pending) {
-                const float4 va = ld_row(sv + ia), wa = ld_row(sw + ia);
-                float4 vb = make_float4(0, 0, 0, 0), wb = make_float4(0, 0, 0, 0);
-                bool ok = __float_as_int(va.w) == ea && (__float_as_int(wa.w) & kVerMask) == (ea & kVerMask);
-                if (ib >= 0) {
-                    vb = ld_row(sv + ib); wb = ld_row(sw + ib);
-                    ok = ok && __float_as_int(vb.w) == eb && (__float_as_int(wb.w) & kVerMask) == (eb & kVerMask);
+                if (!loaded) {
+                    // the velocity-independent part of the contact, straight into registers (no record
+                    // round trip through memory); runs while the predecessors are still at work
+                    int ra, rb;
+                    constraint_prepare(w, c, dt, q, ra, rb);
+                    ib = rb; eb = w.succ_b[c];
+                    if (!have_a) { ia = ra; ea = w.succ_a[c]; }
+                    loaded = true;
                 }
-                if (ok) {
-                    vec3 V1 = V3(va), W1 = V3(wa), V2 = V3(vb), W2 = V3(wb);   // the Floor: V = W = 0
-                    constraint_apply(q, V1, W1, V2, W2, ib >= 0);
-                    int lv = __float_as_int(wa.w) >> 20;
-                    if (ib >= 0) lv = max(lv, __float_as_int(wb.w) >> 20);
-                    const int lv1 = min(lv + 1, 4095) << 20;
-                    max_level = max(max_level, lv + 1);
-                    st_row(sv + ia, V1, ea + 1);
-                    st_row(sw + ia, W1, ((ea + 1) & kVerMask) | lv1);
-                    if (ib >= 0) {
-                        st_row(sv + ib, V2, eb + 1);
-                        st_row(sw + ib, W2, ((eb + 1) & kVerMask) | lv1);
+                if (!have_a) {
+                    const float4 va = ld_row(sv + ia), wa = ld_row(sw + ia);
+                    if (__float_as_int(va.w) == ea && (__float_as_int(wa.w) & kVerMask) == (ea & kVerMask)) {
+                        V1 = V3(va); W1 = V3(wa);
+                        lva = __float_as_int(wa.w) >> 20;
+                        have_a = true;
                     }
-                    pending = false;
-                    fired = true;
+                }
+                if (have_a) {
+                    float4 vb = make_float4(0, 0, 0, 0), wb = make_float4(0, 0, 0, 0);
+                    bool ok = true;
+                    if (ib >= 0) {
+                        vb = ld_row(sv + ib); wb = ld_row(sw + ib);
+                        ok = __float_as_int(vb.w) == eb && (__float_as_int(wb.w) & kVerMask) == (eb & kVerMask);
+                    }
+                    if (ok) {
+                        unsigned long long t_fire = 0;
+                        if (trace) t_fire = global_ns();
+                        vec3 V2 = V3(vb), W2 = V3(wb);                     // the Floor: V = W = 0
+                        constraint_apply(q, V1, W1, V2, W2, ib >= 0);
+                        int lv = lva;
+                        if (ib >= 0) lv = max(lv, __float_as_int(wb.w) >> 20);
+                        lva = min(lv + 1, 4095);
+                        max_level = max(max_level, lv + 1);
+                        if (ib >= 0) {
+                            st_row(sv + ib, V2, eb + 1);
+                            st_row(sw + ib, W2, ((eb + 1) & kVerMask) | (lva << 20));
+                        }
+                        if (trace) {
+                            trace[4 * (size_t)c] = t_fire;
+                            trace[4 * (size_t)c + 1] = global_ns();
+                            trace[4 * (size_t)c + 2] = t_ticket;
+                            trace[4 * (size_t)c + 3] = (unsigned long long)spins;
+                            w.frontier[1][c] = lv;
+                        }
+                        ++ea; ++c;
+                        loaded = false;
+                        fired = true;
+                        if (c == c_end) {          // body A leaves the run: publish it
+                            st_row(sv + ia, V1, ea);
+                            st_row(sw + ia, W1, (ea & kVerMask) | (lva << 20));
+                            pending = false;
+                        }
+                    }
                 }
             }
             if (!__any_sync(0xffffffffu, fired)) {
@@ -611,7 +681,7 @@ int launch_solver(World *w, float dt)
     NANS_CUDA(cudaMemsetAsync(d.cursor, 0, sizeof(uint32_t) * (size_t)d.nb, s));
     NANS_CUDA(cudaMemsetAsync(d.counters->frontier_n, 0, sizeof(int32_t) * 3, s));
     const int grid = min(div_up(d.max_contacts, 256), kNumSMs * 8);
-    incidence_count_kernel<<<grid, 256, 0, s>>>(d);
+    incidence_count_kernel<<<grid, 256, 0, s>>>(d, mode == 2);
     NANS_LAUNCH_CHECK();
     int rc = exclusive_scan_u32(d.deg, d.deg, d.nb + 1, d.scan_block, s);
     if (rc) return rc;
@@ -619,8 +689,10 @@ int launch_solver(World *w, float dt)
     NANS_LAUNCH_CHECK();
     schedule_kernel<<<div_up(d.nb, 256), 256, 0, s>>>(d, mode == 2);
     NANS_LAUNCH_CHECK();
-    contact_prep_kernel<<<grid, 256, 0, s>>>(d, dt, mode == 2);
-    NANS_LAUNCH_CHECK();
+    if (mode != 2) {
+        contact_prep_kernel<<<grid, 256, 0, s>>>(d, dt);
+        NANS_LAUNCH_CHECK();
+    }
 
     if (mode == 1) {
         if (!w->coop_blocks_per_sm) {
@@ -645,9 +717,16 @@ int launch_solver(World *w, float dt)
             ver_blocks = sm_count * (want < per_sm ? want : per_sm);   // every CTA must be resident (spinning lanes)
             ver_sleep = (e = getenv("NANS_VER_SLEEP")) ? atoi(e) : 0;
         }
+        rc = exclusive_scan_u32_dn((const uint32_t *)d.indeg, d.pair_hit_scan, d.max_contacts, &d.counters->n_contacts, 0,
+                                   d.scan_block, s);
+        if (rc) return rc;
+        run_scatter_kernel<<<grid, 256, 0, s>>>(d);
+        NANS_LAUNCH_CHECK();
         ver_seed_kernel<<<div_up(d.nb, 256), 256, 0, s>>>(d);
         NANS_LAUNCH_CHECK();
-        solve_versioned_kernel<<<ver_blocks, kVerThreads, 0, s>>>(d, ver_sleep);
+        static int ver_trace = -1;
+        if (ver_trace < 0) ver_trace = getenv("NANS_SOLVER_TRACE") ? 1 : 0;
+        solve_versioned_kernel<<<ver_blocks, kVerThreads, 0, s>>>(d, dt, ver_sleep, ver_trace ? (unsigned long long *)d.pair_out : nullptr);
         NANS_LAUNCH_CHECK();
         ver_finish_kernel<<<div_up(d.nb, 256), 256, 0, s>>>(d);
         NANS_LAUNCH_CHECK();

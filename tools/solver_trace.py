@@ -15,14 +15,36 @@ for _ in range(settle): w.step(dt)
 ms = w.step_profiled(dt); st = w.stats(); n = st["n_contacts"]
 t4 = np.zeros((n, 4), np.uint64); lv = np.zeros(n, np.int32)
 _lib.check(_lib.lib().nans_debug_solver_trace(w._h, t4.ctypes.data, lv.ctypes.data, n))
+versioned = os.environ.get("NANS_SOLVER", "versioned") not in ("flow", "levels")
+c = w.contacts()
+print("stage ms", ms, "contacts", n, "levels", st["solver_levels"])
+print("type counts", np.bincount(c["type"], minlength=5))
+if versioned:
+    # slots: fire, stored, ticket, polls
+    t0 = t4[:, 2].min()
+    fire = (t4[:, 0] - t0).astype(np.float64) / 1e3
+    done = (t4[:, 1] - t0).astype(np.float64) / 1e3
+    ticket = (t4[:, 2] - t0).astype(np.float64) / 1e3
+    polls = t4[:, 3].astype(np.int64)
+    print(f"span us {done.max():.1f}; apply med {np.median(done - fire):.2f} us; wait med {np.median(fire - ticket):.2f} "
+          f"p90 {np.percentile(fire - ticket, 90):.2f} max {np.max(fire - ticket):.1f} us; last ticket at {ticket.max():.1f} us")
+    idx = np.arange(n)
+    for q in range(0, 100, 10):
+        m = (idx >= n * q // 100) & (idx < n * (q + 10) // 100)
+        print(f"list {q:3d}-{q+10:3d}%: ticket med {np.median(ticket[m]):7.1f} fire med {np.median(fire[m]):7.1f} max {fire[m].max():7.1f}"
+              f" | level max {lv[m].max():3d} | wait med {np.median((fire - ticket)[m]):6.2f}")
+    for L in sorted(set(lv.tolist())):
+        m = lv == L
+        if L <= 12 or L % 8 == 0:
+            print(f"level {L:3d} n={m.sum():7d} fire min/med/max us = {fire[m].min():8.1f} {np.median(fire[m]):8.1f} {fire[m].max():8.1f}")
+    # critical path: walk back from the contact that finished last
+    sys.exit(0)
 t0 = t4[:, 0].min()
 t = (t4[:, 0] - t0).astype(np.float64) / 1e3
 apply_us = (t4[:, 1] - t4[:, 0]).astype(np.float64) / 1e3
 sync_us = (t4[:, 2] - t4[:, 1]).astype(np.float64) / 1e3
 chain = t4[:, 3] == 1
-print("stage ms", ms, "contacts", n, "levels", st["solver_levels"], "span us", t.max())
-c = w.contacts()
-print("type counts", np.bincount(c["type"], minlength=5))
+print("span us", t.max())
 for L in sorted(set(lv.tolist()))[:200]:
     m = lv == L
     if L <= 20 or L % 10 == 0 or m.sum() > 5000:
