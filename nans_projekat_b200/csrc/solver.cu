@@ -225,24 +225,47 @@ __device__ __forceinline__ void constraint_apply(const float4 (&q)[kRecQuads], v
     float DLN = 0.f, sumN = 0.f, DLT1 = 0.f, sumT1 = 0.f, DLT2 = 0.f, sumT2 = 0.f;
     constexpr int kBlk = 10;
     float bound[kBlk], bound_next[kBlk];
-    auto normal_step = [&]() -> float {
-        const float oldN = sumN;
-        sumN = fadd(sumN, lambdaN);
-        if (sumN < 0) sumN = 0.0f;
-        DLN = fsub(sumN, oldN);
-        return __double2float_rn(__dmul_rn(kFric, (double)sumN));
-    };
+    if (lambdaN == lambdaN && lambdaT1 == lambdaT1 && lambdaT2 == lambdaT2) {
+        // No NaN among the increments: then no sum is ever NaN and none is ever -0.0 where it matters, so
+        //   if (s < lo) s = lo; if (s > hi) s = hi;   ==   fminf(fmaxf(s, lo), hi)
+        // bit for bit (a NaN BOUND leaves s alone in both forms; max(+0,-0) = +0 and min(-0,+0) = -0 are
+        // what the compares leave too).  Half the instructions and a shorter chain per iteration; only the
+        // last iteration's deltas are ever used, so they are formed after the loop.
+        float oldN = 0.f, oldT1 = 0.f, oldT2 = 0.f;
+        auto normal_step = [&]() -> float {
+            oldN = sumN;
+            sumN = fmaxf(fadd(sumN, lambdaN), 0.0f);
+            return __double2float_rn(__dmul_rn(kFric, (double)sumN));
+        };
 #pragma unroll
-    for (int j = 0; j < kBlk; ++j) bound_next[j] = normal_step();
+        for (int j = 0; j < kBlk; ++j) bound_next[j] = normal_step();
 #pragma unroll 1
-    for (int blk = 0; blk < 70 / kBlk; ++blk) {
+        for (int blk = 0; blk < 70 / kBlk; ++blk) {
 #pragma unroll
-        for (int j = 0; j < kBlk; ++j) bound[j] = bound_next[j];
-        const bool more = blk + 1 < 70 / kBlk;
+            for (int j = 0; j < kBlk; ++j) bound[j] = bound_next[j];
+            const bool more = blk + 1 < 70 / kBlk;
 #pragma unroll
-        for (int j = 0; j < kBlk; ++j) {
-            if (more) bound_next[j] = normal_step();
-            const float maxT = bound[j];
+            for (int j = 0; j < kBlk; ++j) {
+                if (more) bound_next[j] = normal_step();
+                const float maxT = bound[j];
+                oldT1 = sumT1;
+                sumT1 = fminf(fmaxf(fadd(sumT1, lambdaT1), -maxT), maxT);
+                oldT2 = sumT2;
+                sumT2 = fminf(fmaxf(fadd(sumT2, lambdaT2), -maxT), maxT);
+            }
+        }
+        DLN = fsub(sumN, oldN);
+        DLT1 = fsub(sumT1, oldT1);
+        DLT2 = fsub(sumT2, oldT2);
+    } else {
+        // the reference's compares, literally (NaN increments poison the sums)
+#pragma unroll 1
+        for (int it = 0; it < 70; ++it) {
+            const float oldN = sumN;
+            sumN = fadd(sumN, lambdaN);
+            if (sumN < 0) sumN = 0.0f;
+            DLN = fsub(sumN, oldN);
+            const float maxT = __double2float_rn(__dmul_rn(kFric, (double)sumN));
             const float oldT1 = sumT1;
             sumT1 = fadd(sumT1, lambdaT1);
             if (sumT1 < -maxT) sumT1 = -maxT;
