@@ -555,7 +555,7 @@ __global__ void __launch_bounds__(256) run_scatter_kernel(DeviceWorld w)
 // rows go through memory, and the lanes of a warp fire their j-th contacts together (a lane per
 // contact left ~8 of 32 lanes active per firing: the kernel was bound by issue slots).
 // trace (debug, NANS_SOLVER_TRACE=1): per contact {fire ns, stored ns, ticket ns, polls}; frontier[1] = DAG level
-__global__ void __launch_bounds__(kVerThreads) solve_versioned_kernel(DeviceWorld w, float dt, int sleep_ns, unsigned long long *trace)
+__global__ void __launch_bounds__(kVerThreads) solve_versioned_kernel(DeviceWorld w, float dt, int sleep_ns, int patience, unsigned long long *trace)
 {
     const int n = w.counters->n_contacts;
     const int n_runs = w.counters->frontier_n[1];
@@ -580,8 +580,9 @@ __global__ void __launch_bounds__(kVerThreads) solve_versioned_kernel(DeviceWorl
         float4 q[kRecQuads];
         int ia = 0, ib = -1, ea = 0, eb = 0, lva = 0;
         vec3 V1 = V3(0.f, 0.f, 0.f), W1 = V3(0.f, 0.f, 0.f);
-        bool loaded = false, have_a = false;
-        int spins = 0;
+        bool loaded = false, have_a = false, have_b = false;
+        float4 vb4 = make_float4(0, 0, 0, 0), wb4 = make_float4(0, 0, 0, 0);
+        int spins = 0, held = 0;
         unsigned long long t_ticket = 0;
         if (trace) t_ticket = global_ns();
         while (__any_sync(0xffffffffu, pending)) {
@@ -596,52 +597,61 @@ __global__ void __launch_bounds__(kVerThreads) solve_versioned_kernel(DeviceWorl
                     if (!have_a) { ia = ra; ea = w.succ_a[c]; }
                     loaded = true;
                 }
-                if (!have_a) {
-                    const float4 va = ld_row(sv + ia), wa = ld_row(sw + ia);
-                    if (__float_as_int(va.w) == ea && (__float_as_int(wa.w) & kVerMask) == (ea & kVerMask)) {
-                        V1 = V3(va); W1 = V3(wa);
-                        lva = __float_as_int(wa.w) >> 20;
-                        have_a = true;
-                    }
+                // all outstanding rows in ONE round trip (the hop latency is what bounds the solve)
+                const bool need_a = !have_a, need_b = !have_b && ib >= 0;
+                float4 va, wa;
+                if (need_a) { va = ld_row(sv + ia); wa = ld_row(sw + ia); }
+                if (need_b) { vb4 = ld_row(sv + ib); wb4 = ld_row(sw + ib); }
+                if (need_a && __float_as_int(va.w) == ea && (__float_as_int(wa.w) & kVerMask) == (ea & kVerMask)) {
+                    V1 = V3(va); W1 = V3(wa);
+                    lva = __float_as_int(wa.w) >> 20;
+                    have_a = true;
                 }
-                if (have_a) {
-                    float4 vb = make_float4(0, 0, 0, 0), wb = make_float4(0, 0, 0, 0);
-                    bool ok = true;
-                    if (ib >= 0) {
-                        vb = ld_row(sv + ib); wb = ld_row(sw + ib);
-                        ok = __float_as_int(vb.w) == eb && (__float_as_int(wb.w) & kVerMask) == (eb & kVerMask);
-                    }
-                    if (ok) {
-                        unsigned long long t_fire = 0;
-                        if (trace) t_fire = global_ns();
-                        vec3 V2 = V3(vb), W2 = V3(wb);                     // the Floor: V = W = 0
-                        constraint_apply(q, V1, W1, V2, W2, ib >= 0);
-                        int lv = lva;
-                        if (ib >= 0) lv = max(lv, __float_as_int(wb.w) >> 20);
-                        lva = min(lv + 1, 4095);
-                        max_level = max(max_level, lv + 1);
-                        if (ib >= 0) {
-                            st_row(sv + ib, V2, eb + 1);
-                            st_row(sw + ib, W2, ((eb + 1) & kVerMask) | (lva << 20));
-                        }
-                        if (trace) {
-                            trace[4 * (size_t)c] = t_fire;
-                            trace[4 * (size_t)c + 1] = global_ns();
-                            trace[4 * (size_t)c + 2] = t_ticket;
-                            trace[4 * (size_t)c + 3] = (unsigned long long)spins;
-                            w.frontier[1][c] = lv;
-                        }
-                        ++ea; ++c;
-                        loaded = false;
-                        fired = true;
-                        if (c == c_end) {          // body A leaves the run: publish it
-                            st_row(sv + ia, V1, ea);
-                            st_row(sw + ia, W1, (ea & kVerMask) | (lva << 20));
-                            pending = false;
-                        }
-                    }
+                if (need_b) have_b = __float_as_int(vb4.w) == eb && (__float_as_int(wb4.w) & kVerMask) == (eb & kVerMask);
+                if (ib < 0) have_b = true;
+            }
+            // Fire when every lane that still has work is ready, or when the ready ones have waited
+            // `patience` polls: a firing costs the warp ~1000 issue slots however few lanes take part,
+            // and the lanes of a chunk become ready within a few hundred ns of each other.
+            const bool ready = pending && have_a && have_b;
+            const unsigned rm = __ballot_sync(0xffffffffu, ready), pm = __ballot_sync(0xffffffffu, pending);
+            bool go = false;
+            if (rm) {
+                go = rm == pm || held >= patience;
+                held = go ? 0 : held + 1;
+            }
+            if (go && ready) {
+                unsigned long long t_fire = 0;
+                long long ck = 0;
+                if (trace) { t_fire = global_ns(); ck = clock64(); }
+                vec3 V2 = V3(vb4), W2 = V3(wb4);                     // the Floor: V = W = 0
+                constraint_apply(q, V1, W1, V2, W2, ib >= 0);
+                int lv = lva;
+                if (ib >= 0) lv = max(lv, __float_as_int(wb4.w) >> 20);
+                lva = min(lv + 1, 4095);
+                max_level = max(max_level, lv + 1);
+                if (ib >= 0) {
+                    st_row(sv + ib, V2, eb + 1);
+                    st_row(sw + ib, W2, ((eb + 1) & kVerMask) | (lva << 20));
+                }
+                if (trace) {
+                    trace[4 * (size_t)c] = t_fire;
+                    trace[4 * (size_t)c + 1] = global_ns();
+                    trace[4 * (size_t)c + 2] = t_ticket;
+                    trace[4 * (size_t)c + 3] = (unsigned long long)(clock64() - ck);   // cycles: apply + row stores
+                    w.frontier[1][c] = lv;
+                }
+                ++ea; ++c;
+                loaded = false;
+                have_b = false;
+                vb4 = make_float4(0, 0, 0, 0); wb4 = make_float4(0, 0, 0, 0);
+                if (c == c_end) {          // body A leaves the run: publish it
+                    st_row(sv + ia, V1, ea);
+                    st_row(sw + ia, W1, (ea & kVerMask) | (lva << 20));
+                    pending = false;
                 }
             }
+            fired = go;
             if (!__any_sync(0xffffffffu, fired)) {
                 if (++spins > kSpinCap || *abort_flag) { *abort_flag = 1; return; }
                 if (sleep_ns) __nanosleep(sleep_ns);
@@ -730,7 +740,7 @@ int launch_solver(World *w, float dt)
         return NANS_OK;
     }
     if (mode == 2) {
-        static int ver_blocks = 0, ver_sleep = 0;
+        static int ver_blocks = 0, ver_sleep = 0, ver_patience = 0;
         if (!ver_blocks) {
             int per_sm = 0;
             NANS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, solve_versioned_kernel, kVerThreads, 0));
@@ -739,6 +749,7 @@ int launch_solver(World *w, float dt)
             if (want < 1) want = 1;
             ver_blocks = sm_count * (want < per_sm ? want : per_sm);   // every CTA must be resident (spinning lanes)
             ver_sleep = (e = getenv("NANS_VER_SLEEP")) ? atoi(e) : 0;
+            ver_patience = (e = getenv("NANS_VER_PATIENCE")) ? atoi(e) : 0;   // sweep: every poll of patience costs ~50 us (latency-bound)
         }
         rc = exclusive_scan_u32_dn((const uint32_t *)d.indeg, d.pair_hit_scan, d.max_contacts, &d.counters->n_contacts, 0,
                                    d.scan_block, s);
@@ -749,7 +760,7 @@ int launch_solver(World *w, float dt)
         NANS_LAUNCH_CHECK();
         static int ver_trace = -1;
         if (ver_trace < 0) ver_trace = getenv("NANS_SOLVER_TRACE") ? 1 : 0;
-        solve_versioned_kernel<<<ver_blocks, kVerThreads, 0, s>>>(d, dt, ver_sleep, ver_trace ? (unsigned long long *)d.pair_out : nullptr);
+        solve_versioned_kernel<<<ver_blocks, kVerThreads, 0, s>>>(d, dt, ver_sleep, ver_patience, ver_trace ? (unsigned long long *)d.pair_out : nullptr);
         NANS_LAUNCH_CHECK();
         ver_finish_kernel<<<div_up(d.nb, 256), 256, 0, s>>>(d);
         NANS_LAUNCH_CHECK();

@@ -25,7 +25,16 @@ if versioned:
     fire = (t4[:, 0] - t0).astype(np.float64) / 1e3
     done = (t4[:, 1] - t0).astype(np.float64) / 1e3
     ticket = (t4[:, 2] - t0).astype(np.float64) / 1e3
-    polls = t4[:, 3].astype(np.int64)
+    cyc = t4[:, 3].astype(np.int64)
+    print(f"apply cycles (clock64): med {np.median(cyc):.0f} p10 {np.percentile(cyc, 10):.0f} p90 {np.percentile(cyc, 90):.0f}")
+    # hop latency along the deepest chains: fire time of a level-L contact minus the latest fire of level L-1 is
+    # not available per edge, so report the slope of the per-level minimum fire time instead
+    lvs = np.array(sorted(set(lv.tolist())))
+    fmin = np.array([fire[lv == L].min() for L in lvs])
+    if len(lvs) > 20:
+        k = len(lvs) // 2
+        print(f"per-level slope (min fire time): first half {(fmin[k] - fmin[0]) / (lvs[k] - lvs[0]):.2f} us/level, "
+              f"second half {(fmin[-1] - fmin[k]) / (lvs[-1] - lvs[k]):.2f} us/level")
     print(f"span us {done.max():.1f}; apply med {np.median(done - fire):.2f} us; wait med {np.median(fire - ticket):.2f} "
           f"p90 {np.percentile(fire - ticket, 90):.2f} max {np.max(fire - ticket):.1f} us; last ticket at {ticket.max():.1f} us")
     idx = np.arange(n)
