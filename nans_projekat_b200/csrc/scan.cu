@@ -1,6 +1,9 @@
 // scan.cu — exclusive prefix sum over uint32 (pair offsets, hit compaction, incidence offsets).
-// Three phases: per-tile reduce -> single-block scan of tile sums -> per-tile scan + offset.
-// HBM-bound: reads n twice, writes n once (12 B/element); tiles of 4096 keep loads 16 B wide.
+// Default: single pass with decoupled look-back (8 B/element, one launch).  The first version —
+// three phases: per-tile reduce -> single-block scan of tile sums -> per-tile scan + offset
+// (12 B/element, three launches) — is kept for A/B runs (NANS_SCAN_3PASS=1).
+#include <stdlib.h>
+
 #include "world.cuh"
 
 namespace nans {
@@ -99,7 +102,121 @@ __global__ void __launch_bounds__(kScanThreads) scan_apply_kernel(const uint32_t
     }
 }
 
-int scan_scratch_elems(int n) { return div_up(n, kScanTile) + 1; }
+// ---- single pass: decoupled look-back ------------------------------------------------------------
+// One kernel per scan, n read once and written once (8 B/element).  Tiles take their index from a
+// ticket counter (so every tile a block waits on is already running), publish {epoch, status, value}
+// as ONE 64-bit word (status 1 = tile aggregate, 2 = inclusive prefix) and look back over their
+// predecessors 32 descriptors at a time.  The epoch lives in device memory and is advanced by the
+// last block to finish, so stale descriptors never need clearing and the launch replays unchanged
+// inside a CUDA graph.  scratch: [0] ticket, [1] epoch, [2] finished blocks, [4..] descriptors.
+constexpr int kLbThreads = 256;
+constexpr int kLbItems = 16;
+constexpr int kLbTile = kLbThreads * kLbItems;   // 4096
+
+__device__ __forceinline__ unsigned long long lb_pack(uint32_t epoch, uint32_t status, uint32_t value)
+{
+    return ((unsigned long long)((epoch << 2) | status) << 32) | value;
+}
+
+__global__ void __launch_bounds__(kLbThreads) scan_lookback_kernel(const uint32_t *in, uint32_t *out, int n,
+                                                                   const int32_t *__restrict__ d_n, int extra,
+                                                                   uint32_t *scratch)
+{
+    __shared__ uint32_t s_tile, s_epoch, s_prefix;
+    volatile unsigned long long *desc = reinterpret_cast<volatile unsigned long long *>(scratch + 4);
+    if (d_n) n = min(n, *d_n + extra);
+    if (threadIdx.x == 0) {
+        s_epoch = *(volatile uint32_t *)(scratch + 1);
+        s_tile = atomicAdd(scratch, 1u);
+    }
+    __syncthreads();
+    const uint32_t tile = s_tile, epoch = s_epoch;
+    const int n_tiles = n > 0 ? (n + kLbTile - 1) / kLbTile : 0;
+    if ((int)tile < n_tiles) {
+        const int base = (int)tile * kLbTile + threadIdx.x * kLbItems;
+        uint32_t v[kLbItems];
+        if (base + kLbItems <= n) {
+            const uint4 *p = reinterpret_cast<const uint4 *>(in + base);
+#pragma unroll
+            for (int k = 0; k < kLbItems / 4; ++k) {
+                const uint4 t = p[k];
+                v[4 * k] = t.x; v[4 * k + 1] = t.y; v[4 * k + 2] = t.z; v[4 * k + 3] = t.w;
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < kLbItems; ++k) v[k] = base + k < n ? in[base + k] : 0u;
+        }
+        uint32_t s = 0;
+#pragma unroll
+        for (int k = 0; k < kLbItems; ++k) s += v[k];
+        uint32_t total;
+        uint32_t ex = block_excl_scan(s, &total);
+        if (tile == 0) {
+            if (threadIdx.x == 0) { desc[0] = lb_pack(epoch, 2u, total); s_prefix = 0u; }
+        } else {
+            if (threadIdx.x == 0) desc[tile] = lb_pack(epoch, 1u, total);
+            if (threadIdx.x < 32) {
+                const int lane = threadIdx.x;
+                int look = (int)tile - 1;
+                uint32_t acc = 0;
+                while (true) {
+                    const int idx = look - lane;
+                    unsigned long long d;
+                    bool ok;
+                    do {   // until the 32 descriptors in view are all of this epoch
+                        d = idx >= 0 ? desc[idx] : lb_pack(epoch, 2u, 0u);
+                        const uint32_t tag = (uint32_t)(d >> 32);
+                        ok = (tag >> 2) == epoch && (tag & 3u) != 0u;
+                    } while (!__all_sync(0xffffffffu, ok));
+                    const uint32_t val = (uint32_t)d;
+                    const unsigned pm = __ballot_sync(0xffffffffu, ((uint32_t)(d >> 32) & 3u) == 2u);
+                    // lanes up to (and including) the nearest inclusive prefix contribute
+                    const int stop = pm ? __ffs(pm) - 1 : 31;
+                    acc += __reduce_add_sync(0xffffffffu, lane <= stop ? val : 0u);
+                    if (pm) break;
+                    look -= 32;
+                }
+                if (lane == 0) {
+                    s_prefix = acc;
+                    desc[tile] = lb_pack(epoch, 2u, acc + total);
+                }
+            }
+        }
+        __syncthreads();
+        ex += s_prefix;
+        if (base + kLbItems <= n) {
+            uint4 *q = reinterpret_cast<uint4 *>(out + base);
+#pragma unroll
+            for (int k = 0; k < kLbItems / 4; ++k) {
+                uint4 t;
+                t.x = ex; ex += v[4 * k];
+                t.y = ex; ex += v[4 * k + 1];
+                t.z = ex; ex += v[4 * k + 2];
+                t.w = ex; ex += v[4 * k + 3];
+                q[k] = t;
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < kLbItems; ++k) {
+                if (base + k < n) out[base + k] = ex;
+                ex += v[k];
+            }
+        }
+    }
+    // the last block to finish re-arms the scratch for the next scan
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        if (atomicAdd(scratch + 2, 1u) == gridDim.x - 1) {
+            scratch[0] = 0u;
+            scratch[2] = 0u;
+            __threadfence();
+            *(volatile uint32_t *)(scratch + 1) = (epoch + 1u) & 0x3fffffffu;
+        }
+    }
+}
+
+int scan_scratch_elems(int n) { return 2 * div_up(n, kLbTile) + 8; }
 
 // out[i] = sum(in[0..i)) for i in [0, n).  in == out allowed.  To also get the grand total,
 // scan n+1 elements with in[n] = 0.
@@ -114,7 +231,14 @@ int exclusive_scan_u32_dn(const uint32_t *in, uint32_t *out, int cap_n, const in
                           uint32_t *block_scratch, cudaStream_t s)
 {
     if (cap_n <= 0) return NANS_OK;
+    static int three_pass = -1;
+    if (three_pass < 0) three_pass = getenv("NANS_SCAN_3PASS") ? 1 : 0;
     const int tiles = div_up(cap_n, kScanTile);
+    if (!three_pass) {
+        scan_lookback_kernel<<<div_up(cap_n, kLbTile), kLbThreads, 0, s>>>(in, out, cap_n, d_n, extra, block_scratch);
+        NANS_LAUNCH_CHECK();
+        return NANS_OK;
+    }
     scan_reduce_kernel<<<tiles, kScanThreads, 0, s>>>(in, cap_n, block_scratch, d_n, extra);
     NANS_LAUNCH_CHECK();
     scan_tiles_kernel<<<1, kScanThreads, 0, s>>>(block_scratch, tiles);
