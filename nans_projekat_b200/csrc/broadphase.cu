@@ -316,40 +316,77 @@ __device__ __forceinline__ void for_each_partner(const DeviceWorld &w, const uin
             }
 }
 
-// One neighbourhood scan per body: counts per (type, body) AND the partners themselves, parked in
-// a fixed-stride slot buffer (kPairSlots per body, tagged seg<<28 | row).  The emit pass only moves
-// them to their scanned offsets; a body with more partners than slots (crowded cell) is rescanned.
+// The counting pass yields counts per (type, body) AND the partners themselves, parked in a
+// fixed-stride slot buffer (kPairSlots per body, tagged seg<<28 | row).  The emit pass only moves
+// them to their scanned offsets; a body with more partners than slots (crowded cell) is rescanned
+// there with the full 27-cell walk (for_each_partner).
 constexpr int kPairSlots = 24;
 
 #ifndef NANS_PC_MINBLOCKS
 #define NANS_PC_MINBLOCKS 12   // 40 registers: 1536 threads/SM hide the probe latency best (sweep: 1/10/12/16 -> 0.69/0.66/0.64/0.71 ms)
 #endif
-__global__ void __launch_bounds__(128, NANS_PC_MINBLOCKS) pair_count_kernel(DeviceWorld w, const uint32_t *__restrict__ keys)
+
+// Every unordered pair of dynamic bodies is looked at ONCE: a body scans the rest of its own cell
+// (sorted positions after its own) and the 13 neighbour cells that follow its cell in (z, y, x)
+// order — half the hash probes and half the AABB loads of a full 27-cell scan.  A hit is credited
+// to the body the reference lists it under (lower cube / the cube of a cube-sphere pair / lower
+// sphere), whichever of the two found it: per-(type, body) counts and the slot cursor are atomics,
+// the slot order is arbitrary (the emit pass sorts every run by partner).
+__global__ void __launch_bounds__(128, NANS_PC_MINBLOCKS) pair_count_kernel(DeviceWorld w, const uint32_t *__restrict__ keys,
+                                                                            uint32_t *__restrict__ fill)
 {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= w.nb) return;
     const float4 alo = w.sbox[2 * (size_t)t], ahi = w.sbox[2 * (size_t)t + 1];
     const int row = __float_as_int(alo.w);
-    uint32_t cnt[5] = {0, 0, 0, 0, 0};
-    uint32_t filled = 0;
-    uint32_t *slots = w.pair_tmp + (size_t)t * kPairSlots;
-    if (row >= w.n_owned) {   // slab mode: a ghost's pairs belong to its owner rank
-#pragma unroll
-        for (int s = 0; s < 5; ++s) w.pair_count[(size_t)s * w.nb + row] = 0;
-        return;
+    const int wid = __float_as_int(ahi.w);
+    const bool a_cube = row < w.n_cubes;
+    const uint32_t key = keys[t];
+
+    auto visit = [&](uint32_t u) {
+        const float4 blo = __ldg(&w.sbox[2 * (size_t)u]), bhi = __ldg(&w.sbox[2 * (size_t)u + 1]);
+        if (__float_as_int(bhi.w) != wid) return;
+        if (!overlap(alo, ahi, blo, bhi)) return;
+        const int brow = __float_as_int(blo.w);
+        const bool b_cube = brow < w.n_cubes;
+        // owner = the body the pair is listed under; cube-sphere pairs are cube-major
+        const bool mine = (a_cube == b_cube) ? row < brow : a_cube;
+        const int orow = mine ? row : brow, prow = mine ? brow : row;
+        const uint32_t ot = mine ? (uint32_t)t : u;
+        if (orow >= w.n_owned) return;          // slab mode: a ghost's pairs belong to its owner rank
+        const int seg = (a_cube && b_cube) ? SEG_CC : (a_cube != b_cube) ? SEG_CS : SEG_SS;
+        atomicAdd(&w.pair_count[(size_t)seg * w.nb + orow], 1u);
+        const uint32_t slot = atomicAdd(&fill[ot], 1u);
+        if (slot < (uint32_t)kPairSlots) w.pair_tmp[(size_t)ot * kPairSlots + slot] = ((uint32_t)seg << 28) | (uint32_t)prow;
+    };
+
+    // the rest of the own cell
+    for (uint32_t u = (uint32_t)t + 1; u < (uint32_t)w.nb && keys[u] == key; ++u) visit(u);
+    // the 13 cells after it
+    const int cx = (int)compact_bits10(key >> 2), cy = (int)compact_bits10(key >> 1), cz = (int)compact_bits10(key);
+    const uint32_t ex0 = expand_bits10((uint32_t)(cx - 1)) << 2, ex1 = expand_bits10((uint32_t)cx) << 2,
+                   ex2 = expand_bits10((uint32_t)(cx + 1)) << 2;
+    const uint32_t ey0 = expand_bits10((uint32_t)(cy - 1)) << 1, ey1 = expand_bits10((uint32_t)cy) << 1,
+                   ey2 = expand_bits10((uint32_t)(cy + 1)) << 1;
+    const uint32_t ez1 = expand_bits10((uint32_t)cz), ez2 = expand_bits10((uint32_t)(cz + 1));
+    for (int k = 14; k < 27; ++k) {             // k = (dz+1)*9 + (dy+1)*3 + (dx+1), after the centre (13)
+        const int dx = k % 3 - 1, dy = (k / 3) % 3 - 1, dz = k / 9 - 1;
+        const int nx = cx + dx, ny = cy + dy, nz = cz + dz;
+        if ((unsigned)nx > 1023u || (unsigned)ny > 1023u || (unsigned)nz > 1023u) continue;
+        const uint32_t nkey = (dx < 0 ? ex0 : dx == 0 ? ex1 : ex2) | (dy < 0 ? ey0 : dy == 0 ? ey1 : ey2) |
+                              (dz == 0 ? ez1 : ez2);
+        uint32_t s, e;
+        if (!cell_lookup(w, nkey, s, e)) continue;
+        for (uint32_t u = s; u < e; ++u) visit(u);
     }
-    for_each_partner(w, keys, t, [&](int seg, int brow) {
-        cnt[seg]++;
-        if (filled < (uint32_t)kPairSlots) slots[filled] = ((uint32_t)seg << 28) | (uint32_t)brow;
-        ++filled;
-    });
-    // statics: CF for cubes, SF for spheres, static index ascending (recomputed in the emit pass)
-    uint32_t ns = 0;
-    for (int k = 0; k < w.n_statics; ++k)
-        if (overlap(alo, ahi, w.st_aabb[2 * k], w.st_aabb[2 * k + 1])) ++ns;
-    cnt[row < w.n_cubes ? SEG_CF : SEG_SF] = ns;
-#pragma unroll
-    for (int s = 0; s < 5; ++s) w.pair_count[(size_t)s * w.nb + row] = cnt[s];
+    // statics: CF for cubes, SF for spheres, static index ascending (recomputed in the emit pass);
+    // only the body itself writes these two segments
+    if (row < w.n_owned) {
+        uint32_t ns = 0;
+        for (int k = 0; k < w.n_statics; ++k)
+            if (overlap(alo, ahi, w.st_aabb[2 * k], w.st_aabb[2 * k + 1])) ++ns;
+        w.pair_count[(size_t)(a_cube ? SEG_CF : SEG_SF) * w.nb + row] = ns;
+    }
 }
 
 __global__ void __launch_bounds__(128) pair_emit_kernel(DeviceWorld w, const uint32_t *__restrict__ keys)
@@ -449,9 +486,11 @@ int launch_broadphase(World *w)
     NANS_CUDA(cudaMemsetAsync(d.cell_tab, 0xff, sizeof(uint4) * ((size_t)d.cell_mask + 1), s));
     gather_sorted_kernel<<<div_up(nb, 256), 256, 0, s>>>(d, d.key[0], d.val[0]);
     NANS_LAUNCH_CHECK();
-    pair_count_kernel<<<div_up(nb, 128), 128, 0, s>>>(d, d.key[0]);
+    // counts and slot cursors are accumulated with atomics; the cursors borrow the sort's spare key buffer
+    NANS_CUDA(cudaMemsetAsync(d.pair_count, 0, sizeof(uint32_t) * ((size_t)5 * nb + 1), s));
+    NANS_CUDA(cudaMemsetAsync(d.key[1], 0, sizeof(uint32_t) * (size_t)nb, s));
+    pair_count_kernel<<<div_up(nb, 128), 128, 0, s>>>(d, d.key[0], d.key[1]);
     NANS_LAUNCH_CHECK();
-    NANS_CUDA(cudaMemsetAsync(d.pair_count + (size_t)5 * nb, 0, sizeof(uint32_t), s));
     int rc = exclusive_scan_u32(d.pair_count, d.pair_count, 5 * nb + 1, d.scan_block, s);
     if (rc) return rc;
     pair_emit_kernel<<<div_up(nb, 128), 128, 0, s>>>(d, d.key[0]);
