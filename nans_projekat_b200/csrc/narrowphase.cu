@@ -9,6 +9,10 @@
 #define NANS_NP_MINBLOCKS 5   // 96 registers/thread: best of the sweep in profiles/ (4: 128 regs, 6: 80 regs + spills)
 #endif
 
+#ifndef NANS_NP_STREAM
+#define NANS_NP_STREAM 1
+#endif
+
 namespace nans {
 
 __device__ __forceinline__ void load_box(int side, const float4 *__restrict__ v6)
@@ -16,7 +20,11 @@ __device__ __forceinline__ void load_box(int side, const float4 *__restrict__ v6
     float *p = g_np_verts + 24 * side * kNpThreads + threadIdx.x;
 #pragma unroll
     for (int q = 0; q < 6; ++q) {
+#if NANS_NP_STREAM
+        const float4 t = __ldcs(v6 + q);     // evict-first: keep the L2 for the per-thread EPA arenas
+#else
         const float4 t = __ldg(v6 + q);
+#endif
         p[(4 * q) * kNpThreads] = t.x; p[(4 * q + 1) * kNpThreads] = t.y;
         p[(4 * q + 2) * kNpThreads] = t.z; p[(4 * q + 3) * kNpThreads] = t.w;
     }
@@ -65,9 +73,15 @@ __global__ void __launch_bounds__(kNpThreads, NANS_NP_MINBLOCKS) narrowphase_wor
             w.pair_hit[p] = r.hit;
             if (r.hit) {
                 float4 *o = w.pair_out + 3 * (size_t)p;
+#if NANS_NP_STREAM
+                __stcs(o, make_float4(r.PA.x, r.PA.y, r.PA.z, 0.f));
+                __stcs(o + 1, make_float4(r.PB.x, r.PB.y, r.PB.z, 0.f));
+                __stcs(o + 2, make_float4(r.N.x, r.N.y, r.N.z, 0.f));
+#else
                 o[0] = make_float4(r.PA.x, r.PA.y, r.PA.z, 0.f);
                 o[1] = make_float4(r.PB.x, r.PB.y, r.PB.z, 0.f);
                 o[2] = make_float4(r.N.x, r.N.y, r.N.z, 0.f);
+#endif
             }
         }
     }

@@ -5,12 +5,7 @@
 cd "$(dirname "$0")/.."
 CFGS=(
   "128 5"
-  "128 5 -DNANS_NP_OPT_A=1"
-  "128 5 -DNANS_NP_OPT_B=1"
-  "128 5 -DNANS_NP_OPT_C=1"
-  "128 5 -DNANS_NP_OPT_A=1 -DNANS_NP_OPT_B=1 -DNANS_NP_OPT_C=1"
-  "128 4 -DNANS_NP_OPT_A=1 -DNANS_NP_OPT_B=1 -DNANS_NP_OPT_C=1"
-  "128 6 -DNANS_NP_OPT_A=1 -DNANS_NP_OPT_B=1 -DNANS_NP_OPT_C=1"
+  "128 5 -DNANS_NP_STREAM=1"
 )
 V=gpurun_variants
 case "$1" in
