@@ -429,7 +429,7 @@ def main():
     traffic, traffic_src = None, None
     try:   # DRAM bytes per launch of the dominant kernel, from the committed `ncu --set full` capture
         tj = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
-        kname = {"narrowphase": "narrowphase_world_kernel", "solver": "solve_dataflow_kernel",
+        kname = {"narrowphase": "narrowphase_world_kernel", "solver": "solve_versioned_kernel",
                  "integrate_forces": "integrate_forces_kernel", "integrate_velocities": "integrate_velocities_kernel",
                  "broadphase": "pair_count_kernel"}[dom]
         traffic, traffic_src = tj["dram_bytes_per_launch"].get(kname), tj["source"] + " : " + kname
@@ -442,8 +442,8 @@ def main():
                                   "frac": alg[k] / (stage[k] * 1e-3) / 1e9 / peak} for k in alg},
                 "note": "stage = all kernels of that stage (CUDA events between stages on the launching stream); "
                         "narrowphase (GJK+EPA) is FP32-latency/divergence bound and the solver is bound by the "
-                        "dependency depth of the exact-order sweep, their HBM fractions are reported for "
-                        "completeness; pairs/s = %.3g" % (pairs_acc / (stage["narrowphase"] * 1e-3))}
+                        "dependency depth of the exact-order sweep (depth x store->poll->apply hop), their HBM "
+                        "fractions are reported for completeness; pairs/s = %.3g" % (pairs_acc / (stage["narrowphase"] * 1e-3))}
 
     # ---- e2e: through the public API with HOST buffers, H2D + D2H inside the timed region ----
     e2e = None
@@ -536,7 +536,7 @@ def main():
                            "l2": "inputs larger than L2 (>= 1 GB of world state touched per step vs 126 MB L2)",
                            "window": f"steps [{args.settle}, {args.settle + window}) of the simulation, restored from a "
                                      f"device snapshot every {window} steps inside the timed region",
-                           "solver": "exact reference order (dependency dataflow)",
+                           "solver": "exact reference order (versioned body rows: value + version in one 128-bit row)",
                            "pairs_per_step": pairs_acc, "contacts_per_step": contacts_acc,
                            "solver_dag_depth": acc["levels"]},
                 "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
