@@ -80,6 +80,7 @@ static Layout carve(const nans_world_desc &desc, char *base)
     const size_t ns = (size_t)(d.n_statics > 0 ? d.n_statics : 1);
     d.max_pairs = desc.max_pairs > 0 ? desc.max_pairs : (int32_t)(24 * nb + 1024);
     d.max_contacts = desc.max_contacts > 0 ? desc.max_contacts : (int32_t)(8 * nb + 1024);
+    if (d.max_pairs < d.max_contacts) d.max_pairs = d.max_contacts;   // contacts are a subset of the pairs; the solver borrows pair-sized scratch
     const size_t mp = (size_t)d.max_pairs, mc = (size_t)d.max_contacts;
     d.pos = b.take<float4>(nb); d.vel = b.take<float4>(nb); d.angvel = b.take<float4>(nb);
     d.ang = b.take<float4>(nb); d.force = b.take<float4>(nb); d.torque = b.take<float4>(nb);

@@ -604,7 +604,7 @@ __global__ void __launch_bounds__(kVerThreads) solve_versioned_kernel(DeviceWorl
                 if (need_b) { vb4 = ld_row(sv + ib); wb4 = ld_row(sw + ib); }
                 if (need_a && __float_as_int(va.w) == ea && (__float_as_int(wa.w) & kVerMask) == (ea & kVerMask)) {
                     V1 = V3(va); W1 = V3(wa);
-                    lva = __float_as_int(wa.w) >> 20;
+                    lva = (int)(__float_as_uint(wa.w) >> 20);
                     have_a = true;
                 }
                 if (need_b) have_b = __float_as_int(vb4.w) == eb && (__float_as_int(wb4.w) & kVerMask) == (eb & kVerMask);
@@ -627,7 +627,7 @@ __global__ void __launch_bounds__(kVerThreads) solve_versioned_kernel(DeviceWorl
                 vec3 V2 = V3(vb4), W2 = V3(wb4);                     // the Floor: V = W = 0
                 constraint_apply(q, V1, W1, V2, W2, ib >= 0);
                 int lv = lva;
-                if (ib >= 0) lv = max(lv, __float_as_int(wb4.w) >> 20);
+                if (ib >= 0) lv = max(lv, (int)(__float_as_uint(wb4.w) >> 20));
                 lva = min(lv + 1, 4095);
                 max_level = max(max_level, lv + 1);
                 if (ib >= 0) {
