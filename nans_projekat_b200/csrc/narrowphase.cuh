@@ -35,9 +35,6 @@ constexpr int kNoVertex = 8;
 #ifndef NANS_NP_OPT_A
 #define NANS_NP_OPT_A 1   // support scan keeps (best, index) only: -2 %
 #endif
-#ifndef NANS_NP_OPT_B
-#define NANS_NP_OPT_B 1   // face scan loads the next record ahead: -1 %
-#endif
 #ifndef NANS_NP_OPT_C
 #define NANS_NP_OPT_C 0   // equivalence-class scan without early exit: +4 % (worse)
 #endif   // box support when every compare failed (NaN direction): vec3(0)
@@ -204,16 +201,17 @@ __device__ __forceinline__ int evolve_simplex(const NpShapes &S, GjkVertex<AS, B
 }
 
 // ---- EPA --------------------------------------------------------------------------------------
-// Per-thread arena (local memory; only the touched part costs traffic).  A face record is two float4:
-// (unflipped unit normal n, d = dot(n, A.P)) and (A.P, packed vertex indices a | b<<8 | c<<16), so
-// the visibility test of a face needs no dependent load.
+// Per-thread arena (local memory; only the touched part costs traffic).  A face record is 20 bytes:
+// the unflipped unit normal n with d = dot(n, A.P), and the packed vertex indices a | b<<8 | c<<16.
+// (Carrying A.P in the record as well saved a dependent load but grew the arena: 640 threads/SM x
+// the touched part already exceeds L1, and the smaller record measured 6 % faster.)
 struct EpaArena {
     vec3 P[kEpaMaxVerts];
     vec3 SA[kEpaMaxVerts], SB[kEpaMaxVerts];    // sphere sides only
     uint8_t ia[kEpaMaxVerts], ib[kEpaMaxVerts]; // box sides only
     uint8_t cid[kEpaMaxVerts];                  // lowest vertex index with an equal P (kCidNaN: equal to nothing)
     float4 fnd[kEpaMaxFaces];
-    float4 fpa[kEpaMaxFaces];
+    uint32_t fidx[kEpaMaxFaces];
     uint32_t vis[kEpaMaxFaces];                 // packed indices of the faces dissolved this iteration
     uint32_t edge[kEpaMaxEdges];                // a | b<<8 | cid[a]<<16 | cid[b]<<24
 };
@@ -265,7 +263,7 @@ __device__ __forceinline__ void epa_push_face(EpaArena &E, int &nf, int a, int b
     const vec3 n = normalize(cross(E.P[b] - pa, E.P[c] - pa));
     const float d = dot(pa, n);
     E.fnd[nf] = make_float4(n.x, n.y, n.z, d);
-    E.fpa[nf] = make_float4(pa.x, pa.y, pa.z, __uint_as_float((uint32_t)a | ((uint32_t)b << 8) | ((uint32_t)c << 16)));
+    E.fidx[nf] = (uint32_t)a | ((uint32_t)b << 8) | ((uint32_t)c << 16);
     epa_track_min(d, nf, cur, ci);
     ++nf;
 }
@@ -313,12 +311,11 @@ __device__ __forceinline__ int epa_resolve(const NpShapes &S, const GjkVertex<AS
         const vec3 N = face_normal_flipped(cnd);
         const GjkVertex<AS, BS> ns = calc_support<AS, BS>(S, N);
         if (fsub(dot(N, ns.P), cur) < 0.001f) {   // MAX_EPA_ERROR, code/nans.h:55
-            const float4 cpa = E.fpa[ci];
-            const uint32_t f = __float_as_uint(cpa.w);
+            const uint32_t f = E.fidx[ci];
             const int a = f & 255, b = (f >> 8) & 255, c = (f >> 16) & 255;
             // Barycentric, code/nans.cpp:772-785
             const vec3 Pp = N * cur;
-            const vec3 A0 = V3(cpa);
+            const vec3 A0 = E.P[a];
             const vec3 v0 = E.P[b] - A0, v1 = E.P[c] - A0, v2 = Pp - A0;
             const float d00 = dot(v0, v0), d01 = dot(v0, v1), d11 = dot(v1, v1);
             const float d20 = dot(v2, v0), d21 = dot(v2, v1);
@@ -339,22 +336,17 @@ __device__ __forceinline__ int epa_resolve(const NpShapes &S, const GjkVertex<AS
         // dissolved faces are only LISTED here; their edges are pushed in a second loop, so the warp
         // stays converged over the face scan.
         int keep = 0, nvis = 0;
-#if NANS_NP_OPT_B
-        float4 nd_next = E.fnd[0], pa_next = E.fpa[0];
-#endif
+        float4 nd_next = E.fnd[0];
+        uint32_t f_next = E.fidx[0];
         for (int i = 0; i < nf; ++i) {
-#if NANS_NP_OPT_B
-            const float4 nd = nd_next, pa = pa_next;
-            if (i + 1 < nf) { nd_next = E.fnd[i + 1]; pa_next = E.fpa[i + 1]; }   // before the stores below: in flight during the test
-#else
-            const float4 nd = E.fnd[i];
-            const float4 pa = E.fpa[i];
-#endif
-            const vec3 tmp = ns.P - V3(pa);
+            const float4 nd = nd_next;
+            const uint32_t f = f_next;
+            if (i + 1 < nf) { nd_next = E.fnd[i + 1]; f_next = E.fidx[i + 1]; }
+            const vec3 tmp = ns.P - E.P[f & 255];
             if (dot(face_normal_flipped(nd), tmp) > 0.0f) {
-                E.vis[nvis++] = __float_as_uint(pa.w);
+                E.vis[nvis++] = f;
             } else {
-                if (keep != i) { E.fnd[keep] = nd; E.fpa[keep] = pa; }
+                if (keep != i) { E.fnd[keep] = nd; E.fidx[keep] = f; }
                 epa_track_min(nd.w, keep, cur, ci);
                 ++keep;
             }

@@ -5,7 +5,9 @@
 cd "$(dirname "$0")/.."
 CFGS=(
   "128 5"
-  "128 5 -DNANS_NP_STREAM=1"
+  "128 5 -DNANS_NP_COMPACT=1"
+  "128 6 -DNANS_NP_COMPACT=1"
+  "128 4 -DNANS_NP_COMPACT=1"
 )
 V=gpurun_variants
 case "$1" in
