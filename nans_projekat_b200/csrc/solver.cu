@@ -555,7 +555,7 @@ __global__ void __launch_bounds__(256) run_scatter_kernel(DeviceWorld w)
 // rows go through memory, and the lanes of a warp fire their j-th contacts together (a lane per
 // contact left ~8 of 32 lanes active per firing: the kernel was bound by issue slots).
 // trace (debug, NANS_SOLVER_TRACE=1): per contact {fire ns, stored ns, ticket ns, polls}; frontier[1] = DAG level
-__global__ void __launch_bounds__(kVerThreads) solve_versioned_kernel(DeviceWorld w, float dt, int sleep_ns, int patience, unsigned long long *trace)
+__global__ void __launch_bounds__(kVerThreads) solve_versioned_kernel(DeviceWorld w, float dt, int sleep_ns, unsigned long long *trace)
 {
     const int n = w.counters->n_contacts;
     const int n_runs = w.counters->frontier_n[1];
@@ -582,11 +582,10 @@ __global__ void __launch_bounds__(kVerThreads) solve_versioned_kernel(DeviceWorl
         vec3 V1 = V3(0.f, 0.f, 0.f), W1 = V3(0.f, 0.f, 0.f);
         bool loaded = false, have_a = false, have_b = false;
         float4 vb4 = make_float4(0, 0, 0, 0), wb4 = make_float4(0, 0, 0, 0);
-        int spins = 0, held = 0;
+        int spins = 0;
         unsigned long long t_ticket = 0;
         if (trace) t_ticket = global_ns();
         while (__any_sync(0xffffffffu, pending)) {
-            bool fired = false;
             if (pending) {
                 if (!loaded) {
                     // the velocity-independent part of the contact, straight into registers (no record
@@ -610,16 +609,10 @@ __global__ void __launch_bounds__(kVerThreads) solve_versioned_kernel(DeviceWorl
                 if (need_b) have_b = __float_as_int(vb4.w) == eb && (__float_as_int(wb4.w) & kVerMask) == (eb & kVerMask);
                 if (ib < 0) have_b = true;
             }
-            // Fire when every lane that still has work is ready, or when the ready ones have waited
-            // `patience` polls: a firing costs the warp ~1000 issue slots however few lanes take part,
-            // and the lanes of a chunk become ready within a few hundred ns of each other.
+            // every ready lane fires at once (holding ready lanes back to fire more of them together was
+            // measured: each poll of patience costs ~50 us per step, the solve is bound by hop latency)
             const bool ready = pending && have_a && have_b;
-            const unsigned rm = __ballot_sync(0xffffffffu, ready), pm = __ballot_sync(0xffffffffu, pending);
-            bool go = false;
-            if (rm) {
-                go = rm == pm || held >= patience;
-                held = go ? 0 : held + 1;
-            }
+            const bool go = __any_sync(0xffffffffu, ready);
             if (go && ready) {
                 unsigned long long t_fire = 0;
                 long long ck = 0;
@@ -651,8 +644,7 @@ __global__ void __launch_bounds__(kVerThreads) solve_versioned_kernel(DeviceWorl
                     pending = false;
                 }
             }
-            fired = go;
-            if (!__any_sync(0xffffffffu, fired)) {
+            if (!go) {
                 if (++spins > kSpinCap || *abort_flag) { *abort_flag = 1; return; }
                 if (sleep_ns) __nanosleep(sleep_ns);
             }
@@ -740,7 +732,7 @@ int launch_solver(World *w, float dt)
         return NANS_OK;
     }
     if (mode == 2) {
-        static int ver_blocks = 0, ver_sleep = 0, ver_patience = 0;
+        static int ver_blocks = 0, ver_sleep = 0;
         if (!ver_blocks) {
             int per_sm = 0;
             NANS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, solve_versioned_kernel, kVerThreads, 0));
@@ -749,7 +741,6 @@ int launch_solver(World *w, float dt)
             if (want < 1) want = 1;
             ver_blocks = sm_count * (want < per_sm ? want : per_sm);   // every CTA must be resident (spinning lanes)
             ver_sleep = (e = getenv("NANS_VER_SLEEP")) ? atoi(e) : 0;
-            ver_patience = (e = getenv("NANS_VER_PATIENCE")) ? atoi(e) : 0;   // sweep: every poll of patience costs ~50 us (latency-bound)
         }
         rc = exclusive_scan_u32_dn((const uint32_t *)d.indeg, d.pair_hit_scan, d.max_contacts, &d.counters->n_contacts, 0,
                                    d.scan_block, s);
@@ -760,7 +751,7 @@ int launch_solver(World *w, float dt)
         NANS_LAUNCH_CHECK();
         static int ver_trace = -1;
         if (ver_trace < 0) ver_trace = getenv("NANS_SOLVER_TRACE") ? 1 : 0;
-        solve_versioned_kernel<<<ver_blocks, kVerThreads, 0, s>>>(d, dt, ver_sleep, ver_patience, ver_trace ? (unsigned long long *)d.pair_out : nullptr);
+        solve_versioned_kernel<<<ver_blocks, kVerThreads, 0, s>>>(d, dt, ver_sleep, ver_trace ? (unsigned long long *)d.pair_out : nullptr);
         NANS_LAUNCH_CHECK();
         ver_finish_kernel<<<div_up(d.nb, 256), 256, 0, s>>>(d);
         NANS_LAUNCH_CHECK();
