@@ -15,6 +15,8 @@
 //   pair_emit_kernel     moves the parked partners to their offsets, sorts each short run ascending
 //
 // All kernels are HBM/L2-bound integer + compare work; see DESIGN.md §4 for bytes per body.
+#include <float.h>
+
 #include "world.cuh"
 
 namespace nans {
@@ -85,6 +87,17 @@ __device__ __forceinline__ int cell_coord(float c, float inv_cell)
     return (int)f + 512;   // NaN -> (int)NaN = 0 -> 512
 }
 
+// monotone map float -> uint32 (total order of the finite floats)
+__device__ __forceinline__ uint32_t order_bits(float f)
+{
+    const uint32_t b = __float_as_uint(f);
+    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__device__ __forceinline__ float order_float(uint32_t e)
+{
+    return __uint_as_float((e & 0x80000000u) ? (e & 0x7fffffffu) : ~e);
+}
+
 // AABB per body + the largest AABB extent of this step (block reduce -> one atomicMax per block).
 __global__ void __launch_bounds__(256) aabb_kernel(DeviceWorld w)
 {
@@ -96,6 +109,7 @@ __global__ void __launch_bounds__(256) aabb_kernel(DeviceWorld w)
         w.st_aabb[2 * i + 1] = make_float4(hi[0], hi[1], hi[2], 0.f);
     }
     float ext = 0.f;
+    float ctr[3] = {FLT_MAX, FLT_MAX, FLT_MAX};
     if (i < w.nb) {
         float lo[3], hi[3];
         if (i < w.n_cubes) {
@@ -111,17 +125,39 @@ __global__ void __launch_bounds__(256) aabb_kernel(DeviceWorld w)
         w.aabb_lo[i] = make_float4(lo[0], lo[1], lo[2], 0.f);
         w.aabb_hi[i] = make_float4(hi[0], hi[1], hi[2], 0.f);
         ext = fmaxf(fmaxf(hi[0] - lo[0], hi[1] - lo[1]), hi[2] - lo[2]);   // fmaxf drops NaN
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const float c = 0.5f * (lo[k] + hi[k]);                           // the expression key_kernel uses
+            if (isfinite(c)) ctr[k] = c;
+        }
     }
     // non-negative floats order like their bit patterns
     ext = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(fmaxf(ext, 0.f))));
+    // smallest AABB centre per axis: the cell grid is anchored there, so the Morton keys start at 0
+    // and the sort can skip the passes above the world's real extent
+    uint32_t cmin[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) cmin[k] = __reduce_max_sync(0xffffffffu, ~order_bits(ctr[k]));
     __shared__ float wmax[8];
-    if ((threadIdx.x & 31) == 0) wmax[threadIdx.x >> 5] = ext;
+    __shared__ uint32_t wmin[8][3];
+    if ((threadIdx.x & 31) == 0) {
+        wmax[threadIdx.x >> 5] = ext;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) wmin[threadIdx.x >> 5][k] = cmin[k];
+    }
     __syncthreads();
     if (threadIdx.x == 0) {
         float m = wmax[0];
 #pragma unroll
         for (int k = 1; k < 8; ++k) m = fmaxf(m, wmax[k]);
         atomicMax((unsigned int *)&w.counters->pad[2], __float_as_uint(m));   // non-negative floats order as uints
+    }
+    if (threadIdx.x < 3) {
+        uint32_t m = wmin[0][threadIdx.x];
+#pragma unroll
+        for (int k = 1; k < 8; ++k) m = max(m, wmin[k][threadIdx.x]);
+        unsigned int *slot = (unsigned int *)&w.counters->pad[kMinCentre + threadIdx.x];
+        if (m > *(volatile unsigned int *)slot) atomicMax(slot, m);       // most blocks do not improve it
     }
 }
 
@@ -140,26 +176,57 @@ __global__ void __launch_bounds__(256) key_kernel(DeviceWorld w)
     int cx = cell_coord(0.5f * (lo.x + hi.x), inv_cell);
     int cy = cell_coord(0.5f * (lo.y + hi.y), inv_cell);
     int cz = cell_coord(0.5f * (lo.z + hi.z), inv_cell);
+    // anchor the grid at the smallest centre (cell_coord is monotone, so the differences stay >= 0)
+    const int bx = cell_coord(order_float(~(uint32_t)w.counters->pad[kMinCentre + 0]), inv_cell);
+    const int by = cell_coord(order_float(~(uint32_t)w.counters->pad[kMinCentre + 1]), inv_cell);
+    const int bz = cell_coord(order_float(~(uint32_t)w.counters->pad[kMinCentre + 2]), inv_cell);
+    cy = max(cy - by, 0);
     if (w.world_id) {
         // batched independent worlds: each world owns a 16x16 column of cells in x,z
         const int wid = w.world_id[i];
         cx = min(max(cx - 512 + 8, 0), 15) + 16 * (wid & 63);
         cz = min(max(cz - 512 + 8, 0), 15) + 16 * ((wid >> 6) & 63);
+    } else {
+        cx = max(cx - bx, 0);
+        cz = max(cz - bz, 0);
     }
-    w.key[0][i] = morton30((uint32_t)cx, (uint32_t)cy, (uint32_t)cz);
+    const uint32_t key = morton30((uint32_t)cx, (uint32_t)cy, (uint32_t)cz);
+    w.key[0][i] = key;
     w.val[0][i] = (uint32_t)i;
+    // the largest key of the step decides how many 8-bit sort passes are needed (kMaxKey)
+    const uint32_t m = __reduce_max_sync(__activemask(), key);
+    unsigned int *slot = (unsigned int *)&w.counters->pad[kMaxKey];
+    if ((threadIdx.x & 31) == 0 && m > *(volatile unsigned int *)slot) atomicMax(slot, m);   // rarely improves it
+}
+
+// Sort passes that only see zero digits are skipped (a 250 x 16 x 250-cell world has 24-bit keys,
+// a 10 k-cube world 15-bit ones), so the sorted data ends in buffer 0 or 1 depending on the
+// step: the consumers pick the buffer with sorted_buf().  pad[kPassLen + p - 1] = histogram length
+// of pass p (0 when skipped), for the scan's device-side length.
+__device__ __forceinline__ int sorted_passes(const DeviceWorld &w)
+{
+    const uint32_t mk = (uint32_t)w.counters->pad[kMaxKey];
+    return 1 + (mk >= (1u << 8)) + (mk >= (1u << 16)) + (mk >= (1u << 24));
+}
+__device__ __forceinline__ int sorted_buf(const DeviceWorld &w) { return sorted_passes(w) & 1; }
+
+__global__ void radix_plan_kernel(DeviceWorld w, int hist_len)
+{
+    const int p = threadIdx.x + 1;   // passes 1..3
+    if (p <= 3) w.counters->pad[kPassLen + p - 1] = p < sorted_passes(w) ? hist_len : 0;
 }
 
 // ---------------------------------------------------------------------------------------------
-// LSD radix sort, 8 bits per pass.
+// LSD radix sort, 8 bits per pass.  (kMaxKey / kPassLen: slots of Counters::pad, see world.cuh.)
 constexpr int kRadixThreads = 256;
 constexpr int kRadixItems = 16;
 constexpr int kRadixTile = kRadixThreads * kRadixItems;  // 4096 keys per block
 
 __global__ void __launch_bounds__(kRadixThreads) radix_hist_kernel(const uint32_t *__restrict__ keys, int n,
                                                                    int shift, uint32_t *__restrict__ hist,
-                                                                   int n_blocks)
+                                                                   int n_blocks, const int32_t *__restrict__ max_key)
 {
+    if (shift && ((uint32_t)*max_key >> shift) == 0u) return;   // nothing but zero digits: pass skipped
     __shared__ uint32_t h[256];
     h[threadIdx.x] = 0;
     __syncthreads();
@@ -176,8 +243,9 @@ __global__ void __launch_bounds__(kRadixThreads) radix_hist_kernel(const uint32_
 __global__ void __launch_bounds__(kRadixThreads) radix_scatter_kernel(
     const uint32_t *__restrict__ keys_in, const uint32_t *__restrict__ vals_in,
     uint32_t *__restrict__ keys_out, uint32_t *__restrict__ vals_out, int n, int shift,
-    const uint32_t *__restrict__ hist_scanned, int n_blocks)
+    const uint32_t *__restrict__ hist_scanned, int n_blocks, const int32_t *__restrict__ max_key)
 {
+    if (shift && ((uint32_t)*max_key >> shift) == 0u) return;
     __shared__ uint32_t base_off[256];            // running global offset per digit for this block
     __shared__ uint32_t warp_cnt[kRadixThreads / 32][256];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -222,11 +290,14 @@ __global__ void __launch_bounds__(kRadixThreads) radix_scatter_kernel(
 // After the sort: AABBs in Morton order as one 32-byte record per body (one L2 sector per
 // candidate test): {lo.xyz, row} {hi.xyz, world id}; and the hash table of cells, one 16-byte
 // entry {key, start, end, -} per slot (one sector per probe).
-__global__ void __launch_bounds__(256) gather_sorted_kernel(DeviceWorld w, const uint32_t *__restrict__ keys,
-                                                            const uint32_t *__restrict__ vals)
+__global__ void __launch_bounds__(256) gather_sorted_kernel(DeviceWorld w)
 {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= w.nb) return;
+    const int fb = sorted_buf(w);
+    const uint32_t *__restrict__ keys = w.key[fb];
+    const uint32_t *__restrict__ vals = w.val[fb];
+    w.key[fb ^ 1][t] = 0u;                    // the spare key buffer becomes the pair-slot cursors
     const uint32_t row = vals[t];
     float4 lo = w.aabb_lo[row], hi = w.aabb_hi[row];
     lo.w = __int_as_float((int)row);
@@ -332,11 +403,13 @@ constexpr int kPairSlots = 24;
 // to the body the reference lists it under (lower cube / the cube of a cube-sphere pair / lower
 // sphere), whichever of the two found it: per-(type, body) counts and the slot cursor are atomics,
 // the slot order is arbitrary (the emit pass sorts every run by partner).
-__global__ void __launch_bounds__(128, NANS_PC_MINBLOCKS) pair_count_kernel(DeviceWorld w, const uint32_t *__restrict__ keys,
-                                                                            uint32_t *__restrict__ fill)
+__global__ void __launch_bounds__(128, NANS_PC_MINBLOCKS) pair_count_kernel(DeviceWorld w)
 {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= w.nb) return;
+    const int fb = sorted_buf(w);
+    const uint32_t *__restrict__ keys = w.key[fb];
+    uint32_t *__restrict__ fill = w.key[fb ^ 1];
     const float4 alo = w.sbox[2 * (size_t)t], ahi = w.sbox[2 * (size_t)t + 1];
     const int row = __float_as_int(alo.w);
     const int wid = __float_as_int(ahi.w);
@@ -389,10 +462,11 @@ __global__ void __launch_bounds__(128, NANS_PC_MINBLOCKS) pair_count_kernel(Devi
     }
 }
 
-__global__ void __launch_bounds__(128) pair_emit_kernel(DeviceWorld w, const uint32_t *__restrict__ keys)
+__global__ void __launch_bounds__(128) pair_emit_kernel(DeviceWorld w)
 {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= w.nb) return;
+    const uint32_t *__restrict__ keys = w.key[sorted_buf(w)];
     const float4 alo = w.sbox[2 * (size_t)t], ahi = w.sbox[2 * (size_t)t + 1];
     const int row = __float_as_int(alo.w);
     if (row >= w.n_owned) {
@@ -471,29 +545,34 @@ int launch_broadphase(World *w)
     key_kernel<<<div_up(nb, 256), 256, 0, s>>>(d);
     NANS_LAUNCH_CHECK();
 
-    // radix sort on key[0]/val[0] <-> key[1]/val[1]; 30-bit keys = 4 passes, ends in buffer 0
+    // radix sort on key[0]/val[0] <-> key[1]/val[1]; up to 4 passes of 8 bits, the top ones skipped on
+    // the device when the step's largest key has no bits there
     const int n_blocks = div_up(nb, kRadixTile);
+    const int32_t *max_key = &d.counters->pad[kMaxKey];
+    radix_plan_kernel<<<1, 32, 0, s>>>(d, 256 * n_blocks);
+    NANS_LAUNCH_CHECK();
     for (int pass = 0; pass < 4; ++pass) {
         const int src = pass & 1, dst = src ^ 1;
-        radix_hist_kernel<<<n_blocks, kRadixThreads, 0, s>>>(d.key[src], nb, pass * 8, d.radix_hist, n_blocks);
+        radix_hist_kernel<<<n_blocks, kRadixThreads, 0, s>>>(d.key[src], nb, pass * 8, d.radix_hist, n_blocks, max_key);
         NANS_LAUNCH_CHECK();
-        int rc = exclusive_scan_u32(d.radix_hist, d.radix_hist, 256 * n_blocks, d.scan_block, s);
+        int rc = pass == 0 ? exclusive_scan_u32(d.radix_hist, d.radix_hist, 256 * n_blocks, d.scan_block, s)
+                           : exclusive_scan_u32_dn(d.radix_hist, d.radix_hist, 256 * n_blocks,
+                                                   &d.counters->pad[kPassLen + pass - 1], 0, d.scan_block, s);
         if (rc) return rc;
         radix_scatter_kernel<<<n_blocks, kRadixThreads, 0, s>>>(d.key[src], d.val[src], d.key[dst], d.val[dst],
-                                                                nb, pass * 8, d.radix_hist, n_blocks);
+                                                                nb, pass * 8, d.radix_hist, n_blocks, max_key);
         NANS_LAUNCH_CHECK();
     }
     NANS_CUDA(cudaMemsetAsync(d.cell_tab, 0xff, sizeof(uint4) * ((size_t)d.cell_mask + 1), s));
-    gather_sorted_kernel<<<div_up(nb, 256), 256, 0, s>>>(d, d.key[0], d.val[0]);
+    gather_sorted_kernel<<<div_up(nb, 256), 256, 0, s>>>(d);
     NANS_LAUNCH_CHECK();
-    // counts and slot cursors are accumulated with atomics; the cursors borrow the sort's spare key buffer
+    // counts and slot cursors are accumulated with atomics; the cursors live in the sort's spare key buffer (zeroed by the gather)
     NANS_CUDA(cudaMemsetAsync(d.pair_count, 0, sizeof(uint32_t) * ((size_t)5 * nb + 1), s));
-    NANS_CUDA(cudaMemsetAsync(d.key[1], 0, sizeof(uint32_t) * (size_t)nb, s));
-    pair_count_kernel<<<div_up(nb, 128), 128, 0, s>>>(d, d.key[0], d.key[1]);
+    pair_count_kernel<<<div_up(nb, 128), 128, 0, s>>>(d);
     NANS_LAUNCH_CHECK();
     int rc = exclusive_scan_u32(d.pair_count, d.pair_count, 5 * nb + 1, d.scan_block, s);
     if (rc) return rc;
-    pair_emit_kernel<<<div_up(nb, 128), 128, 0, s>>>(d, d.key[0]);
+    pair_emit_kernel<<<div_up(nb, 128), 128, 0, s>>>(d);
     NANS_LAUNCH_CHECK();
     return NANS_OK;
 }

@@ -29,8 +29,12 @@ struct Counters {
     int32_t overflow;
     int32_t max_epa_faces;
     int32_t frontier_n[3];   // solver frontier sizes (level L reads L%3, fills (L+1)%3, clears (L+2)%3)
-    int32_t pad[7];
+    int32_t pad[11];         // [0] narrowphase work counter, [1] solver abort flag, [2] max AABB extent bits,
+                             // [3] largest Morton key, [4..6] histogram length of sort passes 1..3 (0 = skipped),
+                             // [7..9] smallest AABB centre per axis (order-encoded, complemented: 0 = none yet)
 };
+
+constexpr int kMaxKey = 3, kPassLen = 4, kMinCentre = 7;   // Counters::pad slots used by the broadphase
 
 // All pointers are DEVICE pointers into the arena.
 struct DeviceWorld {
