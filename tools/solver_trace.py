@@ -46,7 +46,35 @@ if versioned:
         m = lv == L
         if L <= 12 or L % 8 == 0:
             print(f"level {L:3d} n={m.sum():7d} fire min/med/max us = {fire[m].min():8.1f} {np.median(fire[m]):8.1f} {fire[m].max():8.1f}")
-    # critical path: walk back from the contact that finished last
+    # critical path: walk back from the contact that finished last, always to the predecessor (previous
+    # contact on body A or body B) that finished later
+    a = c["a"].astype(np.int64).copy(); b = c["b"].astype(np.int64).copy()
+    nc_ = w.n_cubes
+    ty = c["type"]
+    a[(ty == 3) | (ty == 4)] += nc_                       # SS, SF: a is a sphere
+    b[(ty == 1) | (ty == 3)] += nc_                       # CS, SS: b is a sphere
+    b[(ty == 2) | (ty == 4)] = -1                         # statics are no dependency
+    last = {}
+    pa = np.full(n, -1, np.int64); pb = np.full(n, -1, np.int64)
+    for i in range(n):
+        pa[i] = last.get(a[i], -1); last[a[i]] = i
+        if b[i] >= 0:
+            pb[i] = last.get(b[i], -1); last[b[i]] = i
+    head = np.ones(n, bool); head[1:] = a[1:] != a[:-1]
+    chunk = (np.cumsum(head) - 1) // 32                   # 32 runs per warp ticket
+    cur = int(np.argmax(done)); hops = []; 
+    while True:
+        cand = [p for p in (pa[cur], pb[cur]) if p >= 0]
+        if not cand: break
+        p = max(cand, key=lambda k: done[k])
+        hops.append((fire[cur] - done[p], done[cur] - fire[cur], chunk[cur] == chunk[p], (p == cur - 1) and not head[cur]))
+        cur = int(p)
+    h = np.array(hops, dtype=np.float64)
+    print(f"critical path: {len(h)} hops, ends at {done.max():.1f} us, starts at {fire[cur]:.1f} us")
+    for name, m in (("same lane (run)", h[:, 3] == 1), ("same warp ticket", (h[:, 2] == 1) & (h[:, 3] == 0)), ("other warp", h[:, 2] == 0)):
+        if m.any():
+            print(f"  {name:17s}: {int(m.sum()):4d} hops, detect latency med {np.median(h[m, 0]):.2f} us (sum {h[m, 0].sum():.1f}), "
+                  f"apply med {np.median(h[m, 1]):.2f} us (sum {h[m, 1].sum():.1f})")
     sys.exit(0)
 t0 = t4[:, 0].min()
 t = (t4[:, 0] - t0).astype(np.float64) / 1e3
