@@ -137,6 +137,7 @@ struct IoPipe {               // pipelined host I/O: copies on their own streams
     cudaEvent_t ev_up, ev_unpack, ev_pack, ev_down[8];
     bool have_unpack, have_down;
     int next_ticket;
+    int deferred;             // force/torque uploads in flight whose unpack waits for the step's detection phase
 };
 
 struct WorldImpl : World {
@@ -204,6 +205,7 @@ using namespace nans;
 extern "C" {
 
 static void graph_invalidate(WorldImpl *w);
+static int flush_deferred(WorldImpl *w);
 
 const char *nans_last_error(void) { return g_err; }
 
@@ -279,6 +281,7 @@ void nans_world_destroy(nans_world *h)
     cudaSetDevice(w->device);
     cudaStreamSynchronize(w->stream);
     if (w->graph_exec) cudaGraphExecDestroy(w->graph_exec);
+    if (w->graph_exec_b) cudaGraphExecDestroy(w->graph_exec_b);
     if (w->io.init) {
         cudaStreamSynchronize(w->io.up); cudaStreamSynchronize(w->io.down);
         cudaStreamDestroy(w->io.up); cudaStreamDestroy(w->io.down);
@@ -294,6 +297,7 @@ void nans_world_destroy(nans_world *h)
 int nans_synchronize(nans_world *h)
 {
     if (!h) return fail(NANS_ERR_ARG, "null world");
+    { const int frc = flush_deferred(impl(h)); if (frc) return frc; }
     NANS_CUDA(cudaStreamSynchronize(impl(h)->stream));
     return NANS_OK;
 }
@@ -306,6 +310,7 @@ int nans_world_upload(nans_world *h, const nans_scene_view *sc)
     WorldImpl *w = impl(h);
     DeviceWorld &d = w->d;
     NANS_CUDA(cudaSetDevice(w->device));
+    { const int frc = flush_deferred(w); if (frc) return frc; }
     cudaStream_t s = w->stream;
     const int nb = d.nb;
     const int grid = div_up(nb > 0 ? nb : 1, 256);
@@ -385,6 +390,7 @@ int nans_world_download(nans_world *h, nans_scene_view *sc)
     WorldImpl *w = impl(h);
     DeviceWorld &d = w->d;
     NANS_CUDA(cudaSetDevice(w->device));
+    { const int frc = flush_deferred(w); if (frc) return frc; }
     cudaStream_t s = w->stream;
     const int nb = d.nb;
     const int grid = div_up(nb > 0 ? nb : 1, 256);
@@ -430,7 +436,30 @@ static int io_init(WorldImpl *w)
     for (auto &e : w->io.ev_down) NANS_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     w->io.have_unpack = w->io.have_down = false;
     w->io.next_ticket = 0;
+    w->io.deferred = 0;
     w->io.init = true;
+    return NANS_OK;
+}
+
+// Forces and torques are read by integrate-forces only, and collision detection reads neither them nor
+// the velocities, so an upload that carries nothing else does not have to finish before the step starts:
+// its unpack is DEFERRED until nans_step has queued the detection phase (flush_deferred), and the
+// host-to-device copy overlaps broadphase + narrowphase.  Any other entry point flushes first.
+static int flush_deferred(WorldImpl *w)
+{
+    if (!w->io.init || !w->io.deferred) return NANS_OK;
+    DeviceWorld &d = w->d;
+    float4 *vdst[6] = {d.pos, d.vel, d.force, d.ang, d.angvel, d.torque};
+    NANS_CUDA(cudaStreamWaitEvent(w->stream, w->io.ev_up, 0));
+    const int grid = div_up(d.nb > 0 ? d.nb : 1, 256);
+    for (int k = 0; k < 6; ++k)
+        if ((w->io.deferred >> k) & 1) {
+            unpack_vec3_kernel<<<grid, 256, 0, w->stream>>>(w->st.vec[k], vdst[k], d.nb);
+            NANS_LAUNCH_CHECK();
+        }
+    NANS_CUDA(cudaEventRecord(w->io.ev_unpack, w->stream));
+    w->io.have_unpack = true;
+    w->io.deferred = 0;
     return NANS_OK;
 }
 
@@ -446,12 +475,19 @@ int nans_world_upload_async(nans_world *h, const nans_scene_view *sc)
     if (nb == 0) return NANS_OK;
     const float *vsrc[6] = {sc->pos, sc->vel, sc->force, sc->ang, sc->angvel, sc->torque};
     float4 *vdst[6] = {d.pos, d.vel, d.force, d.ang, d.angvel, d.torque};
+    int mask = 0;
+    for (int k = 0; k < 6; ++k) mask |= vsrc[k] ? 1 << k : 0;
+    const int kForceTorque = (1 << 2) | (1 << 5);
+    const bool defer = mask && !(mask & ~kForceTorque);
+    // a pending deferred upload is unpacked first (keeps the order of writes to the same field)
+    if (w->io.deferred && (!defer || (w->io.deferred & mask))) { rc = flush_deferred(w); if (rc) return rc; }
     // the upload slots are free once the previous unpack has run (downloads use their own slots)
     if (w->io.have_unpack) NANS_CUDA(cudaStreamWaitEvent(w->io.up, w->io.ev_unpack, 0));
     for (int k = 0; k < 6; ++k)
         if (vsrc[k])
             NANS_CUDA(cudaMemcpyAsync(w->st.vec[k], vsrc[k], sizeof(float) * 3 * (size_t)nb, cudaMemcpyHostToDevice, w->io.up));
     NANS_CUDA(cudaEventRecord(w->io.ev_up, w->io.up));
+    if (defer) { w->io.deferred |= mask; return NANS_OK; }
     NANS_CUDA(cudaStreamWaitEvent(w->stream, w->io.ev_up, 0));
     const int grid = div_up(nb, 256);
     for (int k = 0; k < 6; ++k)
@@ -472,6 +508,7 @@ int nans_world_download_async(nans_world *h, nans_scene_view *sc, int32_t *ticke
     NANS_CUDA(cudaSetDevice(w->device));
     int rc = io_init(w);
     if (rc) return rc;
+    { const int frc = flush_deferred(w); if (frc) return frc; }
     const int nb = d.nb;
     float *vdst[6] = {sc->pos, sc->vel, sc->force, sc->ang, sc->angvel, sc->torque};
     const float4 *vsrc[6] = {d.pos, d.vel, d.force, d.ang, d.angvel, d.torque};
@@ -501,6 +538,7 @@ int nans_world_wait(nans_world *h, int32_t ticket)
     if (!h) return fail(NANS_ERR_ARG, "null world");
     WorldImpl *w = impl(h);
     NANS_CUDA(cudaSetDevice(w->device));
+    if (ticket < 0) { const int frc = flush_deferred(w); if (frc) return frc; }
     if (!w->io.init || ticket < 0) {
         if (w->io.init) { NANS_CUDA(cudaStreamSynchronize(w->io.up)); NANS_CUDA(cudaStreamSynchronize(w->io.down)); }
         NANS_CUDA(cudaStreamSynchronize(w->stream));
@@ -517,6 +555,7 @@ int nans_world_add_force(nans_world *h, int32_t row, const float f[3], const flo
     WorldImpl *w = impl(h);
     if (row < 0 || row >= w->d.nb) return fail(NANS_ERR_ARG, "nans_world_add_force: body row out of range");
     NANS_CUDA(cudaSetDevice(w->device));
+    { const int frc = flush_deferred(w); if (frc) return frc; }
     const float3 ff = f ? make_float3(f[0], f[1], f[2]) : make_float3(0, 0, 0);
     const float3 tt = t ? make_float3(t[0], t[1], t[2]) : make_float3(0, 0, 0);
     add_force_kernel<<<1, 1, 0, w->stream>>>(w->d, row, ff, tt);
@@ -546,6 +585,7 @@ static int snapshot_copy(WorldImpl *w, bool restore)
 {
     DeviceWorld &d = w->d;
     NANS_CUDA(cudaSetDevice(w->device));
+    { const int frc = flush_deferred(w); if (frc) return frc; }
     float4 *rows[6] = {d.pos, d.vel, d.angvel, d.ang, d.force, d.torque};
     // fixed layout (capacity strides): slab mode varies nb / n_cubes between snapshot and restore
     const size_t nb = (size_t)w->cap_nb, nc = (size_t)(d.n_spheres ? d.n_cubes : w->cap_nb);
@@ -598,6 +638,7 @@ int nans_slab_pack_halo(nans_world *h, const float box_lo_hi[6], int32_t gid_bas
 {
     if (!h || !box_lo_hi || !d_out || !count) return fail(NANS_ERR_ARG, "null argument");
     WorldImpl *w = impl(h);
+    { const int frc = flush_deferred(w); if (frc) return frc; }
     NANS_CUDA(cudaSetDevice(w->device));
     if (list_offset < 0 || list_offset > w->cap_nb) return fail(NANS_ERR_ARG, "bad list offset");
     const int room = w->cap_nb - list_offset;
@@ -614,6 +655,7 @@ int nans_slab_unpack_halo(nans_world *h, const void *d_in, int32_t count, int32_
 {
     if (!h) return fail(NANS_ERR_ARG, "null world");
     WorldImpl *w = impl(h);
+    { const int frc = flush_deferred(w); if (frc) return frc; }
     NANS_CUDA(cudaSetDevice(w->device));
     if (row0 < 0 || count < 0 || row0 + count > w->cap_nb) return fail(NANS_ERR_CAPACITY, "ghost rows exceed capacity");
     return slab_unpack_halo(w, (const float4 *)d_in, count, row0, w->d.gid);
@@ -639,6 +681,7 @@ int nans_integrate_forces(nans_world *h, float dt)
 {
     if (!h) return fail(NANS_ERR_ARG, "null world");
     NANS_CUDA(cudaSetDevice(impl(h)->device));
+    { const int frc = flush_deferred(impl(h)); if (frc) return frc; }
     return launch_integrate_forces(impl(h), dt);
 }
 
@@ -681,20 +724,32 @@ int nans_rebuild_vertices(nans_world *h)
     return launch_integrate_velocities(w, 0.0f);   // Position += 0*V is exact for finite V; rebuilds every Model
 }
 
-static int step_eager(nans_world *h, float dt)
+// One step = IntegrateForces, DetectCollisions, SolveConstraints, IntegrateVelocities (code/nans.cpp:1758-1762).
+// Detection reads positions and vertices only and integrate-forces writes velocities and clears forces only, so
+// the two commute bit for bit; the step runs detection FIRST, so that a force/torque upload still in flight
+// (nans_world_upload_async) overlaps broadphase + narrowphase and is unpacked just before integrate-forces.
+static int step_phase_a(nans_world *h) { return nans_detect_collisions(h); }
+static int step_phase_b(nans_world *h, float dt)
 {
-    int rc = nans_integrate_forces(h, dt);
-    if (rc) return rc;
-    rc = nans_detect_collisions(h);
+    int rc = launch_integrate_forces(impl(h), dt);
     if (rc) return rc;
     rc = nans_solve_constraints(h, dt);
     if (rc) return rc;
     return nans_integrate_velocities(h, dt);
 }
+static int step_eager(nans_world *h, float dt)
+{
+    int rc = step_phase_a(h);
+    if (rc) return rc;
+    rc = flush_deferred(impl(h));
+    if (rc) return rc;
+    return step_phase_b(h, dt);
+}
 
 static void graph_invalidate(WorldImpl *w)
 {
     if (w->graph_exec) { cudaGraphExecDestroy(w->graph_exec); w->graph_exec = nullptr; }
+    if (w->graph_exec_b) { cudaGraphExecDestroy(w->graph_exec_b); w->graph_exec_b = nullptr; }
     if (w->graph_state > 0) w->graph_state = 0;
 }
 
@@ -710,38 +765,40 @@ int nans_step(nans_world *h, float dt)
     if (enabled < 0) { const char *e = getenv("NANS_GRAPH"); enabled = (e && atoi(e) == 0) ? 0 : 1; }
     if (!enabled || w->graph_state < 0 || w->d.nb == 0) return step_eager(h, dt);
     NANS_CUDA(cudaSetDevice(w->device));
-    if (w->graph_state == 2 && w->graph_dt == dt) {
+    auto replay = [&]() -> int {
         NANS_CUDA(cudaGraphLaunch(w->graph_exec, w->stream));
+        const int rc = flush_deferred(w);            // waits for the upload stream, unpacks forces/torques
+        if (rc) return rc;
+        NANS_CUDA(cudaGraphLaunch(w->graph_exec_b, w->stream));
         g_launches += w->graph_launches;
         w->have_contacts = true;
         return NANS_OK;
-    }
+    };
+    if (w->graph_state == 2 && w->graph_dt == dt) return replay();
     if (w->graph_state == 1 && w->graph_dt == dt) {
+        // two graphs: detection, and everything that follows the (uncaptured) deferred-input unpack
         const unsigned long long before = g_launches;
-        cudaGraph_t graph = nullptr;
-        if (cudaStreamBeginCapture(w->stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
-            cudaGetLastError();
-            w->graph_state = -1;
-            return step_eager(h, dt);
-        }
-        const int rc = step_eager(h, dt);
-        const cudaError_t ee = cudaStreamEndCapture(w->stream, &graph);
-        if (rc || ee != cudaSuccess || !graph ||
-            cudaGraphInstantiate(&w->graph_exec, graph, 0) != cudaSuccess) {
-            cudaGetLastError();
+        auto capture = [&](cudaGraphExec_t *exec, bool phase_b) -> bool {
+            cudaGraph_t graph = nullptr;
+            if (cudaStreamBeginCapture(w->stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) return false;
+            const int rc = phase_b ? step_phase_b(h, dt) : step_phase_a(h);
+            const cudaError_t ee = cudaStreamEndCapture(w->stream, &graph);
+            const bool ok = !rc && ee == cudaSuccess && graph && cudaGraphInstantiate(exec, graph, 0) == cudaSuccess;
             if (graph) cudaGraphDestroy(graph);
-            w->graph_exec = nullptr;
-            w->graph_state = -1;            // capture not possible here: stay eager
-            g_launches = before;
-            return step_eager(h, dt);
-        }
-        cudaGraphDestroy(graph);
+            if (!ok) *exec = nullptr;
+            return ok;
+        };
+        const bool ok = capture(&w->graph_exec, false) && capture(&w->graph_exec_b, true);
         w->graph_launches = (unsigned)(g_launches - before);
         g_launches = before;
+        if (!ok) {
+            cudaGetLastError();
+            graph_invalidate(w);
+            w->graph_state = -1;            // capture not possible here: stay eager
+            return step_eager(h, dt);
+        }
         w->graph_state = 2;
-        NANS_CUDA(cudaGraphLaunch(w->graph_exec, w->stream));
-        g_launches += w->graph_launches;
-        return NANS_OK;
+        return replay();
     }
     graph_invalidate(w);
     w->graph_dt = dt;
@@ -762,6 +819,7 @@ int nans_step_profiled(nans_world *h, float dt, float *stage_ms)
     if (!have) { for (auto &e : ev) NANS_CUDA(cudaEventCreate(&e)); have = true; }
     cudaStream_t s = w->stream;
     int rc;
+    if ((rc = flush_deferred(w))) return rc;
     NANS_CUDA(cudaEventRecord(ev[0], s));
     if ((rc = launch_integrate_forces(w, dt))) return rc;
     NANS_CUDA(cudaEventRecord(ev[1], s));

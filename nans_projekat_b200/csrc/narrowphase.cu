@@ -17,7 +17,7 @@ namespace nans {
 
 __device__ __forceinline__ void load_box(int side, const float4 *__restrict__ v6)
 {
-    float *p = g_np_verts + 24 * side * kNpThreads + threadIdx.x;
+    float v[24];
 #pragma unroll
     for (int q = 0; q < 6; ++q) {
 #if NANS_NP_STREAM
@@ -25,9 +25,9 @@ __device__ __forceinline__ void load_box(int side, const float4 *__restrict__ v6
 #else
         const float4 t = __ldg(v6 + q);
 #endif
-        p[(4 * q) * kNpThreads] = t.x; p[(4 * q + 1) * kNpThreads] = t.y;
-        p[(4 * q + 2) * kNpThreads] = t.z; p[(4 * q + 3) * kNpThreads] = t.w;
+        v[4 * q] = t.x; v[4 * q + 1] = t.y; v[4 * q + 2] = t.z; v[4 * q + 3] = t.w;
     }
+    NpShapes::store_box(side, v);
 }
 
 __device__ __forceinline__ NpResult dispatch(bool a_sphere, bool b_sphere, NpShapes &S, EpaArena &E,

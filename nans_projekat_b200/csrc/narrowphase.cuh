@@ -32,57 +32,86 @@ enum { kNoIntersection = 0, kFoundIntersection = 1, kStillEvolving = 2 };  // ev
 #endif
 constexpr int kNpThreads = NANS_NP_THREADS;
 constexpr int kNoVertex = 8;
-#ifndef NANS_NP_OPT_A
-#define NANS_NP_OPT_A 1   // support scan keeps (best, index) only: -2 %
-#endif
+
 #ifndef NANS_NP_OPT_C
 #define NANS_NP_OPT_C 0   // equivalence-class scan without early exit: +4 % (worse)
 #endif   // box support when every compare failed (NaN direction): vec3(0)
 
+#ifndef NANS_NP_V4
+#define NANS_NP_V4 0      // 1: box vertices in shared memory as one float4 per vertex (LDS.128); measured 7-15 % slower
+#endif
+
+#if NANS_NP_V4
+// Both shapes' box vertices, one float4 (x, y, z, -) per vertex: g_np_verts4[(8*side + k) * kNpThreads + tid].
+// A warp's LDS.128 of the same vertex is contiguous (conflict free) and a vertex fetch is one instruction.
+// File-scope __shared__ so every access compiles to LDS/STS (a pointer carried through the call chain
+// degrades to generic loads).
+__shared__ float4 g_np_verts4[16 * kNpThreads];
+constexpr int kNpSmemBytes = 16 * 16 * kNpThreads;
+#else
 // Both shapes' box vertices, transposed: g_np_verts[(24*side + 3*k + r) * kNpThreads + tid].
-// File-scope __shared__ so every access compiles to LDS/STS (a pointer carried through the call
-// chain degrades to generic loads).
 __shared__ float g_np_verts[48 * kNpThreads];
+#endif
 
 // Per-thread view of the two shapes.
 struct NpShapes {
     vec3 posA, posB;     // body centres (GJK start direction; sphere support)
     vec3 dir0;           // normalize(posB - posA): EvolveSimplex recomputes it every call (:575); hoisted
     float radA, radB;    // spheres
+    // box vertex k of a side; k = kNoVertex (every support compare failed) is vec3(0)
     __device__ __forceinline__ vec3 vertex(int side, int k) const
     {
+#if NANS_NP_V4
+        const float4 v = g_np_verts4[(8 * side + (k & 7)) * kNpThreads + threadIdx.x];
+        return k >= 8 ? V3(0.f, 0.f, 0.f) : V3(v.x, v.y, v.z);
+#else
         if (k >= 8) return V3(0.f, 0.f, 0.f);
         const float *p = g_np_verts + (24 * side + 3 * k) * kNpThreads + threadIdx.x;
         return V3(p[0], p[kNpThreads], p[2 * kNpThreads]);
+#endif
+    }
+    __device__ __forceinline__ float vertex_x(int side, int k) const
+    {
+#if NANS_NP_V4
+        return k >= 8 ? 0.f : g_np_verts4[(8 * side + (k & 7)) * kNpThreads + threadIdx.x].x;
+#else
+        return k >= 8 ? 0.f : g_np_verts[(24 * side + 3 * (k & 7)) * kNpThreads + threadIdx.x];
+#endif
+    }
+    // stage one box: v24 = its 8 packed vec3 (reference vertex order)
+    __device__ __forceinline__ static void store_box(int side, const float (&v24)[24])
+    {
+#if NANS_NP_V4
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+            g_np_verts4[(8 * side + k) * kNpThreads + threadIdx.x] = make_float4(v24[3 * k], v24[3 * k + 1], v24[3 * k + 2], 0.f);
+#else
+#pragma unroll
+        for (int q = 0; q < 24; ++q) g_np_verts[(24 * side + q) * kNpThreads + threadIdx.x] = v24[q];
+#endif
     }
 };
 
 // GetCubeSupport / GetFloorSupport, code/nans.cpp:410-430,441-461: first vertex with strictly
-// greater dot; vec3(0) if every compare fails (NaN direction)
+// greater dot; vec3(0) if every compare fails (NaN direction).  Keeps (best, index) only while
+// scanning and fetches the winner afterwards.
 __device__ __forceinline__ vec3 box_support(const NpShapes &S, int side, vec3 d, int &idx)
 {
     float best = -FLT_MAX;
     idx = kNoVertex;
-    const float *p = g_np_verts + 24 * side * kNpThreads + threadIdx.x;
-#if NANS_NP_OPT_A
-    // keep only (best, index) while scanning; fetch the winner afterwards
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
+#if NANS_NP_V4
+        const float4 c4 = g_np_verts4[(8 * side + k) * kNpThreads + threadIdx.x];
+        const vec3 c = V3(c4.x, c4.y, c4.z);
+#else
+        const float *p = g_np_verts + 24 * side * kNpThreads + threadIdx.x;
         const vec3 c = V3(p[(3 * k) * kNpThreads], p[(3 * k + 1) * kNpThreads], p[(3 * k + 2) * kNpThreads]);
+#endif
         const float dist = dot(c, d);
         if (dist > best) { best = dist; idx = k; }
     }
     return S.vertex(side, idx);
-#else
-    vec3 res = V3(0.f, 0.f, 0.f);
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-        const vec3 c = V3(p[(3 * k) * kNpThreads], p[(3 * k + 1) * kNpThreads], p[(3 * k + 2) * kNpThreads]);
-        const float dist = dot(c, d);
-        if (dist > best) { best = dist; res = c; idx = k; }
-    }
-    return res;
-#endif
 }
 // GetSphereSupport, code/nans.cpp:433-438
 __device__ __forceinline__ vec3 sphere_support(vec3 pos, float radius, vec3 d)
@@ -205,7 +234,7 @@ __device__ __forceinline__ int evolve_simplex(const NpShapes &S, GjkVertex<AS, B
 // the unflipped unit normal n with d = dot(n, A.P), and the packed vertex indices a | b<<8 | c<<16.
 // (Carrying A.P in the record as well saved a dependent load but grew the arena: 640 threads/SM x
 // the touched part already exceeds L1, and the smaller record measured 6 % faster.)
-struct EpaArena {
+struct EpaGenericArena {
     vec3 P[kEpaMaxVerts];
     vec3 SA[kEpaMaxVerts], SB[kEpaMaxVerts];    // sphere sides only
     uint8_t ia[kEpaMaxVerts], ib[kEpaMaxVerts]; // box sides only
@@ -215,13 +244,28 @@ struct EpaArena {
     uint32_t vis[kEpaMaxFaces];                 // packed indices of the faces dissolved this iteration
     uint32_t edge[kEpaMaxEdges];                // a | b<<8 | cid[a]<<16 | cid[b]<<24
 };
+// Box-box pairs (the bulk of every pile / drop world): a polytope vertex is fully described by the two box
+// vertex indices it came from (P = vertsA[ia] - vertsB[ib], both in shared memory), so the arena holds no
+// per-vertex arrays at all and nothing in the face scan is a dependent local-memory load.  A face/edge corner
+// is 16 bits: code = ia | ib<<4 (4 bits each: 8 = "no vertex", vec3(0)) and the vertex's equivalence class.
+struct EpaBoxArena {
+    float4 fnd[kEpaMaxFaces];                   // flipped unit normal (PushTriangle's N), |dot(n, A.P)|
+    uint2 fcr[kEpaMaxFaces];                    // x = code0 | code1<<8 | code2<<16, y = cid0 | cid1<<8 | cid2<<16
+    uint2 vis[kEpaMaxFaces];                    // corners of the faces dissolved this iteration
+    uint32_t edge[kEpaMaxEdges];                // codeA | codeB<<8 | cidA<<16 | cidB<<24
+    uint32_t vcw[kEpaMaxVerts / 4];             // vertex codes in vertex order, 4 per word (equivalence-class scan)
+};
+union EpaArena {
+    EpaGenericArena g;
+    EpaBoxArena b;
+};
 constexpr int kCidNaN = 254;
 
 // The reference's edge cancels an opposite-winding edge BY VALUE of P (code/nans.h:251-254).  Float
 // equality is an equivalence on non-NaN vectors (+0 == -0 included), so every vertex gets the lowest
 // index of its class once, when it is stored, and the edge compares become one integer compare.
 template <bool AS, bool BS>
-__device__ __forceinline__ void epa_store_vertex(EpaArena &E, int i, const GjkVertex<AS, BS> &v)
+__device__ __forceinline__ void epa_store_vertex(EpaGenericArena &E, int i, const GjkVertex<AS, BS> &v)
 {
     E.P[i] = v.P;
     if constexpr (AS) E.SA[i] = v.a.v; else E.ia[i] = (uint8_t)v.a.idx;
@@ -240,11 +284,11 @@ __device__ __forceinline__ void epa_store_vertex(EpaArena &E, int i, const GjkVe
     }
     E.cid[i] = (uint8_t)c;
 }
-template <bool AS> __device__ __forceinline__ vec3 epa_sup_a(const EpaArena &E, const NpShapes &S, int i)
+template <bool AS> __device__ __forceinline__ vec3 epa_sup_a(const EpaGenericArena &E, const NpShapes &S, int i)
 {
     if constexpr (AS) return E.SA[i]; else return S.vertex(0, E.ia[i]);
 }
-template <bool BS> __device__ __forceinline__ vec3 epa_sup_b(const EpaArena &E, const NpShapes &S, int i)
+template <bool BS> __device__ __forceinline__ vec3 epa_sup_b(const EpaGenericArena &E, const NpShapes &S, int i)
 {
     if constexpr (BS) return E.SB[i]; else return S.vertex(1, E.ib[i]);
 }
@@ -257,7 +301,7 @@ __device__ __forceinline__ void epa_track_min(float d, int slot, float &cur, int
     if (slot == 0 || dist < cur) { cur = dist; ci = slot; }
 }
 
-__device__ __forceinline__ void epa_push_face(EpaArena &E, int &nf, int a, int b, int c, vec3 pa, float &cur, int &ci)
+__device__ __forceinline__ void epa_push_face(EpaGenericArena &E, int &nf, int a, int b, int c, vec3 pa, float &cur, int &ci)
 {
     // PushTriangle, code/nans.cpp:293-322 (flip folded into the sign of d); pa == E.P[a]
     const vec3 n = normalize(cross(E.P[b] - pa, E.P[c] - pa));
@@ -275,7 +319,7 @@ __device__ __forceinline__ vec3 face_normal_flipped(const float4 &nd)
 
 // PushEdge, code/nans.cpp:233-266: an opposite-winding edge already in the list is erased (order of
 // the rest kept), otherwise the edge is appended
-__device__ __forceinline__ void epa_push_edge(EpaArena &E, int &ne, int a, int b, int &ovf)
+__device__ __forceinline__ void epa_push_edge(EpaGenericArena &E, int &ne, int a, int b, int &ovf)
 {
     const uint32_t ca = E.cid[a], cb = E.cid[b];
     // a NaN vertex equals nothing, itself included: its id on the probing side never matches a stored one
@@ -293,7 +337,7 @@ __device__ __forceinline__ void epa_push_edge(EpaArena &E, int &ne, int a, int b
 
 // ResolveCollision, code/nans.cpp:788-904.  Returns the bool32 result; fills PointA/PointB/N.
 template <bool AS, bool BS>
-__device__ __forceinline__ int epa_resolve(const NpShapes &S, const GjkVertex<AS, BS> (&s)[4], EpaArena &E,
+__device__ __forceinline__ int epa_resolve(const NpShapes &S, const GjkVertex<AS, BS> (&s)[4], EpaGenericArena &E,
                                            vec3 &outPA, vec3 &outPB, vec3 &outN, int &ovf, int &max_faces)
 {
 #pragma unroll
@@ -372,6 +416,160 @@ __device__ __forceinline__ int epa_resolve(const NpShapes &S, const GjkVertex<AS
     return 0;
 }
 
+// ---- EPA, box-box specialisation ---------------------------------------------------------------
+// Same algorithm and the same list orders as epa_resolve above; only where the data lives differs.
+#ifndef NANS_NP_BOX_EPA
+#define NANS_NP_BOX_EPA 0   // 1: DRAM traffic of the kernel halves (914 -> 444 MB), run time +7-10 % (more LDS/ALU work)
+#endif
+
+__device__ __forceinline__ vec3 box_corner_P(const NpShapes &S, uint32_t code)
+{
+    return S.vertex(0, code & 15) - S.vertex(1, (code >> 4) & 15);   // CalculateSupport's P = SupA - SupB
+}
+
+// appends the vertex code and returns the corner descriptor code | cid<<8 of polytope vertex i
+__device__ __forceinline__ uint32_t epa_box_store_vertex(EpaBoxArena &E, const NpShapes &S, int i, vec3 P, uint32_t code)
+{
+    uint32_t c = (uint32_t)i;
+    if (!equal(P, P)) {
+        c = kCidNaN;
+    } else {
+        // lowest earlier vertex with an equal P (by value: different box-vertex pairs can give the same point);
+        // x decides almost always, y and z are only formed when x matches
+        for (int j0 = 0; j0 < i; j0 += 4) {
+            uint32_t wv = E.vcw[j0 >> 2];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int j = j0 + k;
+                const uint32_t cj = wv & 255;
+                wv >>= 8;
+                if (j < i && c == (uint32_t)i) {
+                    if (fsub(S.vertex_x(0, cj & 15), S.vertex_x(1, cj >> 4)) == P.x && equal(box_corner_P(S, cj), P))
+                        c = (uint32_t)j;
+                }
+            }
+        }
+    }
+    const int w = i >> 2, sh = 8 * (i & 3);
+    const uint32_t old = sh ? E.vcw[w] : 0u;
+    E.vcw[w] = old | (code << sh);
+    return code | (c << 8);
+}
+
+__device__ __forceinline__ void epa_box_push_face(EpaBoxArena &E, int &nf, uint32_t c0, uint32_t c1, uint32_t c2,
+                                                  vec3 pa, vec3 pb, vec3 pc, float &cur, int &ci)
+{
+    // PushTriangle, code/nans.cpp:293-322 (flip folded into the sign of d)
+    const vec3 n = normalize(cross(pb - pa, pc - pa));
+    const float d = dot(pa, n);
+    // stored FLIPPED (PushTriangle's N, :316-320) with |d|: every later use wants exactly these two
+    const vec3 nfl = d < 0.0f ? n * -1.0f : n;
+    E.fnd[nf] = make_float4(nfl.x, nfl.y, nfl.z, fabsf(d));
+    E.fcr[nf] = make_uint2((c0 & 255) | ((c1 & 255) << 8) | ((c2 & 255) << 16),
+                           (c0 >> 8) | ((c1 >> 8) << 8) | ((c2 >> 8) << 16));
+    epa_track_min(d, nf, cur, ci);
+    ++nf;
+}
+
+// PushEdge, code/nans.cpp:233-266, on corner descriptors
+__device__ __forceinline__ void epa_box_push_edge(EpaBoxArena &E, int &ne, uint32_t codeA, uint32_t codeB,
+                                                  uint32_t ca, uint32_t cb, int &ovf)
+{
+    const uint32_t want = (cb == kCidNaN ? 255u : cb) | ((ca == kCidNaN ? 255u : ca) << 8);
+    int i = 0;
+    while (i < ne && (E.edge[i] >> 16) != want) ++i;
+    if (i < ne) {
+        for (int k = i; k < ne - 1; ++k) E.edge[k] = E.edge[k + 1];
+        --ne;
+        return;
+    }
+    if (ne >= kEpaMaxEdges) { ovf |= OVF_EPA_EDGES; return; }
+    E.edge[ne++] = codeA | (codeB << 8) | (ca << 16) | (cb << 24);
+}
+
+// ResolveCollision, code/nans.cpp:788-904, for two boxes
+__device__ __forceinline__ int epa_resolve_box(const NpShapes &S, const GjkVertex<false, false> (&s)[4], EpaBoxArena &E,
+                                               vec3 &outPA, vec3 &outPB, vec3 &outN, int &ovf, int &max_faces)
+{
+    uint32_t c[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+        c[k] = epa_box_store_vertex(E, S, k, s[k].P, (uint32_t)s[k].a.idx | ((uint32_t)s[k].b.idx << 4));
+    int nv = 4, nf = 0, ne = 0, ci = 0;
+    float cur = 0.f;
+    epa_box_push_face(E, nf, c[0], c[1], c[2], s[0].P, s[1].P, s[2].P, cur, ci);  // ABC
+    epa_box_push_face(E, nf, c[0], c[2], c[3], s[0].P, s[2].P, s[3].P, cur, ci);  // ACD
+    epa_box_push_face(E, nf, c[0], c[3], c[1], s[0].P, s[3].P, s[1].P, cur, ci);  // ADB
+    epa_box_push_face(E, nf, c[1], c[3], c[2], s[1].P, s[3].P, s[2].P, cur, ci);  // BDC
+    int it = 0;
+    while (it++ <= 64) {            // MAX_EPA_ITERATIONS, code/nans.h:56
+        max_faces = max(max_faces, nf);
+        const float4 cnd = E.fnd[ci];
+        const vec3 N = V3(cnd);
+        const GjkVertex<false, false> ns = calc_support<false, false>(S, N);
+        if (fsub(dot(N, ns.P), cur) < 0.001f) {   // MAX_EPA_ERROR, code/nans.h:55
+            const uint32_t f = E.fcr[ci].x;
+            const uint32_t k0 = f & 255, k1 = (f >> 8) & 255, k2 = (f >> 16) & 255;
+            // Barycentric, code/nans.cpp:772-785
+            const vec3 Pp = N * cur;
+            const vec3 A0 = box_corner_P(S, k0);
+            const vec3 v0 = box_corner_P(S, k1) - A0, v1 = box_corner_P(S, k2) - A0, v2 = Pp - A0;
+            const float d00 = dot(v0, v0), d01 = dot(v0, v1), d11 = dot(v1, v1);
+            const float d20 = dot(v2, v0), d21 = dot(v2, v1);
+            const float denom = fsub(fmul(d00, d11), fmul(d01, d01));
+            const float bv = fdiv(fsub(fmul(d11, d20), fmul(d01, d21)), denom);
+            const float bw = fdiv(fsub(fmul(d00, d21), fmul(d01, d20)), denom);
+            const float bu = fsub(fsub(1.0f, bv), bw);
+            if (fabsf(bu) > 1.0f || fabsf(bv) > 1.0f || fabsf(bw) > 1.0f) return 0;
+            if (!isfinite(bu) || !isfinite(bv) || !isfinite(bw)) return 0;   // IsValid, :4-17
+            outPA = ((bu * S.vertex(0, k0 & 15)) + (bv * S.vertex(0, k1 & 15))) + (bw * S.vertex(0, k2 & 15));
+            outN = -1.0f * N;
+            outPB = ((bu * S.vertex(1, k0 >> 4)) + (bv * S.vertex(1, k1 >> 4))) + (bw * S.vertex(1, k2 >> 4));
+            return 1;
+        }
+        if (nv >= kEpaMaxVerts) { ovf |= OVF_EPA_FACES; return 0; }
+        const uint32_t cn = epa_box_store_vertex(E, S, nv, ns.P, (uint32_t)ns.a.idx | ((uint32_t)ns.b.idx << 4));
+        // dissolve every face the new point can see (:869-891); survivors keep their order
+        int keep = 0, nvis = 0;
+        float4 nd_next = E.fnd[0];
+        uint2 f_next = E.fcr[0];
+        for (int i = 0; i < nf; ++i) {
+            const float4 nd = nd_next;
+            const uint2 f = f_next;
+            if (i + 1 < nf) { nd_next = E.fnd[i + 1]; f_next = E.fcr[i + 1]; }
+            const vec3 tmp = ns.P - box_corner_P(S, f.x & 255);
+            if (dot(V3(nd), tmp) > 0.0f) {
+                E.vis[nvis++] = f;
+            } else {
+                if (keep != i) { E.fnd[keep] = nd; E.fcr[keep] = f; }
+                epa_track_min(nd.w, keep, cur, ci);
+                ++keep;
+            }
+        }
+        nf = keep;
+        for (int j = 0; j < nvis; ++j) {
+            uint2 f = E.vis[j];
+#pragma unroll 1
+            for (int k = 0; k < 3; ++k) {           // AB, BC, CA
+                epa_box_push_edge(E, ne, f.x & 255, (f.x >> 8) & 255, f.y & 255, (f.y >> 8) & 255, ovf);
+                f.x = (f.x >> 8) | ((f.x & 255) << 16);
+                f.y = (f.y >> 8) | ((f.y & 255) << 16);
+            }
+        }
+        // one new face per horizon edge, in edge-list order (:894-901)
+        if (nf + ne > kEpaMaxFaces) { ovf |= OVF_EPA_FACES; return 0; }
+        for (int i = 0; i < ne; ++i) {
+            const uint32_t ed = E.edge[i];
+            const uint32_t ka = ed & 255, kb = (ed >> 8) & 255;
+            epa_box_push_face(E, nf, cn, ka | ((ed >> 16) & 255) << 8, kb | (ed >> 24) << 8,
+                              ns.P, box_corner_P(S, ka), box_corner_P(S, kb), cur, ci);
+        }
+        ne = 0;
+        ++nv;
+    }
+    return 0;
+}
+
 struct NpResult { int hit, gjk; vec3 PA, PB, N; };
 
 // CheckCollision, code/nans.cpp:907-966
@@ -387,7 +585,13 @@ __device__ __noinline__ NpResult check_collision(NpShapes &S, EpaArena &E, int &
     r.gjk = ev;
     r.hit = 0;
     r.PA = r.PB = r.N = V3(0.f, 0.f, 0.f);
-    if (ev == kFoundIntersection) r.hit = epa_resolve<AS, BS>(S, s, E, r.PA, r.PB, r.N, ovf, max_faces);
+    if (ev == kFoundIntersection) {
+#if NANS_NP_BOX_EPA
+        if constexpr (!AS && !BS) r.hit = epa_resolve_box(S, s, E.b, r.PA, r.PB, r.N, ovf, max_faces);
+        else
+#endif
+            r.hit = epa_resolve<AS, BS>(S, s, E.g, r.PA, r.PB, r.N, ovf, max_faces);
+    }
     return r;
 }
 

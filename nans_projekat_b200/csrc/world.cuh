@@ -102,7 +102,8 @@ struct World {
     bool have_contacts;
     // whole-step CUDA graph (captured on the 2nd step with an unchanged dt; any change of the launch
     // parameters -- body counts, cell size, world ids -- invalidates it)
-    cudaGraphExec_t graph_exec;
+    cudaGraphExec_t graph_exec;     // detection (broadphase, narrowphase, contact list)
+    cudaGraphExec_t graph_exec_b;   // integrate forces, solve, integrate velocities
     float graph_dt;
     int graph_state;            // 0 none, 1 one eager step seen with graph_dt, 2 captured, -1 disabled
     unsigned graph_launches;    // kernels inside the captured step

@@ -178,6 +178,62 @@ def _settle(oracle, s, steps):
     return w
 
 
+@pytest.mark.gpu
+def test_deferred_force_upload_is_visible_to_every_entry_point(nb200, oracle):
+    """A force/torque-only upload_async is unpacked lazily (after the step's detection phase, so the copy
+    overlaps broadphase + narrowphase).  Every other entry point must see it as if it had been applied
+    at once: download, add_force, a second upload of the same field, the stage calls, snapshot."""
+    from nans_projekat_b200 import scenes
+    s = scenes.cube_drop(n=600, dims=(9, 8, 9), spacing=1.05, jitter=0.04)
+    s.pos[:, 1] -= 0.4
+    w = world_from_scene(oracle, s); w.rebuild_vertices()
+    base = scene_from_oracle_world(w)
+    rng = np.random.default_rng(21)
+    f1 = rng.normal(0, 3, (base.nb, 3)).astype(np.float32); t1 = rng.normal(0, 0.5, (base.nb, 3)).astype(np.float32)
+    f2 = rng.normal(0, 3, (base.nb, 3)).astype(np.float32)
+    io1 = scenes.Scene(base.n_cubes, 0, base.n_statics); io1.force[...], io1.torque[...] = f1, t1
+    io2 = scenes.Scene(base.n_cubes, 0, base.n_statics); io2.force[...] = f2
+    ga, gb = nb200.World(base), nb200.World(base)
+    for g in (ga, gb):                       # settle into contact, graphs captured
+        for _ in range(25):
+            g.step(DT)
+    # 1) download right after the deferred upload
+    gb.upload_async(io1, fields=("force", "torque"))
+    d = gb.download(fields=("force", "torque"))
+    assert_bit_equal(d.force, f1, "deferred force visible to download"); assert_bit_equal(d.torque, t1, "torque")
+    # 2) a second upload of one field overrides the first, add_force adds on top, then a step
+    gb.upload_async(io1, fields=("force", "torque"))
+    gb.upload_async(io2, fields=("force",))
+    gb.add_force(3, (1.0, 2.0, 3.0), (0.5, 0.0, -0.5))
+    gb.step(DT)
+    ga.upload(io1, fields=("force", "torque")); ga.upload(io2, fields=("force",))
+    ga.add_force(3, (1.0, 2.0, 3.0), (0.5, 0.0, -0.5))
+    ga.step(DT)
+    da, db = ga.download(), gb.download()
+    for fld in ("pos", "vel", "ang", "angvel", "force", "torque", "verts"):
+        assert_bit_equal(getattr(db, fld), getattr(da, fld), f"after step: {fld}")
+    # 3) stage calls and snapshot/restore with an upload pending
+    gb.upload_async(io1, fields=("force", "torque")); gb.snapshot()
+    gb.integrate_forces(DT); gb.detect_collisions(); gb.solve_constraints(DT); gb.integrate_velocities(DT)
+    ga.upload(io1, fields=("force", "torque"))
+    ga.integrate_forces(DT); ga.detect_collisions(); ga.solve_constraints(DT); ga.integrate_velocities(DT)
+    da, db = ga.download(), gb.download()
+    for fld in ("pos", "vel", "ang", "angvel", "verts"):
+        assert_bit_equal(getattr(db, fld), getattr(da, fld), f"after stage calls: {fld}")
+    gb.restore()
+    d = gb.download(fields=("force", "torque"))
+    assert_bit_equal(d.force, f1, "snapshot holds the deferred force")
+    # 4) several frames of upload_async -> step -> synchronous download (the e2e loop of bench.py)
+    ga.upload(gb.download(), fields=("pos", "vel", "force", "ang", "angvel", "torque", "verts"))
+    for k in range(6):
+        io1.force[...] = rng.normal(0, 3, (base.nb, 3)).astype(np.float32)
+        gb.upload_async(io1, fields=("force", "torque")); gb.step(DT); db = gb.download(fields=("pos", "ang"))
+        ga.upload(io1, fields=("force", "torque")); ga.step(DT); da = ga.download(fields=("pos", "ang"))
+        for fld in ("pos", "ang"):
+            assert_bit_equal(getattr(db, fld), getattr(da, fld), f"e2e frame {k}: {fld}")
+    ga.close(); gb.close()
+
+
 @pytest.mark.parametrize("n,dims,steps", [(1500, (12, 11, 12), 40)])
 def test_drop_scene_steps_vs_oracle(nb200, oracle, n, dims, steps):
     """Config C2 at reduced size (cubes dropped into the static box: floor + 4 wall slabs).
