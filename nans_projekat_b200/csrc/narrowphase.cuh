@@ -175,6 +175,7 @@ template <bool AS, bool BS>
 __device__ __forceinline__ int evolve_simplex(const NpShapes &S, GjkVertex<AS, BS> (&s)[4], int &n)
 {
     vec3 dir = S.dir0;
+    bool found = false;
     if (n == 1) {
         dir = dir * -1.0f;
     } else if (n == 2) {
@@ -220,8 +221,11 @@ __device__ __forceinline__ int evolve_simplex(const NpShapes &S, GjkVertex<AS, B
         if (dot(abd, d0) > 0.0f) { simplex_erase(s, n, 2); dir = abd; }
         else if (dot(bcd, d0) > 0.0f) { simplex_erase(s, n, 0); dir = bcd; }
         else if (dot(cad, d0) > 0.0f) { simplex_erase(s, n, 1); dir = cad; }
-        else return kFoundIntersection;
+        else found = true;
     }
+    // (the origin-enclosed exit is taken HERE, after the case chain, so that the chain's branches reconverge
+    // before the support call below instead of each running it on its own)
+    if (found) return kFoundIntersection;
     if (length(dir) <= 0.0001f) return kNoIntersection;
     // AddSupport, code/nans.cpp:522-537
     const GjkVertex<AS, BS> nv = calc_support<AS, BS>(S, dir);
