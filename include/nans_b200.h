@@ -82,7 +82,8 @@ typedef struct {
     int32_t solver_levels;    /* dependency levels the exact-order solver ran */
     int32_t overflow;         /* bit0 pairs, bit1 contacts, bit2 EPA faces, bit3 EPA edges, bit4 cell list */
     int32_t max_epa_faces;    /* high-water mark of the per-thread polytope arena */
-    int32_t reserved[2];
+    int32_t accum_fallbacks;  /* contacts of the last solve whose 70-iteration accumulation took the literal loop */
+    int32_t reserved[1];
 } nans_step_stats;
 
 /* ---- lifecycle ------------------------------------------------------------------------- */

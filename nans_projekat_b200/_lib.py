@@ -30,7 +30,7 @@ class SceneView(C.Structure):
 class StepStats(C.Structure):
     _fields_ = [("n_pairs", C.c_int32), ("n_contacts", C.c_int32), ("n_gjk_found", C.c_int32),
                 ("solver_levels", C.c_int32), ("overflow", C.c_int32), ("max_epa_faces", C.c_int32),
-                ("reserved", C.c_int32 * 2)]
+                ("accum_fallbacks", C.c_int32), ("reserved", C.c_int32 * 1)]
 
 
 # every symbol include/nans_b200.h declares

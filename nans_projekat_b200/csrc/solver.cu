@@ -30,6 +30,9 @@
 #include <string.h>
 
 #include "nans_math.cuh"
+namespace nans { __device__ unsigned int g_accum_fallbacks; }   // contacts whose accumulation fell back to the literal loop
+#define NANS_ACCUM_ON_FALLBACK atomicAdd(&nans::g_accum_fallbacks, 1u)
+#include "solver_accum.cuh"
 #include "world.cuh"
 
 namespace cg = cooperative_groups;
@@ -217,67 +220,18 @@ __device__ __forceinline__ void constraint_apply(const float4 (&q)[kRecQuads], v
     const float lambdaN = fmul(fadd(-JdVn, B), JMJn);
     const float lambdaT1 = fmul(-JdVt1, JMJt1);
     const float lambdaT2 = fmul(-JdVt2, JMJt2);
-    const double kFric = 1.4142135623730951 * (double)0.1f;   // sqrt(2) * Cf, evaluated in fp64 (:1197)
-    // Three dependency chains per iteration: the normal sum, and the two tangent sums clamped by a
-    // bound derived (in fp64) from the normal sum of the SAME iteration.  This runs on a warp that is
-    // usually alone on its scheduler, so the chains are software-pipelined by hand: the normal chain
-    // (and the fp64 bound) runs kBlk iterations ahead of the tangent chains.
-    float DLN = 0.f, sumN = 0.f, DLT1 = 0.f, sumT1 = 0.f, DLT2 = 0.f, sumT2 = 0.f;
-    constexpr int kBlk = 10;
-    float bound[kBlk], bound_next[kBlk];
+    // the 70-iteration accumulation (solver_accum.cuh); NaN increments poison the sums: literal compares
+    AccumDeltas acc;
     if (lambdaN == lambdaN && lambdaT1 == lambdaT1 && lambdaT2 == lambdaT2) {
-        // No NaN among the increments: then no sum is ever NaN and none is ever -0.0 where it matters, so
-        //   if (s < lo) s = lo; if (s > hi) s = hi;   ==   fminf(fmaxf(s, lo), hi)
-        // bit for bit (a NaN BOUND leaves s alone in both forms; max(+0,-0) = +0 and min(-0,+0) = -0 are
-        // what the compares leave too).  Half the instructions and a shorter chain per iteration; only the
-        // last iteration's deltas are ever used, so they are formed after the loop.
-        float oldN = 0.f, oldT1 = 0.f, oldT2 = 0.f;
-        auto normal_step = [&]() -> float {
-            oldN = sumN;
-            sumN = fmaxf(fadd(sumN, lambdaN), 0.0f);
-            return __double2float_rn(__dmul_rn(kFric, (double)sumN));
-        };
-#pragma unroll
-        for (int j = 0; j < kBlk; ++j) bound_next[j] = normal_step();
-#pragma unroll 1
-        for (int blk = 0; blk < 70 / kBlk; ++blk) {
-#pragma unroll
-            for (int j = 0; j < kBlk; ++j) bound[j] = bound_next[j];
-            const bool more = blk + 1 < 70 / kBlk;
-#pragma unroll
-            for (int j = 0; j < kBlk; ++j) {
-                if (more) bound_next[j] = normal_step();
-                const float maxT = bound[j];
-                oldT1 = sumT1;
-                sumT1 = fminf(fmaxf(fadd(sumT1, lambdaT1), -maxT), maxT);
-                oldT2 = sumT2;
-                sumT2 = fminf(fmaxf(fadd(sumT2, lambdaT2), -maxT), maxT);
-            }
-        }
-        DLN = fsub(sumN, oldN);
-        DLT1 = fsub(sumT1, oldT1);
-        DLT2 = fsub(sumT2, oldT2);
+#if NANS_ACCUM_FAST
+        acc = accumulate_fast(lambdaN, lambdaT1, lambdaT2);
+#else
+        acc = accumulate_pipelined(lambdaN, lambdaT1, lambdaT2);
+#endif
     } else {
-        // the reference's compares, literally (NaN increments poison the sums)
-#pragma unroll 1
-        for (int it = 0; it < 70; ++it) {
-            const float oldN = sumN;
-            sumN = fadd(sumN, lambdaN);
-            if (sumN < 0) sumN = 0.0f;
-            DLN = fsub(sumN, oldN);
-            const float maxT = __double2float_rn(__dmul_rn(kFric, (double)sumN));
-            const float oldT1 = sumT1;
-            sumT1 = fadd(sumT1, lambdaT1);
-            if (sumT1 < -maxT) sumT1 = -maxT;
-            if (sumT1 > maxT) sumT1 = maxT;
-            DLT1 = fsub(sumT1, oldT1);
-            const float oldT2 = sumT2;
-            sumT2 = fadd(sumT2, lambdaT2);
-            if (sumT2 < -maxT) sumT2 = -maxT;
-            if (sumT2 > maxT) sumT2 = maxT;
-            DLT2 = fsub(sumT2, oldT2);
-        }
+        acc = accumulate_literal(lambdaN, lambdaT1, lambdaT2);
     }
+    const float DLN = acc.DLN, DLT1 = acc.DLT1, DLT2 = acc.DLT2;
     const vec3 LI = N * DLN, LIT1 = T1 * DLT1, LIT2 = T2 * DLT2;
     const vec3 AI1 = RN1 * DLN, AI2 = RN2 * DLN;
     const vec3 AI1T1 = R1T1 * DLT1, AI2T1 = R2T1 * DLT1;
@@ -705,6 +659,11 @@ int launch_solver(World *w, float dt)
     NANS_CUDA(cudaMemsetAsync(d.deg, 0, sizeof(uint32_t) * ((size_t)d.nb + 1), s));
     NANS_CUDA(cudaMemsetAsync(d.cursor, 0, sizeof(uint32_t) * (size_t)d.nb, s));
     NANS_CUDA(cudaMemsetAsync(d.counters->frontier_n, 0, sizeof(int32_t) * 3, s));
+    {
+        void *fb = nullptr;
+        NANS_CUDA(cudaGetSymbolAddress(&fb, g_accum_fallbacks));
+        NANS_CUDA(cudaMemsetAsync(fb, 0, sizeof(unsigned int), s));
+    }
     const int grid = min(div_up(d.max_contacts, 256), kNumSMs * 8);
     incidence_count_kernel<<<grid, 256, 0, s>>>(d, mode == 2);
     NANS_LAUNCH_CHECK();
@@ -785,4 +744,15 @@ int launch_solver(World *w, float dt)
     return NANS_OK;
 }
 
+}  // namespace nans
+
+namespace nans {
+int solver_accum_fallbacks(World *w, int32_t *out)
+{
+    unsigned int v = 0;
+    NANS_CUDA(cudaStreamSynchronize(w->stream));
+    NANS_CUDA(cudaMemcpyFromSymbol(&v, g_accum_fallbacks, sizeof(v)));
+    *out = (int32_t)v;
+    return NANS_OK;
+}
 }  // namespace nans

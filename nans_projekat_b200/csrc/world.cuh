@@ -139,6 +139,7 @@ int launch_broadphase(World *w);
 int launch_narrowphase(World *w);
 int launch_contacts(World *w);
 int launch_solver(World *w, float dt);
+int solver_accum_fallbacks(World *w, int32_t *out);
 int launch_aabb_only(World *w);
 int slab_bounds(World *w, float *scratch, float *out6_dev);
 int slab_pack_halo(World *w, const float box[6], int gid_base, float4 *out, int32_t *sent_rows, int cap,
