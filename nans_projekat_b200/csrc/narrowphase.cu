@@ -3,10 +3,20 @@
 // a global counter (pairs differ by >10x in work: a GJK miss is one support call, an EPA hit is
 // dozens), grid = SM count x resident CTAs.  FP32-pipe / divergence bound, not HBM bound:
 // 216 B in + 48 B out per pair against ~1-5 kflop of unfused fp32.
+#include <stdlib.h>
+
 #include "narrowphase.cuh"
 
 #ifndef NANS_NP_MINBLOCKS
 #define NANS_NP_MINBLOCKS 5   // 96 registers/thread: best of the sweep in profiles/ (4: 128 regs, 6: 80 regs + spills)
+#endif
+
+#ifndef NANS_GJK_MINBLOCKS
+#define NANS_GJK_MINBLOCKS 6   // GJK-only kernel of the split path (80 registers)
+#endif
+
+#ifndef NANS_EPA_MINBLOCKS
+#define NANS_EPA_MINBLOCKS 5   // EPA refill kernel of the split path
 #endif
 
 #ifndef NANS_NP_STREAM
@@ -139,6 +149,207 @@ __global__ void __launch_bounds__(kNpThreads, NANS_NP_MINBLOCKS) narrowphase_bat
     }
 }
 
+// ---- split narrowphase: GJK over every pair, then EPA with lane refill over the intersecting ones ----------
+// In the one-kernel form a lane that misses (or converges early) idles until the slowest pair of its 32-pair
+// chunk is done.  Where hits are sparse or EPA lengths spread widely (random pairs, config C3: 48 % hits, EPA
+// 1-65 iterations; EPA is 89 % of that run) most lanes idle most of the time.  Here a first kernel runs GJK
+// only and appends the intersecting pairs to one list per shape-type class together with their final simplex
+// (128 B record: per vertex the two support points, or the two box vertex indices); a second, persistent
+// kernel runs EPA as the resumable state machine of narrowphase.cuh: a lane whose pair has finished takes the
+// next pair of the list at once.  Results are written per pair, so the list order (atomics) is not observable.
+struct SplitScratch {
+    int32_t *head;        // [cls] pairs listed, [4 + cls] tickets taken
+    int32_t *list[4];     // pair indices, class = 2 * a_sphere + b_sphere
+    float4 *rec;          // [pairs][8]: simplex of pair p (4 x support A, 4 x support B)
+};
+
+struct BatchSrc {
+    int n;
+    const int32_t *type;
+    const float4 *posrad_a, *verts_a, *posrad_b, *verts_b;
+    int32_t *hit, *gjk;
+    float4 *out;
+    __device__ __forceinline__ int n_pairs() const { return n; }
+    __device__ __forceinline__ void classify(int p, bool &as, bool &bs) const
+    {
+        const int t = type[p];
+        as = (t == NANS_SS || t == NANS_SF);
+        bs = (t == NANS_CS || t == NANS_SS);
+    }
+    __device__ __forceinline__ void load(int p, bool as, bool bs, NpShapes &S) const
+    {
+        const float4 pa = posrad_a[p], pb = posrad_b[p];
+        S.posA = V3(pa); S.radA = pa.w;
+        S.posB = V3(pb); S.radB = pb.w;
+        if (!as) load_box(0, verts_a + 6 * (size_t)p);
+        if (!bs) load_box(1, verts_b + 6 * (size_t)p);
+    }
+    __device__ __forceinline__ void store_gjk(int p, int ev) const
+    {
+        hit[p] = 0;
+        if (gjk) gjk[p] = ev;
+        float4 *o = out + 3 * (size_t)p;
+        o[0] = o[1] = o[2] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    __device__ __forceinline__ void store_hit(int p, vec3 PA, vec3 PB, vec3 N) const
+    {
+        hit[p] = 1;
+        float4 *o = out + 3 * (size_t)p;
+        o[0] = make_float4(PA.x, PA.y, PA.z, 0.f);
+        o[1] = make_float4(PB.x, PB.y, PB.z, 0.f);
+        o[2] = make_float4(N.x, N.y, N.z, 0.f);
+    }
+};
+
+template <bool SPHERE> __device__ __forceinline__ float4 pack_sup(const SupRec<SPHERE> &r)
+{
+    if constexpr (SPHERE) return make_float4(r.v.x, r.v.y, r.v.z, 0.f);
+    else return make_float4(__int_as_float(r.idx), 0.f, 0.f, 0.f);
+}
+template <bool SPHERE> __device__ __forceinline__ vec3 unpack_sup(const NpShapes &S, int side, float4 q, SupRec<SPHERE> &r)
+{
+    if constexpr (SPHERE) { r.v = V3(q); return r.v; }
+    else { r.idx = __float_as_int(q.x); return S.vertex(side, r.idx); }
+}
+
+// GJK of one pair; an intersecting pair is appended to its class list with its simplex
+template <bool AS, bool BS, typename Src>
+__device__ __noinline__ int gjk_and_list(const Src &src, const SplitScratch &sc, NpShapes &S, int p)
+{
+    GjkVertex<AS, BS> s[4];
+    const int ev = gjk_run<AS, BS>(S, s);
+    const bool found = ev == kFoundIntersection;
+    // warp-aggregated append (the lanes converged here all belong to this class)
+    const unsigned act = __activemask();
+    const unsigned m = __ballot_sync(act, found);
+    if (found) {
+        const int lane = threadIdx.x & 31, leader = __ffs(m) - 1;
+        constexpr int cls = 2 * (int)AS + (int)BS;
+        int base = 0;
+        if (lane == leader) base = atomicAdd(sc.head + cls, __popc(m));
+        base = __shfl_sync(m, base, leader);
+        sc.list[cls][base + __popc(m & ((1u << lane) - 1u))] = p;
+        float4 *r = sc.rec + 8 * (size_t)p;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { r[k] = pack_sup<AS>(s[k].a); r[4 + k] = pack_sup<BS>(s[k].b); }
+    }
+    return ev;
+}
+
+template <typename Src>
+__global__ void __launch_bounds__(kNpThreads, NANS_GJK_MINBLOCKS) gjk_split_kernel(Src src, SplitScratch sc, int *work_counter, int32_t *n_found)
+{
+    const int lane = threadIdx.x & 31;
+    const int n_pairs = src.n_pairs();
+    int found = 0;
+    NpShapes S;
+    while (true) {
+        int base = 0;
+        if (lane == 0) base = atomicAdd(work_counter, 32);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (base >= n_pairs) break;
+        const int p = base + lane;
+        if (p < n_pairs) {
+            bool as, bs;
+            src.classify(p, as, bs);
+            src.load(p, as, bs, S);
+            int ev;
+            if (!as && !bs) ev = gjk_and_list<false, false>(src, sc, S, p);
+            else if (!as && bs) ev = gjk_and_list<false, true>(src, sc, S, p);
+            else if (as && !bs) ev = gjk_and_list<true, false>(src, sc, S, p);
+            else ev = gjk_and_list<true, true>(src, sc, S, p);
+            src.store_gjk(p, ev);
+            found += ev == kFoundIntersection;
+        }
+    }
+    if (n_found) {
+        found = __reduce_add_sync(0xffffffffu, found);
+        if (lane == 0 && found) atomicAdd(n_found, found);
+    }
+}
+
+#ifndef NANS_EPA_REFILL_MIN
+#define NANS_EPA_REFILL_MIN 32    // idle lanes of a warp before it fetches new pairs
+#endif
+
+// EPA over one class list.  A warp takes new pairs whenever NANS_EPA_REFILL_MIN of its lanes are idle.
+// 32 (= whole chunks of the COMPACTED list) measured best on config C3: 16 Mi pairs in 29.6 ms against 30.6
+// (16), 31.9 (8), 33.8 (4), 35.4 ms (1) and 40.9 ms for the one-kernel form -- lanes at different iteration
+// numbers carry polytopes of very different sizes, and in lock step every lane pays for the largest one in
+// its warp, which costs more than the idle lanes of a chunk do.  Also measured and dropped: iteration caps
+// with the long pairs deferred to a second list and restarted from their simplex next to pairs of their
+// own length (EPA lengths on random cube-sphere pairs: median 9, 99 % <= 24, up to 57): -5 % at best, the
+// repeated iterations cost what the better packing saves.
+template <bool AS, bool BS, typename Src>
+__device__ __noinline__ void epa_refill_list(const Src &src, const SplitScratch &sc, NpShapes &S, EpaArena &E,
+                                             int &ovf, int &max_faces)
+{
+    constexpr int cls = 2 * (int)AS + (int)BS;
+    constexpr unsigned kFull = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const int32_t *list = sc.list[cls];
+    const int count = sc.head[cls];
+    bool active = false, more = count > 0;
+    int p = 0;
+    EpaState st;
+    vec3 PA, PB, N;
+    while (true) {
+        __syncwarp();
+        const unsigned idle = __ballot_sync(kFull, !active);
+        if (more && (idle == kFull || __popc(idle) >= NANS_EPA_REFILL_MIN)) {
+            int base = 0;
+            if (lane == 0) base = atomicAdd(sc.head + 4 + cls, __popc(idle));
+            base = __shfl_sync(kFull, base, 0);
+            const int k = base + __popc(idle & ((1u << lane) - 1u));
+            if (!active && k < count) {
+                p = list[k];
+                src.load(p, AS, BS, S);
+                const float4 *r = sc.rec + 8 * (size_t)p;
+                GjkVertex<AS, BS> s[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const vec3 sa = unpack_sup<AS>(S, 0, r[j], s[j].a);
+                    const vec3 sb = unpack_sup<BS>(S, 1, r[4 + j], s[j].b);
+                    s[j].P = sa - sb;                 // CalculateSupport's P, same operands, same bits
+                }
+                epa_begin<AS, BS>(s, E.g, st);
+                active = true;
+            }
+            more = base + __popc(idle) < count;
+        }
+        __syncwarp();
+        if (!__any_sync(kFull, active)) {
+            if (!more) break;
+            continue;
+        }
+        if (active) {
+            const int r = epa_step<AS, BS>(S, E.g, st, PA, PB, N, ovf, max_faces);
+            if (r != kEpaContinue) {
+                if (r) src.store_hit(p, PA, PB, N);
+                active = false;
+            }
+        }
+    }
+}
+
+template <typename Src>
+__global__ void __launch_bounds__(kNpThreads, NANS_EPA_MINBLOCKS) epa_refill_kernel(Src src, SplitScratch sc, Counters *counters)
+{
+    EpaArena E;
+    NpShapes S;
+    int ovf = 0, max_faces = 0;
+    epa_refill_list<false, false>(src, sc, S, E, ovf, max_faces);
+    epa_refill_list<false, true>(src, sc, S, E, ovf, max_faces);
+    epa_refill_list<true, false>(src, sc, S, E, ovf, max_faces);
+    epa_refill_list<true, true>(src, sc, S, E, ovf, max_faces);
+    ovf = __reduce_or_sync(0xffffffffu, ovf);
+    max_faces = __reduce_max_sync(0xffffffffu, max_faces);
+    if ((threadIdx.x & 31) == 0 && counters) {
+        if (ovf) atomicOr(&counters->overflow, ovf);
+        atomicMax(&counters->max_epa_faces, max_faces);
+    }
+}
+
 static int np_grid(int blocks_needed)
 {
     static int per_sm = 0;
@@ -163,16 +374,70 @@ int launch_narrowphase(World *w)
     return NANS_OK;
 }
 
+// device scratch of the split path, grown on demand and kept (one per process; the batch entry points are
+// not re-entrant across streams)
+static int split_scratch(int n, SplitScratch &sc)
+{
+    static char *blk = nullptr;
+    static size_t cap = 0;
+    const size_t need = 256 + 4 * sizeof(int32_t) * (size_t)n + 8 * sizeof(float4) * (size_t)n;
+    if (need > cap) {
+        if (blk) NANS_CUDA(cudaFree(blk));
+        blk = nullptr; cap = 0;
+        NANS_CUDA(cudaMalloc(&blk, need));
+        cap = need;
+    }
+    sc.head = reinterpret_cast<int32_t *>(blk);
+    sc.rec = reinterpret_cast<float4 *>(blk + 256);
+    int32_t *l = reinterpret_cast<int32_t *>(blk + 256 + 8 * sizeof(float4) * (size_t)n);
+    for (int k = 0; k < 4; ++k) sc.list[k] = l + (size_t)k * n;
+    return NANS_OK;
+}
+
 int launch_narrowphase_batch(int n, const int32_t *type, const float4 *posrad_a, const float4 *verts_a,
                              const float4 *posrad_b, const float4 *verts_b, int32_t *hit, int32_t *gjk,
                              float4 *out, int *work_counter, Counters *counters, cudaStream_t s)
 {
     if (n <= 0) return NANS_OK;
-    NANS_CUDA(cudaMemsetAsync(work_counter, 0, sizeof(int), s));
-    const int grid = np_grid(div_up(n, kNpThreads));
-    narrowphase_batch_kernel<<<grid, kNpThreads, 0, s>>>(n, type, posrad_a, verts_a, posrad_b, verts_b, hit, gjk,
-                                                         out, work_counter, counters);
-    NANS_LAUNCH_CHECK();
+    static int split = -1;
+    if (split < 0) { const char *e = getenv("NANS_NP_SPLIT"); split = (e && atoi(e) == 0) ? 0 : 1; }
+    if (!split) {
+        NANS_CUDA(cudaMemsetAsync(work_counter, 0, sizeof(int), s));
+        const int grid = np_grid(div_up(n, kNpThreads));
+        narrowphase_batch_kernel<<<grid, kNpThreads, 0, s>>>(n, type, posrad_a, verts_a, posrad_b, verts_b, hit, gjk,
+                                                             out, work_counter, counters);
+        NANS_LAUNCH_CHECK();
+        return NANS_OK;
+    }
+    // at most kSplitChunk pairs per round (bounds the scratch: 144 B per pair)
+    constexpr int kSplitChunk = 1 << 24;   // (scratch: 144 B per pair)
+    static int gjk_per_sm = 0, epa_per_sm = 0;
+    if (!gjk_per_sm) {
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&gjk_per_sm, gjk_split_kernel<BatchSrc>, kNpThreads, 0);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&epa_per_sm, epa_refill_kernel<BatchSrc>, kNpThreads, 0);
+        if (gjk_per_sm < 1) gjk_per_sm = 1;
+        if (epa_per_sm < 1) epa_per_sm = 1;
+    }
+    for (int o = 0; o < n; o += kSplitChunk) {
+        const int m = n - o < kSplitChunk ? n - o : kSplitChunk;
+        SplitScratch sc;
+        const int rc = split_scratch(m, sc);
+        if (rc) return rc;
+        BatchSrc src;
+        src.n = m; src.type = type + o;
+        src.posrad_a = posrad_a + o; src.verts_a = verts_a ? verts_a + 6 * (size_t)o : nullptr;
+        src.posrad_b = posrad_b + o; src.verts_b = verts_b ? verts_b + 6 * (size_t)o : nullptr;
+        src.hit = hit + o; src.gjk = gjk ? gjk + o : nullptr; src.out = out + 3 * (size_t)o;
+        NANS_CUDA(cudaMemsetAsync(sc.head, 0, 256, s));
+        NANS_CUDA(cudaMemsetAsync(work_counter, 0, sizeof(int), s));
+        const int need = div_up(m, kNpThreads);
+        const int g1 = need < kNumSMs * gjk_per_sm ? need : kNumSMs * gjk_per_sm;
+        gjk_split_kernel<BatchSrc><<<g1, kNpThreads, 0, s>>>(src, sc, work_counter, nullptr);
+        NANS_LAUNCH_CHECK();
+        const int g2 = need < kNumSMs * epa_per_sm ? need : kNumSMs * epa_per_sm;
+        epa_refill_kernel<BatchSrc><<<g2, kNpThreads, 0, s>>>(src, sc, counters);
+        NANS_LAUNCH_CHECK();
+    }
     return NANS_OK;
 }
 

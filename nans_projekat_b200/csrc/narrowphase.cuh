@@ -420,6 +420,107 @@ __device__ __forceinline__ int epa_resolve(const NpShapes &S, const GjkVertex<AS
     return 0;
 }
 
+// ---- EPA as a resumable state machine ------------------------------------------------------------
+// The same algorithm cut at the iteration boundary, so that a lane can finish one pair and start the next
+// while its neighbours are in the middle of theirs (epa_refill_kernel): a step = "create the faces the
+// previous step (or the start) left pending, then one iteration up to the horizon edges".  The pending
+// faces are vertex triples in E.edge: the start leaves the four tetrahedron faces ABC, ACD, ADB, BDC
+// (:799-802), an iteration leaves (new vertex, e.A, e.B) per horizon edge (:894-901).  Face creation is ONE
+// loop for both, so a lane that has just started shares its instructions with lanes in mid-flight.
+struct EpaState {
+    int nv, nf, ne, ci, it;
+    int newv;      // >= 0: E.edge holds horizon edges of vertex newv; < 0: E.edge holds explicit triples
+    float cur;
+};
+enum { kEpaContinue = 2 };   // epa_step: 0 = no collision, 1 = collision (outputs filled), 2 = call again
+
+template <bool AS, bool BS>
+__device__ __forceinline__ void epa_begin(const GjkVertex<AS, BS> (&s)[4], EpaGenericArena &E, EpaState &st)
+{
+#pragma unroll
+    for (int k = 0; k < 4; ++k) epa_store_vertex<AS, BS>(E, k, s[k]);
+    E.edge[0] = 0u | (1u << 8) | (2u << 16);   // ABC
+    E.edge[1] = 0u | (2u << 8) | (3u << 16);   // ACD
+    E.edge[2] = 0u | (3u << 8) | (1u << 16);   // ADB
+    E.edge[3] = 1u | (3u << 8) | (2u << 16);   // BDC
+    st.nv = 4; st.nf = 0; st.ne = 4; st.ci = 0; st.it = 0; st.newv = -1; st.cur = 0.f;
+}
+
+template <bool AS, bool BS>
+__device__ __forceinline__ int epa_step(const NpShapes &S, EpaGenericArena &E, EpaState &st,
+                                        vec3 &outPA, vec3 &outPB, vec3 &outN, int &ovf, int &max_faces)
+{
+    int nf = st.nf, ci = st.ci;
+    float cur = st.cur;
+    // pending faces, in list order
+    if (nf + st.ne > kEpaMaxFaces) { ovf |= OVF_EPA_FACES; return 0; }
+    for (int i = 0; i < st.ne; ++i) {
+        const uint32_t ed = E.edge[i];
+        const bool tri = st.newv < 0;
+        const int a = tri ? (int)(ed & 255) : st.newv;
+        const int b = tri ? (int)((ed >> 8) & 255) : (int)(ed & 255);
+        const int c = tri ? (int)((ed >> 16) & 255) : (int)((ed >> 8) & 255);
+        epa_push_face(E, nf, a, b, c, E.P[a], cur, ci);
+    }
+    st.ne = 0;
+    if (st.it++ > 64) { st.nf = nf; return 0; }   // MAX_EPA_ITERATIONS, code/nans.h:56: while (it++ <= 64)
+    max_faces = max(max_faces, nf);
+    const float4 cnd = E.fnd[ci];
+    const vec3 N = face_normal_flipped(cnd);
+    const GjkVertex<AS, BS> ns = calc_support<AS, BS>(S, N);
+    if (fsub(dot(N, ns.P), cur) < 0.001f) {   // MAX_EPA_ERROR, code/nans.h:55
+        const uint32_t f = E.fidx[ci];
+        const int a = f & 255, b = (f >> 8) & 255, c = (f >> 16) & 255;
+        // Barycentric, code/nans.cpp:772-785
+        const vec3 Pp = N * cur;
+        const vec3 A0 = E.P[a];
+        const vec3 v0 = E.P[b] - A0, v1 = E.P[c] - A0, v2 = Pp - A0;
+        const float d00 = dot(v0, v0), d01 = dot(v0, v1), d11 = dot(v1, v1);
+        const float d20 = dot(v2, v0), d21 = dot(v2, v1);
+        const float denom = fsub(fmul(d00, d11), fmul(d01, d01));
+        const float bv = fdiv(fsub(fmul(d11, d20), fmul(d01, d21)), denom);
+        const float bw = fdiv(fsub(fmul(d00, d21), fmul(d01, d20)), denom);
+        const float bu = fsub(fsub(1.0f, bv), bw);
+        if (fabsf(bu) > 1.0f || fabsf(bv) > 1.0f || fabsf(bw) > 1.0f) return 0;
+        if (!isfinite(bu) || !isfinite(bv) || !isfinite(bw)) return 0;   // IsValid, :4-17
+        outPA = ((bu * epa_sup_a<AS>(E, S, a)) + (bv * epa_sup_a<AS>(E, S, b))) + (bw * epa_sup_a<AS>(E, S, c));
+        outN = -1.0f * N;
+        outPB = ((bu * epa_sup_b<BS>(E, S, a)) + (bv * epa_sup_b<BS>(E, S, b))) + (bw * epa_sup_b<BS>(E, S, c));
+        return 1;
+    }
+    if (st.nv >= kEpaMaxVerts) { ovf |= OVF_EPA_FACES; return 0; }
+    epa_store_vertex<AS, BS>(E, st.nv, ns);
+    // dissolve every face the new point can see (:869-891); survivors keep their order
+    int keep = 0, nvis = 0, ne = 0;
+    float4 nd_next = E.fnd[0];
+    uint32_t f_next = E.fidx[0];
+    for (int i = 0; i < nf; ++i) {
+        const float4 nd = nd_next;
+        const uint32_t f = f_next;
+        if (i + 1 < nf) { nd_next = E.fnd[i + 1]; f_next = E.fidx[i + 1]; }
+        const vec3 tmp = ns.P - E.P[f & 255];
+        if (dot(face_normal_flipped(nd), tmp) > 0.0f) {
+            E.vis[nvis++] = f;
+        } else {
+            if (keep != i) { E.fnd[keep] = nd; E.fidx[keep] = f; }
+            epa_track_min(nd.w, keep, cur, ci);
+            ++keep;
+        }
+    }
+    for (int j = 0; j < nvis; ++j) {
+        uint32_t f = E.vis[j];
+#pragma unroll 1
+        for (int k = 0; k < 3; ++k) {           // AB, BC, CA
+            epa_push_edge(E, ne, f & 255, (f >> 8) & 255, ovf);
+            f = (f >> 8) | ((f & 255) << 16);
+        }
+    }
+    st.nf = keep; st.ne = ne; st.ci = ci; st.cur = cur;
+    st.newv = st.nv;
+    ++st.nv;
+    return kEpaContinue;
+}
+
 // ---- EPA, box-box specialisation ---------------------------------------------------------------
 // Same algorithm and the same list orders as epa_resolve above; only where the data lives differs.
 #ifndef NANS_NP_BOX_EPA
@@ -576,25 +677,47 @@ __device__ __forceinline__ int epa_resolve_box(const NpShapes &S, const GjkVerte
 
 struct NpResult { int hit, gjk; vec3 PA, PB, N; };
 
+// the GJK loop of CheckCollision (:957-965): the evolve_result it ended with; s = the final simplex
+template <bool AS, bool BS>
+__device__ __forceinline__ int gjk_run(NpShapes &S, GjkVertex<AS, BS> (&s)[4])
+{
+    int n = 0, ev = kStillEvolving, iter = 0;
+    S.dir0 = normalize(S.posB - S.posA);
+    while (ev == kStillEvolving && iter++ <= 64)   // MAX_GJK_ITERATIONS, code/nans.h:54
+        ev = evolve_simplex<AS, BS>(S, s, n);
+    return ev;
+}
+
 // CheckCollision, code/nans.cpp:907-966
 template <bool AS, bool BS>
 __device__ __noinline__ NpResult check_collision(NpShapes &S, EpaArena &E, int &ovf, int &max_faces)
 {
     GjkVertex<AS, BS> s[4];
-    int n = 0, ev = kStillEvolving, iter = 0;
-    S.dir0 = normalize(S.posB - S.posA);
-    while (ev == kStillEvolving && iter++ <= 64)   // MAX_GJK_ITERATIONS, code/nans.h:54
-        ev = evolve_simplex<AS, BS>(S, s, n);
+    const int ev = gjk_run<AS, BS>(S, s);
     NpResult r;
     r.gjk = ev;
     r.hit = 0;
     r.PA = r.PB = r.N = V3(0.f, 0.f, 0.f);
+#ifdef NANS_NP_SKIP_EPA   // timing experiment only: GJK without EPA
+    if (false) {
+#else
     if (ev == kFoundIntersection) {
+#endif
 #if NANS_NP_BOX_EPA
         if constexpr (!AS && !BS) r.hit = epa_resolve_box(S, s, E.b, r.PA, r.PB, r.N, ovf, max_faces);
         else
 #endif
+#ifdef NANS_NP_STEPPED   // the resumable form run to completion (host check of epa_begin / epa_step)
+        {
+            EpaState st;
+            epa_begin<AS, BS>(s, E.g, st);
+            int rr;
+            do rr = epa_step<AS, BS>(S, E.g, st, r.PA, r.PB, r.N, ovf, max_faces); while (rr == kEpaContinue);
+            r.hit = rr;
+        }
+#else
             r.hit = epa_resolve<AS, BS>(S, s, E.g, r.PA, r.PB, r.N, ovf, max_faces);
+#endif
     }
     return r;
 }

@@ -1,8 +1,9 @@
 """The DEVICE narrowphase source (nans_projekat_b200/csrc/narrowphase.cuh, the code the CUDA kernels run)
 compiled as host C++ (tests/np_host_shim.cpp: one thread, __shared__ = static storage, __f*_rn = plain IEEE
 fp32 with -ffp-contract=off) and checked bit for bit against the oracle.  It proves the algorithm of the
-kernel source without a GPU; the GPU tests prove the compiled kernels.  Both EPA data layouts are checked
-(the default per-vertex arena and the gated box-box specialisation)."""
+kernel source without a GPU; the GPU tests prove the compiled kernels.  Checked: the one-loop EPA of the world
+kernel, the resumable epa_begin / epa_step form the split batch path runs ("stepped"), and the gated box-box
+specialisation."""
 import ctypes as C
 import os
 import subprocess
@@ -29,7 +30,8 @@ def _build(name, flags):
     return C.CDLL(out)
 
 
-@pytest.fixture(scope="module", params=[("default", []), ("boxepa", ["-DNANS_NP_BOX_EPA=1"]),
+@pytest.fixture(scope="module", params=[("default", []), ("stepped", ["-DNANS_NP_STEPPED"]),
+                                        ("boxepa", ["-DNANS_NP_BOX_EPA=1"]),
                                         ("boxepa_v4", ["-DNANS_NP_BOX_EPA=1", "-DNANS_NP_V4=1"])],
                 ids=lambda p: p[0])
 def host_np(request):
