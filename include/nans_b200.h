@@ -109,7 +109,13 @@ int nans_world_set_body(nans_world *w, int32_t body_row, const float pos[3], con
  * their own streams and overlap the step.  Host buffers should be pinned and must stay valid until the
  * copy completes (upload: until the next nans_step has been issued and nans_world_wait(w, -1) or a later
  * download ticket returned; download: until nans_world_wait on its ticket).  Fields: pos, vel, force, ang,
- * angvel, torque.  The reference's frame is synchronous (code/sdl_nans.cpp:986); use the calls above for that. */
+ * angvel, torque.  The reference's frame is synchronous (code/sdl_nans.cpp:986); use the calls above for that.
+ *
+ * An upload that carries ONLY force and/or torque is additionally deferred: nans_step runs collision detection
+ * first (it reads neither forces nor velocities, so it commutes with integrate-forces bit for bit) and unpacks
+ * the uploaded rows just before integrate-forces, so the copy overlaps broadphase + narrowphase even when the
+ * same frame's poses are then read back synchronously (upload_async -> step -> download: the loop bench.py
+ * times as e2e).  Every other entry point sees the upload as already applied. */
 int nans_world_upload_async(nans_world *w, const nans_scene_view *scene);
 int nans_world_download_async(nans_world *w, nans_scene_view *scene, int32_t *ticket);
 int nans_world_wait(nans_world *w, int32_t ticket);   /* ticket < 0: everything outstanding */
@@ -142,7 +148,10 @@ int nans_integrate_velocities(nans_world *w, float dt); /* IntegrateVelocities c
 /* the draw section's model rebuild on its own (code/nans.cpp:1870-1881,1913-1941 + UpdateVertices
  * :395-407): Model = T*Rx*Ry*Rz*S -> 8 world vertices for every cube and static, from the pose */
 int nans_rebuild_vertices(nans_world *w);
-/* the step as SimUpdateAndRender runs it (code/nans.cpp:1758-1762) */
+/* the step as SimUpdateAndRender runs it (code/nans.cpp:1758-1762).  Queued as DetectCollisions, then
+ * IntegrateForces, SolveConstraints, IntegrateVelocities: detection reads positions/vertices only and
+ * IntegrateForces writes velocities and clears forces only, so the result is bit-identical to the reference's
+ * order and a pending force/torque upload overlaps detection (see nans_world_upload_async). */
 int nans_step(nans_world *w, float dt);
 int nans_synchronize(nans_world *w);
 /* nans_step with a CUDA event between the stages, recorded on the world's stream (measurement only):

@@ -332,16 +332,66 @@ __device__ __noinline__ void epa_refill_list(const Src &src, const SplitScratch 
     }
 }
 
+// The same over whole chunks with the one-loop EPA (epa_resolve / epa_resolve_box): what NANS_EPA_REFILL_MIN = 32
+// amounts to, without the state-machine bookkeeping: 27.2 ms against 29.6 ms for 16 Mi pairs.  Default
+// (NANS_EPA_STEPPED = 0).  Resident CTAs per SM 2..5 make no difference (27.1-27.2 ms), 7 is slower (29.0);
+// the box-box arena (NANS_NP_BOX_EPA = 1) gives 26.9 ms.
+template <bool AS, bool BS, typename Src>
+__device__ __noinline__ void epa_chunk_list(const Src &src, const SplitScratch &sc, NpShapes &S, EpaArena &E,
+                                            int &ovf, int &max_faces)
+{
+    constexpr int cls = 2 * (int)AS + (int)BS;
+    const int lane = threadIdx.x & 31;
+    const int32_t *list = sc.list[cls];
+    const int count = sc.head[cls];
+    while (true) {
+        int base = 0;
+        if (lane == 0) base = atomicAdd(sc.head + 4 + cls, 32);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (base >= count) break;
+        const int k = base + lane;
+        if (k < count) {
+            const int p = list[k];
+            src.load(p, AS, BS, S);
+            const float4 *r = sc.rec + 8 * (size_t)p;
+            GjkVertex<AS, BS> s[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const vec3 sa = unpack_sup<AS>(S, 0, r[j], s[j].a);
+                const vec3 sb = unpack_sup<BS>(S, 1, r[4 + j], s[j].b);
+                s[j].P = sa - sb;                 // CalculateSupport's P, same operands, same bits
+            }
+            vec3 PA, PB, N;
+            int hit;
+#if NANS_NP_BOX_EPA
+            if constexpr (!AS && !BS) hit = epa_resolve_box(S, s, E.b, PA, PB, N, ovf, max_faces);
+            else
+#endif
+                hit = epa_resolve<AS, BS>(S, s, E.g, PA, PB, N, ovf, max_faces);
+            if (hit) src.store_hit(p, PA, PB, N);
+        }
+    }
+}
+
+#ifndef NANS_EPA_STEPPED
+#define NANS_EPA_STEPPED 0
+#endif
+#if NANS_EPA_STEPPED
+#define NANS_EPA_LIST epa_refill_list
+#else
+#define NANS_EPA_LIST epa_chunk_list
+#endif
+
 template <typename Src>
 __global__ void __launch_bounds__(kNpThreads, NANS_EPA_MINBLOCKS) epa_refill_kernel(Src src, SplitScratch sc, Counters *counters)
 {
     EpaArena E;
     NpShapes S;
     int ovf = 0, max_faces = 0;
-    epa_refill_list<false, false>(src, sc, S, E, ovf, max_faces);
-    epa_refill_list<false, true>(src, sc, S, E, ovf, max_faces);
-    epa_refill_list<true, false>(src, sc, S, E, ovf, max_faces);
-    epa_refill_list<true, true>(src, sc, S, E, ovf, max_faces);
+    NANS_EPA_LIST<false, false>(src, sc, S, E, ovf, max_faces);
+    NANS_EPA_LIST<false, true>(src, sc, S, E, ovf, max_faces);
+    NANS_EPA_LIST<true, false>(src, sc, S, E, ovf, max_faces);
+    NANS_EPA_LIST<true, true>(src, sc, S, E, ovf, max_faces);
     ovf = __reduce_or_sync(0xffffffffu, ovf);
     max_faces = __reduce_max_sync(0xffffffffu, max_faces);
     if ((threadIdx.x & 31) == 0 && counters) {

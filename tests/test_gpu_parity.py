@@ -67,6 +67,33 @@ def test_narrowphase_vs_oracle(nb200, oracle, rotated, n):
     assert g["hit"][p["type"] == 3].sum() == 0   # SS never hits in the reference
 
 
+def test_narrowphase_mixed_types_and_value_equal_vertices(nb200, oracle):
+    """All five pair types shuffled (every warp of the GJK kernel feeds several class lists of the split batch
+    path) and axis-aligned boxes on a lattice, where different box-vertex pairs give Minkowski vertices that
+    are equal BY VALUE (the reference cancels horizon edges by value, code/nans.h:251-254)."""
+    from nans_projekat_b200 import scenes
+    rng = np.random.default_rng(77)
+    n = 1 << 17
+    p = scenes.narrowphase_pairs(n, seed=78, types=rng.integers(0, 5, n).astype(np.int32))
+    c8 = scenes.CORNERS.astype(np.float32)
+    m = n // 2                                                   # second half: lattice boxes
+    pos_a = rng.integers(-2, 3, (m, 3)).astype(np.float32) * np.float32(0.25)
+    pos_b = pos_a + rng.integers(-4, 5, (m, 3)).astype(np.float32) * np.float32(0.25)
+    sa = rng.choice([0.5, 1.0, 2.0], (m, 1, 3)).astype(np.float32)
+    sb = rng.choice([0.5, 1.0, 2.0], (m, 1, 3)).astype(np.float32)
+    p["pos_a"][m:], p["pos_b"][m:] = pos_a, pos_b
+    p["verts_a"][m:] = c8[None] * sa + pos_a[:, None]
+    p["verts_b"][m:] = c8[None] * sb + pos_b[:, None]
+    args = (p["type"], p["pos_a"], p["verts_a"], p["rad_a"], p["pos_b"], p["verts_b"], p["rad_b"])
+    g = nb200.check_collision(*args)
+    o = oracle.check_collision_batch(*args)
+    assert np.array_equal(g["gjk"], o["gjk"]) and np.array_equal(g["hit"], o["hit"])
+    h = o["hit"] == 1
+    assert h[:m].any() and h[m:].any()
+    for k in ("N", "PA", "PB"):
+        assert_bit_equal(g[k][h], o[k][h], k)
+
+
 def test_narrowphase_edge_cases(nb200, oracle):
     """Degenerate inputs: coincident shapes, exactly aligned cubes, NaN/inf vertices, zero radius,
     touching faces.  Flags must still match the oracle bit for bit."""
