@@ -426,18 +426,20 @@ def main():
            "integrate_velocities": nb * BYTES["integrate_velocities"]}
     dom = max(alg, key=lambda k: stage[k])
     ach = alg[dom] / (stage[dom] * 1e-3) / 1e9
-    traffic, traffic_src = None, None
+    traffic, traffic_src, pipes = None, None, None
     try:   # DRAM bytes per launch of the dominant kernel, from the committed `ncu --set full` capture
         tj = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
         kname = {"narrowphase": "narrowphase_world_kernel", "solver": "solve_versioned_kernel",
                  "integrate_forces": "integrate_forces_kernel", "integrate_velocities": "integrate_velocities_kernel",
                  "broadphase": "pair_count_kernel"}[dom]
         traffic, traffic_src = tj["dram_bytes_per_launch"].get(kname), tj["source"] + " : " + kname
+        pipes = tj.get("pipes", {}).get(kname)
     except Exception:
         pass
     roofline = {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                 "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                 "share_of_step": stage[dom] / stage["step"],
+                "pipes_ncu": pipes,   # FMA / ALU pipe and issue-slot utilisation, active lanes per instruction (same capture)
                 "per_stage": {k: {"ms": stage[k], "alg_bytes": alg[k], "gbs": alg[k] / (stage[k] * 1e-3) / 1e9,
                                   "frac": alg[k] / (stage[k] * 1e-3) / 1e9 / peak} for k in alg},
                 "note": "stage = all kernels of that stage (CUDA events between stages on the launching stream); "

@@ -733,6 +733,8 @@ static int step_phase_b(nans_world *h, float dt)
 {
     // (forking integrate-forces onto a side stream next to the solver's schedule kernels was measured:
     // 1.813 vs 1.808 ms per step, the fork/join costs what the overlap saves)
+    // (seeding the solver's velocity rows from integrate-forces and consuming them in integrate-velocities --
+    // two launches and 130 MB of traffic fewer -- was measured too: 1.7936 vs 1.7944 ms, not kept)
     int rc = launch_integrate_forces(impl(h), dt);
     if (rc) return rc;
     rc = nans_solve_constraints(h, dt);

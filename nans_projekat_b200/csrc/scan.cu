@@ -125,13 +125,18 @@ __global__ void __launch_bounds__(kLbThreads) scan_lookback_kernel(const uint32_
     __shared__ uint32_t s_tile, s_epoch, s_prefix;
     volatile unsigned long long *desc = reinterpret_cast<volatile unsigned long long *>(scratch + 4);
     if (d_n) n = min(n, *d_n + extra);
+    const int n_tiles = n > 0 ? (n + kLbTile - 1) / kLbTile : 0;
+    // the grid is sized for the CAPACITY (the live length is device-resident): blocks beyond the live tiles
+    // leave before taking a ticket -- with 24 M slots of pair capacity and 1.1 M live pairs that is 5600 of
+    // 5860 blocks, each of which used to cost two atomics and a barrier
+    const unsigned live_blocks = n_tiles > 0 ? (unsigned)n_tiles : 1u;
+    if (blockIdx.x >= live_blocks) return;
     if (threadIdx.x == 0) {
         s_epoch = *(volatile uint32_t *)(scratch + 1);
         s_tile = atomicAdd(scratch, 1u);
     }
     __syncthreads();
     const uint32_t tile = s_tile, epoch = s_epoch;
-    const int n_tiles = n > 0 ? (n + kLbTile - 1) / kLbTile : 0;
     if ((int)tile < n_tiles) {
         const int base = (int)tile * kLbTile + threadIdx.x * kLbItems;
         uint32_t v[kLbItems];
@@ -207,7 +212,7 @@ __global__ void __launch_bounds__(kLbThreads) scan_lookback_kernel(const uint32_
     __syncthreads();
     if (threadIdx.x == 0) {
         __threadfence();
-        if (atomicAdd(scratch + 2, 1u) == gridDim.x - 1) {
+        if (atomicAdd(scratch + 2, 1u) == live_blocks - 1u) {
             scratch[0] = 0u;
             scratch[2] = 0u;
             __threadfence();
