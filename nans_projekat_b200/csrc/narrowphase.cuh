@@ -95,10 +95,12 @@ struct NpShapes {
 // GetCubeSupport / GetFloorSupport, code/nans.cpp:410-430,441-461: first vertex with strictly
 // greater dot; vec3(0) if every compare fails (NaN direction).  Keeps (best, index) only while
 // scanning and fetches the winner afterwards.
+#ifndef NANS_NP_TREE_SUPPORT
+#define NANS_NP_TREE_SUPPORT 0   // 1: tournament instead of the reference's sequential scan (same result); measured slower: 0.943 vs 0.902 ms
+#endif
 __device__ __forceinline__ vec3 box_support(const NpShapes &S, int side, vec3 d, int &idx)
 {
-    float best = -FLT_MAX;
-    idx = kNoVertex;
+    float dist[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
 #if NANS_NP_V4
@@ -108,9 +110,32 @@ __device__ __forceinline__ vec3 box_support(const NpShapes &S, int side, vec3 d,
         const float *p = g_np_verts + 24 * side * kNpThreads + threadIdx.x;
         const vec3 c = V3(p[(3 * k) * kNpThreads], p[(3 * k + 1) * kNpThreads], p[(3 * k + 2) * kNpThreads]);
 #endif
-        const float dist = dot(c, d);
-        if (dist > best) { best = dist; idx = k; }
+        dist[k] = dot(c, d);
     }
+#if NANS_NP_TREE_SUPPORT
+    // "first vertex whose dot is strictly greater than everything before it, starting from -FLT_MAX" is the
+    // lowest-index maximum over the dots that compare greater than -FLT_MAX (a NaN dot never does); as a
+    // tournament the dependent chain is 3 compares deep instead of 8.  b wins only if strictly greater, so
+    // ties keep the lower index; an invalid entry is (-FLT_MAX, 8) and loses to every valid one.
+    float v[8]; int ix[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { const bool ok = dist[k] > -FLT_MAX; v[k] = ok ? dist[k] : -FLT_MAX; ix[k] = ok ? k : kNoVertex; }
+#pragma unroll
+    for (int w = 1; w < 8; w <<= 1)
+#pragma unroll
+        for (int k = 0; k < 8; k += 2 * w) {
+            const bool take = v[k + w] > v[k];
+            v[k] = take ? v[k + w] : v[k];
+            ix[k] = take ? ix[k + w] : ix[k];
+        }
+    idx = ix[0];
+#else
+    float best = -FLT_MAX;
+    idx = kNoVertex;
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+        if (dist[k] > best) { best = dist[k]; idx = k; }
+#endif
     return S.vertex(side, idx);
 }
 // GetSphereSupport, code/nans.cpp:433-438
