@@ -321,10 +321,14 @@ __global__ void __launch_bounds__(256) gather_sorted_kernel(DeviceWorld w)
     }
 }
 
+__device__ __forceinline__ uint32_t cell_slot(const DeviceWorld &w, uint32_t key)
+{
+    const uint32_t h = key * 0x9E3779B1u;
+    return (h ^ (h >> 15)) & w.cell_mask;
+}
 __device__ __forceinline__ bool cell_lookup(const DeviceWorld &w, uint32_t key, uint32_t &start, uint32_t &end)
 {
-    uint32_t h = key * 0x9E3779B1u;
-    uint32_t slot = (h ^ (h >> 15)) & w.cell_mask;
+    uint32_t slot = cell_slot(w, key);
     while (true) {
         const uint4 e = __ldg(&w.cell_tab[slot]);
         if (e.x == key) { start = e.y; end = e.z; return true; }
@@ -393,6 +397,9 @@ __device__ __forceinline__ void for_each_partner(const DeviceWorld &w, const uin
 // there with the full 27-cell walk (for_each_partner).
 constexpr int kPairSlots = 24;
 
+#ifndef NANS_PC_PIPELINE
+#define NANS_PC_PIPELINE 1
+#endif
 #ifndef NANS_PC_MINBLOCKS
 #define NANS_PC_MINBLOCKS 12   // 40 registers: 1536 threads/SM hide the probe latency best (sweep: 1/10/12/16 -> 0.69/0.66/0.64/0.71 ms)
 #endif
@@ -448,19 +455,49 @@ __global__ void __launch_bounds__(128, NANS_PC_MINBLOCKS) pair_count_kernel(Devi
     const bool xm_ok = x0 != 0u, xp_ok = x0 != kMx, ym_ok = y0 != 0u, yp_ok = y0 != kMy, zp_ok = z0 != kMz;
     // 4 bits per cell: (dx + 1) | (dy + 1) << 2; cells 0..3 have dz = 0 (+x; then the row y + 1), cells 4..12 dz = +1
     constexpr unsigned long long kCells = 0xa98654210a986ull;
-#pragma unroll 1
-    for (int k = 0; k < 13; ++k) {
+    // the hash probe of cell k + 1 is issued before cell k's candidates are tested (NANS_PC_PIPELINE), so its
+    // L2 round trip hides behind their loads
+    auto cell_key = [&](int k, uint32_t &nkey) -> bool {
         const uint32_t c = (uint32_t)(kCells >> (4 * k)) & 15u;
         const uint32_t sx = c & 3u, sy = c >> 2;
         const bool up = k >= 4;
-        const bool ok = (sx == 0u ? xm_ok : sx == 2u ? xp_ok : true) && (sy == 0u ? ym_ok : sy == 2u ? yp_ok : true) &&
-                        (!up || zp_ok);
-        if (!ok) continue;
-        const uint32_t nkey = (sx == 0u ? xm : sx == 1u ? x0 : xp) | (sy == 0u ? ym : sy == 1u ? y0 : yp) | (up ? zp : z0);
+        nkey = (sx == 0u ? xm : sx == 1u ? x0 : xp) | (sy == 0u ? ym : sy == 1u ? y0 : yp) | (up ? zp : z0);
+        return (sx == 0u ? xm_ok : sx == 2u ? xp_ok : true) && (sy == 0u ? ym_ok : sy == 2u ? yp_ok : true) && (!up || zp_ok);
+    };
+#if NANS_PC_PIPELINE
+    uint32_t nkey, slot = 0;
+    bool ok = cell_key(0, nkey);
+    uint4 ent = make_uint4(kEmptyKey, 0u, 0u, 0u);
+    if (ok) { slot = cell_slot(w, nkey); ent = __ldg(&w.cell_tab[slot]); }
+#pragma unroll 1
+    for (int k = 0; k < 13; ++k) {
+        uint32_t nkey2 = 0, slot2 = 0;
+        bool ok2 = false;
+        uint4 ent2 = make_uint4(kEmptyKey, 0u, 0u, 0u);
+        if (k + 1 < 13) {
+            ok2 = cell_key(k + 1, nkey2);
+            if (ok2) { slot2 = cell_slot(w, nkey2); ent2 = __ldg(&w.cell_tab[slot2]); }
+        }
+        if (ok) {
+            while (ent.x != nkey && ent.x != kEmptyKey) {       // linear probing, as cell_lookup
+                slot = (slot + 1) & w.cell_mask;
+                ent = __ldg(&w.cell_tab[slot]);
+            }
+            if (ent.x == nkey)
+                for (uint32_t u = ent.y; u < ent.z; ++u) visit(u);
+        }
+        nkey = nkey2; slot = slot2; ok = ok2; ent = ent2;
+    }
+#else
+#pragma unroll 1
+    for (int k = 0; k < 13; ++k) {
+        uint32_t nkey;
+        if (!cell_key(k, nkey)) continue;
         uint32_t s, e;
         if (!cell_lookup(w, nkey, s, e)) continue;
         for (uint32_t u = s; u < e; ++u) visit(u);
     }
+#endif
     // statics: CF for cubes, SF for spheres, static index ascending (recomputed in the emit pass);
     // only the body itself writes these two segments
     if (row < w.n_owned) {
