@@ -397,11 +397,14 @@ __device__ __forceinline__ void for_each_partner(const DeviceWorld &w, const uin
 // there with the full 27-cell walk (for_each_partner).
 constexpr int kPairSlots = 24;
 
+#ifndef NANS_PC_PAIRWISE
+#define NANS_PC_PAIRWISE 1   // extra candidate records in flight per thread
+#endif
 #ifndef NANS_PC_PIPELINE
 #define NANS_PC_PIPELINE 1
 #endif
 #ifndef NANS_PC_MINBLOCKS
-#define NANS_PC_MINBLOCKS 12   // 40 registers: 1536 threads/SM hide the probe latency best (sweep: 1/10/12/16 -> 0.69/0.66/0.64/0.71 ms)
+#define NANS_PC_MINBLOCKS 10   // 47 registers with two candidate records in flight (sweep, broadphase stage: w2/b10 0.415, w2/b9 0.413, w2/b12 0.445 (spills), w3/b10 0.448, w3/b8 0.437, w4/b8 0.437, w4/b6 0.434, w1/b12 0.452 ms)
 #endif
 
 // Every unordered pair of dynamic bodies is looked at ONCE: a body scans the rest of its own cell
@@ -423,8 +426,7 @@ __global__ void __launch_bounds__(128, NANS_PC_MINBLOCKS) pair_count_kernel(Devi
     const bool a_cube = row < w.n_cubes;
     const uint32_t key = keys[t];
 
-    auto visit = [&](uint32_t u) {
-        const float4 blo = __ldg(&w.sbox[2 * (size_t)u]), bhi = __ldg(&w.sbox[2 * (size_t)u + 1]);
+    auto test = [&](uint32_t u, const float4 &blo, const float4 &bhi) {
         if (__float_as_int(bhi.w) != wid) return;
         if (!overlap(alo, ahi, blo, bhi)) return;
         const int brow = __float_as_int(blo.w);
@@ -438,6 +440,27 @@ __global__ void __launch_bounds__(128, NANS_PC_MINBLOCKS) pair_count_kernel(Devi
         atomicAdd(&w.pair_count[(size_t)seg * w.nb + orow], 1u);
         const uint32_t slot = atomicAdd(&fill[ot], 1u);
         if (slot < (uint32_t)kPairSlots) w.pair_tmp[(size_t)ot * kPairSlots + slot] = ((uint32_t)seg << 28) | (uint32_t)prow;
+    };
+    auto visit = [&](uint32_t u) {
+        const float4 blo = __ldg(&w.sbox[2 * (size_t)u]), bhi = __ldg(&w.sbox[2 * (size_t)u + 1]);
+        test(u, blo, bhi);
+    };
+    // candidates [s, e): NANS_PC_PAIRWISE + 1 records in flight
+    auto visit_range = [&](uint32_t s, uint32_t e) {
+#if NANS_PC_PAIRWISE
+        constexpr int W = NANS_PC_PAIRWISE + 1;       // records in flight
+        for (uint32_t u = s; u < e; u += W) {
+            float4 lo[W], hi[W];
+#pragma unroll
+            for (int j = 0; j < W; ++j)
+                if (j == 0 || u + j < e) { lo[j] = __ldg(&w.sbox[2 * (size_t)(u + j)]); hi[j] = __ldg(&w.sbox[2 * (size_t)(u + j) + 1]); }
+#pragma unroll
+            for (int j = 0; j < W; ++j)
+                if (j == 0 || u + j < e) test(u + j, lo[j], hi[j]);
+        }
+#else
+        for (uint32_t u = s; u < e; ++u) visit(u);
+#endif
     };
 
     // the rest of the own cell
@@ -483,8 +506,7 @@ __global__ void __launch_bounds__(128, NANS_PC_MINBLOCKS) pair_count_kernel(Devi
                 slot = (slot + 1) & w.cell_mask;
                 ent = __ldg(&w.cell_tab[slot]);
             }
-            if (ent.x == nkey)
-                for (uint32_t u = ent.y; u < ent.z; ++u) visit(u);
+            if (ent.x == nkey) visit_range(ent.y, ent.z);
         }
         nkey = nkey2; slot = slot2; ok = ok2; ent = ent2;
     }
