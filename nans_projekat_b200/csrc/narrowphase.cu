@@ -49,6 +49,46 @@ __device__ __forceinline__ NpResult dispatch(bool a_sphere, bool b_sphere, NpSha
     return check_collision<true, true>(S, E, ovf, max_faces);
 }
 
+#ifndef NANS_NP_CHUNK2
+#define NANS_NP_CHUNK2 0   // 1: a warp takes 64 pairs per ticket, both index pairs arrive in one round trip and the
+#endif                     // second pair's shapes are prefetched to L2 during the first: measured slower (0.935 vs 0.902 ms)
+
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
+__device__ __forceinline__ void np_world_pair(const DeviceWorld &w, int p, int ra, int rb, NpShapes &S, EpaArena &E,
+                                              int &ovf, int &max_faces, int &found)
+{
+    const bool a_sphere = ra >= w.n_cubes;
+    const bool b_sphere = rb >= w.n_cubes;   // statics are negative -> box
+    S.posA = V3(w.pos[ra]);
+    S.radA = 0.f;
+    if (a_sphere) S.radA = w.scale[ra].w; else load_box(0, w.verts + 6 * (size_t)ra);
+    S.radB = 0.f;
+    if (rb < 0) {
+        const int k = -rb - 1;
+        S.posB = V3(w.st_pos[k]);
+        load_box(1, w.st_verts + 6 * k);
+    } else {
+        S.posB = V3(w.pos[rb]);
+        if (b_sphere) S.radB = w.scale[rb].w; else load_box(1, w.verts + 6 * (size_t)rb);
+    }
+    const NpResult r = dispatch(a_sphere, b_sphere, S, E, ovf, max_faces);
+    found += (r.gjk == kFoundIntersection);
+    w.pair_hit[p] = r.hit;
+    if (r.hit) {
+        float4 *o = w.pair_out + 3 * (size_t)p;
+#if NANS_NP_STREAM
+        __stcs(o, make_float4(r.PA.x, r.PA.y, r.PA.z, 0.f));
+        __stcs(o + 1, make_float4(r.PB.x, r.PB.y, r.PB.z, 0.f));
+        __stcs(o + 2, make_float4(r.N.x, r.N.y, r.N.z, 0.f));
+#else
+        o[0] = make_float4(r.PA.x, r.PA.y, r.PA.z, 0.f);
+        o[1] = make_float4(r.PB.x, r.PB.y, r.PB.z, 0.f);
+        o[2] = make_float4(r.N.x, r.N.y, r.N.z, 0.f);
+#endif
+    }
+}
+
 __global__ void __launch_bounds__(kNpThreads, NANS_NP_MINBLOCKS) narrowphase_world_kernel(DeviceWorld w, int *work_counter)
 {
     EpaArena E;
@@ -56,44 +96,29 @@ __global__ void __launch_bounds__(kNpThreads, NANS_NP_MINBLOCKS) narrowphase_wor
     const int n_pairs = w.counters->n_pairs;
     int ovf = 0, max_faces = 0, found = 0;
     NpShapes S;
+    constexpr int kPerTicket = NANS_NP_CHUNK2 ? 64 : 32;
     while (true) {
         int base = 0;
-        if (lane == 0) base = atomicAdd(work_counter, 32);
+        if (lane == 0) base = atomicAdd(work_counter, kPerTicket);
         base = __shfl_sync(0xffffffffu, base, 0);
         if (base >= n_pairs) break;
         const int p = base + lane;
-        if (p < n_pairs) {
-            const int ra = w.pair_a[p], rb = w.pair_b[p];
-            const bool a_sphere = ra >= w.n_cubes;
-            const bool b_sphere = rb >= w.n_cubes;   // statics are negative -> box
-            S.posA = V3(w.pos[ra]);
-            S.radA = 0.f;
-            if (a_sphere) S.radA = w.scale[ra].w; else load_box(0, w.verts + 6 * (size_t)ra);
-            S.radB = 0.f;
-            if (rb < 0) {
-                const int k = -rb - 1;
-                S.posB = V3(w.st_pos[k]);
-                load_box(1, w.st_verts + 6 * k);
-            } else {
-                S.posB = V3(w.pos[rb]);
-                if (b_sphere) S.radB = w.scale[rb].w; else load_box(1, w.verts + 6 * (size_t)rb);
-            }
-            const NpResult r = dispatch(a_sphere, b_sphere, S, E, ovf, max_faces);
-            found += (r.gjk == kFoundIntersection);
-            w.pair_hit[p] = r.hit;
-            if (r.hit) {
-                float4 *o = w.pair_out + 3 * (size_t)p;
-#if NANS_NP_STREAM
-                __stcs(o, make_float4(r.PA.x, r.PA.y, r.PA.z, 0.f));
-                __stcs(o + 1, make_float4(r.PB.x, r.PB.y, r.PB.z, 0.f));
-                __stcs(o + 2, make_float4(r.N.x, r.N.y, r.N.z, 0.f));
-#else
-                o[0] = make_float4(r.PA.x, r.PA.y, r.PA.z, 0.f);
-                o[1] = make_float4(r.PB.x, r.PB.y, r.PB.z, 0.f);
-                o[2] = make_float4(r.N.x, r.N.y, r.N.z, 0.f);
-#endif
-            }
+#if NANS_NP_CHUNK2
+        const int p2 = p + 32;
+        int ra = 0, rb = 0, ra2 = 0, rb2 = 0;
+        if (p < n_pairs) { ra = w.pair_a[p]; rb = w.pair_b[p]; }
+        if (p2 < n_pairs) {
+            ra2 = w.pair_a[p2]; rb2 = w.pair_b[p2];
+            // the second pair's bodies: towards L2 now, wanted after the first pair's GJK + EPA
+            if (ra2 < w.n_cubes) { const char *q = (const char *)(w.verts + 6 * (size_t)ra2); prefetch_l2(q); prefetch_l2(q + 64); }
+            if (rb2 >= 0 && rb2 < w.n_cubes) { const char *q = (const char *)(w.verts + 6 * (size_t)rb2); prefetch_l2(q); prefetch_l2(q + 64); }
         }
+        if (p < n_pairs) np_world_pair(w, p, ra, rb, S, E, ovf, max_faces, found);
+        __syncwarp();
+        if (p2 < n_pairs) np_world_pair(w, p2, ra2, rb2, S, E, ovf, max_faces, found);
+#else
+        if (p < n_pairs) np_world_pair(w, p, w.pair_a[p], w.pair_b[p], S, E, ovf, max_faces, found);
+#endif
     }
     // per-warp stats
     found = __reduce_add_sync(0xffffffffu, found);
