@@ -976,7 +976,10 @@ int nans_check_collision_device(int32_t n, const int32_t *d_type, const float *d
                                 const float *d_posrad_b, const float *d_verts_b, int32_t *d_hit, float *d_out,
                                 void *stream)
 {
-    static int *d_work = nullptr;
+    static int *d_works[64] = {nullptr};      // one work counter per device (the caller's current device)
+    int dev = 0;
+    NANS_CUDA(cudaGetDevice(&dev));
+    int *&d_work = d_works[(dev >= 0 && dev < 64) ? dev : 0];
     if (!d_work) NANS_CUDA(cudaMalloc(&d_work, 256));
     return launch_narrowphase_batch(n, d_type, (const float4 *)d_posrad_a, (const float4 *)d_verts_a,
                                     (const float4 *)d_posrad_b, (const float4 *)d_verts_b, d_hit, nullptr,

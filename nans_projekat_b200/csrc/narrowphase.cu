@@ -449,12 +449,18 @@ int launch_narrowphase(World *w)
     return NANS_OK;
 }
 
-// device scratch of the split path, grown on demand and kept (one per process; the batch entry points are
-// not re-entrant across streams)
+// device scratch of the split path, grown on demand and kept (one per device; the batch entry points are
+// not re-entrant across streams of the same device)
 static int split_scratch(int n, SplitScratch &sc)
 {
-    static char *blk = nullptr;
-    static size_t cap = 0;
+    constexpr int kMaxDevices = 64;
+    static char *blks[kMaxDevices] = {nullptr};
+    static size_t caps[kMaxDevices] = {0};
+    int dev = 0;
+    NANS_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= kMaxDevices) dev = 0;
+    char *&blk = blks[dev];
+    size_t &cap = caps[dev];
     const size_t need = 256 + 4 * sizeof(int32_t) * (size_t)n + 8 * sizeof(float4) * (size_t)n;
     if (need > cap) {
         if (blk) NANS_CUDA(cudaFree(blk));
