@@ -447,7 +447,13 @@ __global__ void __launch_bounds__(kFlowThreads) solve_dataflow_kernel(DeviceWorl
 // Warps take contacts in LIST order, 32 at a time.  Progress: every contact a lane waits for is
 // earlier in the list, so its ticket is already held by a running warp; by induction the earliest
 // unfinished contact is always runnable.  (A spin cap turns any violation into an error.)
-constexpr int kVerThreads = 256;
+#ifndef NANS_VER_THREADS
+#define NANS_VER_THREADS 256
+#endif
+#ifndef NANS_VER_MINBLOCKS
+#define NANS_VER_MINBLOCKS 2   // resident CTAs the register budget is sized for (sweep, solver stage: 256x2 0.374, 128x4 0.375,
+#endif                         // 256x3 / 128x6 (80 registers, spills) 0.455, 256x4 (64 registers) 0.539 ms)
+constexpr int kVerThreads = NANS_VER_THREADS;
 constexpr int kVerMask = 0xfffff;   // version bits kept in the angular row (the rest carries the DAG level)
 
 __device__ __forceinline__ float4 ld_row(const float4 *p)
@@ -509,7 +515,7 @@ __global__ void __launch_bounds__(256) run_scatter_kernel(DeviceWorld w)
 // rows go through memory, and the lanes of a warp fire their j-th contacts together (a lane per
 // contact left ~8 of 32 lanes active per firing: the kernel was bound by issue slots).
 // trace (debug, NANS_SOLVER_TRACE=1): per contact {fire ns, stored ns, ticket ns, polls}; frontier[1] = DAG level
-__global__ void __launch_bounds__(kVerThreads) solve_versioned_kernel(DeviceWorld w, float dt, int sleep_ns, unsigned long long *trace)
+__global__ void __launch_bounds__(kVerThreads, NANS_VER_MINBLOCKS) solve_versioned_kernel(DeviceWorld w, float dt, int sleep_ns, unsigned long long *trace)
 {
     const int n = w.counters->n_contacts;
     const int n_runs = w.counters->frontier_n[1];
