@@ -183,9 +183,10 @@ __global__ void __launch_bounds__(kNpThreads, NANS_NP_MINBLOCKS) narrowphase_bat
 // kernel runs EPA as the resumable state machine of narrowphase.cuh: a lane whose pair has finished takes the
 // next pair of the list at once.  Results are written per pair, so the list order (atomics) is not observable.
 struct SplitScratch {
-    int32_t *head;        // [cls] pairs listed, [4 + cls] tickets taken
-    int32_t *list[4];     // pair indices, class = 2 * a_sphere + b_sphere
-    float4 *rec;          // [pairs][8]: simplex of pair p (4 x support A, 4 x support B)
+    int32_t *head;        // [cls] pairs listed for EPA, [4 + cls] tickets taken; [8 + cls], [12 + cls]: the same for glist
+    int32_t *list[4];     // intersecting pairs, class = 2 * a_sphere + b_sphere
+    int32_t *glist[4];    // pairs whose GJK was still evolving after NANS_GJK_CAP evolutions
+    float4 *rec;          // [pairs][8]: simplex of pair p (4 x support A, 4 x support B); .w of [0], [1]: n, iter
 };
 
 struct BatchSrc {
@@ -237,28 +238,99 @@ template <bool SPHERE> __device__ __forceinline__ vec3 unpack_sup(const NpShapes
     else { r.idx = __float_as_int(q.x); return S.vertex(side, r.idx); }
 }
 
-// GJK of one pair; an intersecting pair is appended to its class list with its simplex
+#ifndef NANS_GJK_CAP
+#define NANS_GJK_CAP 6     // evolutions in the first GJK kernel; 0 = run every pair to the end there
+                           // (config C3, 16 Mi pairs: cap 0 / 6 / 8 / 12 -> 28.0 / 23.8 / 24.0 / 24.4 ms)
+#endif
+
+// append pair p to list[cls] (warp-aggregated over the lanes converged here, which all belong to this class)
+// and save its simplex
+template <bool AS, bool BS>
+__device__ __forceinline__ void list_pair(int32_t *head, int32_t *list, float4 *rec, int p, bool want,
+                                          const GjkVertex<AS, BS> (&s)[4], int n, int iter)
+{
+    const unsigned act = __activemask();
+    const unsigned m = __ballot_sync(act, want);
+    if (!want) return;
+    const int lane = threadIdx.x & 31, leader = __ffs(m) - 1;
+    int base = 0;
+    if (lane == leader) base = atomicAdd(head, __popc(m));
+    base = __shfl_sync(m, base, leader);
+    list[base + __popc(m & ((1u << lane) - 1u))] = p;
+    float4 *r = rec + 8 * (size_t)p;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;      // entries past n are not part of the simplex
+        if (k < n) { a = pack_sup<AS>(s[k].a); b = pack_sup<BS>(s[k].b); }
+        if (k == 0) a.w = __int_as_float(n);
+        if (k == 1) a.w = __int_as_float(iter);
+        r[k] = a; r[4 + k] = b;
+    }
+}
+
+// the simplex a list entry saved (P = SupA - SupB re-formed: same operands, same bits)
+template <bool AS, bool BS>
+__device__ __forceinline__ void load_simplex(const NpShapes &S, const float4 *rec, int p, GjkVertex<AS, BS> (&s)[4], int &n, int &iter)
+{
+    const float4 *r = rec + 8 * (size_t)p;
+    n = __float_as_int(r[0].w); iter = __float_as_int(r[1].w);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const vec3 sa = unpack_sup<AS>(S, 0, r[j], s[j].a);
+        const vec3 sb = unpack_sup<BS>(S, 1, r[4 + j], s[j].b);
+        s[j].P = sa - sb;
+    }
+}
+
+// GJK of one pair, at most NANS_GJK_CAP evolutions: an intersecting pair goes to its class's EPA list, a pair
+// that is still evolving to its class's GJK list (GJK lengths are long-tailed too: most pairs decide in 1 or
+// 5 evolutions, a few cycle up to the limit of 65, and a chunk waits for its slowest lane)
 template <bool AS, bool BS, typename Src>
 __device__ __noinline__ int gjk_and_list(const Src &src, const SplitScratch &sc, NpShapes &S, int p)
 {
+    constexpr int cls = 2 * (int)AS + (int)BS;
     GjkVertex<AS, BS> s[4];
-    const int ev = gjk_run<AS, BS>(S, s);
-    const bool found = ev == kFoundIntersection;
-    // warp-aggregated append (the lanes converged here all belong to this class)
-    const unsigned act = __activemask();
-    const unsigned m = __ballot_sync(act, found);
-    if (found) {
-        const int lane = threadIdx.x & 31, leader = __ffs(m) - 1;
-        constexpr int cls = 2 * (int)AS + (int)BS;
-        int base = 0;
-        if (lane == leader) base = atomicAdd(sc.head + cls, __popc(m));
-        base = __shfl_sync(m, base, leader);
-        sc.list[cls][base + __popc(m & ((1u << lane) - 1u))] = p;
-        float4 *r = sc.rec + 8 * (size_t)p;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) { r[k] = pack_sup<AS>(s[k].a); r[4 + k] = pack_sup<BS>(s[k].b); }
-    }
+    int n = 0, iter = 0;
+    const int ev = gjk_resume<AS, BS>(S, s, n, iter, NANS_GJK_CAP > 0 ? NANS_GJK_CAP : 1000);
+    list_pair<AS, BS>(sc.head + cls, sc.list[cls], sc.rec, p, ev == kFoundIntersection, s, 4, iter);
+    list_pair<AS, BS>(sc.head + 8 + cls, sc.glist[cls], sc.rec, p, ev == kStillEvolving && iter <= 64, s, n, iter);
     return ev;
+}
+
+// the rest of GJK for the pairs the first kernel left evolving, over whole chunks of their (compacted) lists
+template <bool AS, bool BS, typename Src>
+__device__ __noinline__ void gjk_continue_list(const Src &src, const SplitScratch &sc, NpShapes &S)
+{
+    constexpr int cls = 2 * (int)AS + (int)BS;
+    const int lane = threadIdx.x & 31;
+    const int count = sc.head[8 + cls];
+    while (true) {
+        int base = 0;
+        if (lane == 0) base = atomicAdd(sc.head + 12 + cls, 32);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (base >= count) break;
+        const int k = base + lane;
+        if (k < count) {
+            const int p = sc.glist[cls][k];
+            src.load(p, AS, BS, S);
+            GjkVertex<AS, BS> s[4];
+            int n, iter;
+            load_simplex<AS, BS>(S, sc.rec, p, s, n, iter);
+            const int ev = gjk_resume<AS, BS>(S, s, n, iter, 1000);
+            src.store_gjk(p, ev);
+            list_pair<AS, BS>(sc.head + cls, sc.list[cls], sc.rec, p, ev == kFoundIntersection, s, 4, iter);
+        }
+    }
+}
+
+template <typename Src>
+__global__ void __launch_bounds__(kNpThreads, NANS_GJK_MINBLOCKS) gjk_continue_kernel(Src src, SplitScratch sc)
+{
+    NpShapes S;
+    gjk_continue_list<false, false>(src, sc, S);
+    gjk_continue_list<false, true>(src, sc, S);
+    gjk_continue_list<true, false>(src, sc, S);
+    gjk_continue_list<true, true>(src, sc, S);
 }
 
 template <typename Src>
@@ -378,14 +450,9 @@ __device__ __noinline__ void epa_chunk_list(const Src &src, const SplitScratch &
         if (k < count) {
             const int p = list[k];
             src.load(p, AS, BS, S);
-            const float4 *r = sc.rec + 8 * (size_t)p;
             GjkVertex<AS, BS> s[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const vec3 sa = unpack_sup<AS>(S, 0, r[j], s[j].a);
-                const vec3 sb = unpack_sup<BS>(S, 1, r[4 + j], s[j].b);
-                s[j].P = sa - sb;                 // CalculateSupport's P, same operands, same bits
-            }
+            int n_, iter_;
+            load_simplex<AS, BS>(S, sc.rec, p, s, n_, iter_);
             vec3 PA, PB, N;
             int hit;
 #if NANS_NP_BOX_EPA
@@ -461,7 +528,7 @@ static int split_scratch(int n, SplitScratch &sc)
     if (dev < 0 || dev >= kMaxDevices) dev = 0;
     char *&blk = blks[dev];
     size_t &cap = caps[dev];
-    const size_t need = 256 + 4 * sizeof(int32_t) * (size_t)n + 8 * sizeof(float4) * (size_t)n;
+    const size_t need = 256 + 8 * sizeof(int32_t) * (size_t)n + 8 * sizeof(float4) * (size_t)n;
     if (need > cap) {
         if (blk) NANS_CUDA(cudaFree(blk));
         blk = nullptr; cap = 0;
@@ -471,7 +538,7 @@ static int split_scratch(int n, SplitScratch &sc)
     sc.head = reinterpret_cast<int32_t *>(blk);
     sc.rec = reinterpret_cast<float4 *>(blk + 256);
     int32_t *l = reinterpret_cast<int32_t *>(blk + 256 + 8 * sizeof(float4) * (size_t)n);
-    for (int k = 0; k < 4; ++k) sc.list[k] = l + (size_t)k * n;
+    for (int k = 0; k < 4; ++k) { sc.list[k] = l + (size_t)k * n; sc.glist[k] = l + (size_t)(4 + k) * n; }
     return NANS_OK;
 }
 
@@ -491,7 +558,7 @@ int launch_narrowphase_batch(int n, const int32_t *type, const float4 *posrad_a,
         return NANS_OK;
     }
     // at most kSplitChunk pairs per round (bounds the scratch: 144 B per pair)
-    constexpr int kSplitChunk = 1 << 24;   // (scratch: 144 B per pair)
+    constexpr int kSplitChunk = 1 << 24;   // (scratch: 160 B per pair)
     static int gjk_per_sm = 0, epa_per_sm = 0;
     if (!gjk_per_sm) {
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&gjk_per_sm, gjk_split_kernel<BatchSrc>, kNpThreads, 0);
@@ -515,6 +582,10 @@ int launch_narrowphase_batch(int n, const int32_t *type, const float4 *posrad_a,
         const int g1 = need < kNumSMs * gjk_per_sm ? need : kNumSMs * gjk_per_sm;
         gjk_split_kernel<BatchSrc><<<g1, kNpThreads, 0, s>>>(src, sc, work_counter, nullptr);
         NANS_LAUNCH_CHECK();
+        if (NANS_GJK_CAP > 0) {
+            gjk_continue_kernel<BatchSrc><<<g1, kNpThreads, 0, s>>>(src, sc);
+            NANS_LAUNCH_CHECK();
+        }
         const int g2 = need < kNumSMs * epa_per_sm ? need : kNumSMs * epa_per_sm;
         epa_refill_kernel<BatchSrc><<<g2, kNpThreads, 0, s>>>(src, sc, counters);
         NANS_LAUNCH_CHECK();

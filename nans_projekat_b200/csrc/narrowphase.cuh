@@ -713,12 +713,29 @@ __device__ __forceinline__ int gjk_run(NpShapes &S, GjkVertex<AS, BS> (&s)[4])
     return ev;
 }
 
+// The same loop, resumable: at most `budget` more evolutions; n and iter carry the progress.  Finished when the
+// result is not kStillEvolving or iter > 64 (the reference's own limit).
+template <bool AS, bool BS>
+__device__ __forceinline__ int gjk_resume(NpShapes &S, GjkVertex<AS, BS> (&s)[4], int &n, int &iter, int budget)
+{
+    int ev = kStillEvolving;
+    S.dir0 = normalize(S.posB - S.posA);
+    while (ev == kStillEvolving && budget-- > 0 && iter++ <= 64) ev = evolve_simplex<AS, BS>(S, s, n);
+    return ev;
+}
+
 // CheckCollision, code/nans.cpp:907-966
 template <bool AS, bool BS>
 __device__ __noinline__ NpResult check_collision(NpShapes &S, EpaArena &E, int &ovf, int &max_faces)
 {
     GjkVertex<AS, BS> s[4];
+#ifdef NANS_NP_GJK_CAPPED   // the capped-then-continued GJK of the split batch path (host check of gjk_resume)
+    int n_ = 0, iter_ = 0;
+    int ev = gjk_resume<AS, BS>(S, s, n_, iter_, NANS_NP_GJK_CAPPED);
+    if (ev == kStillEvolving && iter_ <= 64) ev = gjk_resume<AS, BS>(S, s, n_, iter_, 1000);
+#else
     const int ev = gjk_run<AS, BS>(S, s);
+#endif
     NpResult r;
     r.gjk = ev;
     r.hit = 0;
