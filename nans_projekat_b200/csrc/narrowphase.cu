@@ -1,8 +1,17 @@
-// narrowphase.cu — kernels around narrowphase.cuh: GJK+EPA over the world's candidate pairs and
-// over stand-alone shape pairs (config C3).  One pair per thread; warps fetch 32-pair chunks from
-// a global counter (pairs differ by >10x in work: a GJK miss is one support call, an EPA hit is
-// dozens), grid = SM count x resident CTAs.  FP32-pipe / divergence bound, not HBM bound:
-// 216 B in + 48 B out per pair against ~1-5 kflop of unfused fp32.
+// narrowphase.cu — kernels around narrowphase.cuh.
+//
+//   narrowphase_world_kernel   GJK+EPA over the world's candidate pairs (the step).  One pair per thread; warps
+//                              fetch 32-pair chunks from a global counter (a GJK miss is one support call, an EPA
+//                              hit is dozens), grid = SM count x resident CTAs.  Nearly every candidate of a pile
+//                              intersects (94 %), so GJK and EPA stay in one kernel.
+//   gjk_split_kernel, gjk_continue_kernel, epa_refill_kernel
+//                              the same over stand-alone shape pairs (nans_check_collision_batch/_device, config
+//                              C3), where half the pairs miss and GJK / EPA lengths are long-tailed: GJK capped,
+//                              stragglers and intersecting pairs compacted into lists, EPA over the lists.
+//   narrowphase_batch_kernel   the one-kernel form over stand-alone pairs (NANS_NP_SPLIT=0, A/B).
+//
+// FP32-pipe / divergence bound, not HBM bound: 216 B in + 48 B out per pair against ~1-5 kflop of unfused fp32
+// (SURVEY.md §8d).
 #include <stdlib.h>
 
 #include "narrowphase.cuh"
