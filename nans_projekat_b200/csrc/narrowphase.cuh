@@ -364,21 +364,21 @@ __device__ __forceinline__ void epa_push_edge(EpaGenericArena &E, int &ne, int a
     E.edge[ne++] = (uint32_t)a | ((uint32_t)b << 8) | (ca << 16) | (cb << 24);
 }
 
-// ResolveCollision, code/nans.cpp:788-904.  Returns the bool32 result; fills PointA/PointB/N.
-template <bool AS, bool BS>
-__device__ __forceinline__ int epa_resolve(const NpShapes &S, const GjkVertex<AS, BS> (&s)[4], EpaGenericArena &E,
-                                           vec3 &outPA, vec3 &outPB, vec3 &outN, int &ovf, int &max_faces)
+// The polytope between two iterations of ResolveCollision: everything else in the arena is scratch of one iteration.
+struct EpaProgress { int nv, nf, ci, it; float cur; };
+constexpr int kEpaPaused = 2;     // epa_loop: 0 = no collision, 1 = collision (outputs filled), 2 = stopped at it_stop
+
+// The iteration loop of ResolveCollision (code/nans.cpp:805-903) from the state g.  kCanPause: stop (state in g,
+// arena consistent) once it_stop iterations are done, so that a long pair can be carried to another kernel.
+template <bool AS, bool BS, bool kCanPause>
+__device__ __forceinline__ int epa_loop(const NpShapes &S, EpaGenericArena &E, EpaProgress &g, int it_stop,
+                                        vec3 &outPA, vec3 &outPB, vec3 &outN, int &ovf, int &max_faces)
 {
-#pragma unroll
-    for (int k = 0; k < 4; ++k) epa_store_vertex<AS, BS>(E, k, s[k]);
-    int nv = 4, nf = 0, ne = 0, ci = 0;
-    float cur = 0.f;
-    epa_push_face(E, nf, 0, 1, 2, s[0].P, cur, ci);  // ABC
-    epa_push_face(E, nf, 0, 2, 3, s[0].P, cur, ci);  // ACD
-    epa_push_face(E, nf, 0, 3, 1, s[0].P, cur, ci);  // ADB
-    epa_push_face(E, nf, 1, 3, 2, s[1].P, cur, ci);  // BDC
-    int it = 0;
-    while (it++ <= 64) {            // MAX_EPA_ITERATIONS, code/nans.h:56
+    int nv = g.nv, nf = g.nf, ne = 0, ci = g.ci, it = g.it;
+    float cur = g.cur;
+    while (true) {
+        if (kCanPause && it >= it_stop) { g.nv = nv; g.nf = nf; g.ci = ci; g.it = it; g.cur = cur; return kEpaPaused; }
+        if (!(it++ <= 64)) break;   // MAX_EPA_ITERATIONS, code/nans.h:56: while (it++ <= 64)
         max_faces = max(max_faces, nf);
         const float4 cnd = E.fnd[ci];
         const vec3 N = face_normal_flipped(cnd);
@@ -443,6 +443,91 @@ __device__ __forceinline__ int epa_resolve(const NpShapes &S, const GjkVertex<AS
         ++nv;
     }
     return 0;
+}
+
+// the start of ResolveCollision (:791-802): the simplex becomes the first four vertices and faces
+template <bool AS, bool BS>
+__device__ __forceinline__ void epa_start(const GjkVertex<AS, BS> (&s)[4], EpaGenericArena &E, EpaProgress &g)
+{
+#pragma unroll
+    for (int k = 0; k < 4; ++k) epa_store_vertex<AS, BS>(E, k, s[k]);
+    int nf = 0, ci = 0;
+    float cur = 0.f;
+    epa_push_face(E, nf, 0, 1, 2, s[0].P, cur, ci);  // ABC
+    epa_push_face(E, nf, 0, 2, 3, s[0].P, cur, ci);  // ACD
+    epa_push_face(E, nf, 0, 3, 1, s[0].P, cur, ci);  // ADB
+    epa_push_face(E, nf, 1, 3, 2, s[1].P, cur, ci);  // BDC
+    g.nv = 4; g.nf = nf; g.ci = ci; g.it = 0; g.cur = cur;
+}
+
+// ResolveCollision, code/nans.cpp:788-904.  Returns the bool32 result; fills PointA/PointB/N.
+template <bool AS, bool BS>
+__device__ __forceinline__ int epa_resolve(const NpShapes &S, const GjkVertex<AS, BS> (&s)[4], EpaGenericArena &E,
+                                           vec3 &outPA, vec3 &outPB, vec3 &outN, int &ovf, int &max_faces)
+{
+    EpaProgress g;
+    epa_start<AS, BS>(s, E, g);
+    return epa_loop<AS, BS, false>(S, E, g, 0, outPA, outPB, outN, ovf, max_faces);
+}
+
+// ---- carrying a paused polytope to another thread -------------------------------------------------------------
+// A paused EPA (epa_loop with kCanPause) is nv vertices and nf faces; epa_save / epa_restore move exactly that
+// between a per-thread arena and a global record of kCarryQuads float4, so that a long pair could be finished by
+// another kernel next to pairs of its own length without repeating an iteration.  Host-checked (tests/test_np_host.py,
+// "carry": pause, save, wipe the arena, restore, finish).  A kernel pair built on it for config C3 (pause after 6 / 8 /
+// 10 iterations, paused polytopes to a pool, a second EPA kernel over them) measured 24.2 / 23.9 / 23.3 ms against
+// 23.7 ms without and failed one GPU parity test when the GPU budget of the round ran out; it is not in the tree.
+constexpr int kCarryVerts = 16, kCarryFaces = 32;
+constexpr int kCarryQuads = 2 + 3 * kCarryVerts + kCarryFaces + kCarryFaces / 4;   // 90 float4 = 1440 B
+
+__device__ __forceinline__ bool epa_can_carry(const EpaProgress &g) { return g.nv <= kCarryVerts && g.nf <= kCarryFaces; }
+
+template <bool AS, bool BS>
+__device__ __forceinline__ void epa_save(const EpaGenericArena &E, const EpaProgress &g, float4 *r)
+{
+    r[0] = make_float4(__int_as_float(g.nv), __int_as_float(g.nf), __int_as_float(g.ci), __int_as_float(g.it));
+    r[1] = make_float4(g.cur, 0.f, 0.f, 0.f);
+    for (int i = 0; i < g.nv; ++i) {
+        uint32_t pk = E.cid[i];
+        if constexpr (!AS) pk |= (uint32_t)E.ia[i] << 8;
+        if constexpr (!BS) pk |= (uint32_t)E.ib[i] << 16;
+        r[2 + 3 * i] = make_float4(E.P[i].x, E.P[i].y, E.P[i].z, __int_as_float((int)pk));
+        if constexpr (AS) r[3 + 3 * i] = make_float4(E.SA[i].x, E.SA[i].y, E.SA[i].z, 0.f);
+        if constexpr (BS) r[4 + 3 * i] = make_float4(E.SB[i].x, E.SB[i].y, E.SB[i].z, 0.f);
+    }
+    float4 *f = r + 2 + 3 * kCarryVerts;
+    for (int i = 0; i < g.nf; ++i) f[i] = E.fnd[i];
+    float4 *fi = f + kCarryFaces;
+    for (int i = 0; i < g.nf; i += 4)
+        fi[i >> 2] = make_float4(__int_as_float((int)E.fidx[i]), __int_as_float((int)(i + 1 < g.nf ? E.fidx[i + 1] : 0u)),
+                                 __int_as_float((int)(i + 2 < g.nf ? E.fidx[i + 2] : 0u)),
+                                 __int_as_float((int)(i + 3 < g.nf ? E.fidx[i + 3] : 0u)));
+}
+
+template <bool AS, bool BS>
+__device__ __forceinline__ void epa_restore(EpaGenericArena &E, EpaProgress &g, const float4 *r)
+{
+    const float4 h = r[0];
+    g.nv = __float_as_int(h.x); g.nf = __float_as_int(h.y); g.ci = __float_as_int(h.z); g.it = __float_as_int(h.w);
+    g.cur = r[1].x;
+    for (int i = 0; i < g.nv; ++i) {
+        const float4 v = r[2 + 3 * i];
+        const uint32_t pk = (uint32_t)__float_as_int(v.w);
+        E.P[i] = V3(v);
+        E.cid[i] = (uint8_t)(pk & 255u);
+        if constexpr (!AS) E.ia[i] = (uint8_t)((pk >> 8) & 255u);
+        if constexpr (!BS) E.ib[i] = (uint8_t)((pk >> 16) & 255u);
+        if constexpr (AS) E.SA[i] = V3(r[3 + 3 * i]);
+        if constexpr (BS) E.SB[i] = V3(r[4 + 3 * i]);
+    }
+    const float4 *f = r + 2 + 3 * kCarryVerts;
+    for (int i = 0; i < g.nf; ++i) E.fnd[i] = f[i];
+    const float4 *fi = f + kCarryFaces;
+    for (int i = 0; i < g.nf; ++i) {
+        const float4 q = fi[i >> 2];
+        const float w = (i & 3) == 0 ? q.x : (i & 3) == 1 ? q.y : (i & 3) == 2 ? q.z : q.w;
+        E.fidx[i] = (uint32_t)__float_as_int(w);
+    }
 }
 
 // ---- EPA as a resumable state machine ------------------------------------------------------------
@@ -755,6 +840,23 @@ __device__ __noinline__ NpResult check_collision(NpShapes &S, EpaArena &E, int &
             epa_begin<AS, BS>(s, E.g, st);
             int rr;
             do rr = epa_step<AS, BS>(S, E.g, st, r.PA, r.PB, r.N, ovf, max_faces); while (rr == kEpaContinue);
+            r.hit = rr;
+        }
+#elif defined(NANS_NP_CARRY)   // pause after NANS_NP_CARRY iterations, move the polytope through a record into a
+        {                          // wiped arena and finish there (host check of epa_loop / epa_save / epa_restore)
+            EpaProgress g;
+            epa_start<AS, BS>(s, E.g, g);
+            int rr = epa_loop<AS, BS, true>(S, E.g, g, NANS_NP_CARRY, r.PA, r.PB, r.N, ovf, max_faces);
+            if (rr == kEpaPaused) {
+                if (epa_can_carry(g)) {
+                    static float4 rec[kCarryQuads];
+                    epa_save<AS, BS>(E.g, g, rec);
+                    memset(&E, 0xAB, sizeof(E));
+                    g.nv = g.nf = g.ci = g.it = -1; g.cur = -1.f;
+                    epa_restore<AS, BS>(E.g, g, rec);
+                }
+                rr = epa_loop<AS, BS, false>(S, E.g, g, 0, r.PA, r.PB, r.N, ovf, max_faces);
+            }
             r.hit = rr;
         }
 #else

@@ -32,6 +32,7 @@ def _build(name, flags):
 
 @pytest.fixture(scope="module", params=[("default", []), ("stepped", ["-DNANS_NP_STEPPED"]),
                                         ("gjk_capped", ["-DNANS_NP_GJK_CAPPED=8"]), ("gjk_capped1", ["-DNANS_NP_GJK_CAPPED=1"]),
+                                        ("carry3", ["-DNANS_NP_CARRY=3"]), ("carry8", ["-DNANS_NP_CARRY=8"]),
                                         ("boxepa", ["-DNANS_NP_BOX_EPA=1"]),
                                         ("boxepa_v4", ["-DNANS_NP_BOX_EPA=1", "-DNANS_NP_V4=1"])],
                 ids=lambda p: p[0])
