@@ -5,9 +5,11 @@
 cd "$(dirname "$0")/.."
 CFGS=(
   "128 5"
-  "128 5 -DNANS_NP_COMPACT=1"
-  "128 6 -DNANS_NP_COMPACT=1"
-  "128 4 -DNANS_NP_COMPACT=1"
+  "128 4"
+  "128 6"
+  "128 5 -DNANS_NP_BOX_EPA=1"
+  "128 5 -DNANS_NP_V4=1"
+  "128 5 -DNANS_NP_TREE_SUPPORT=1"
 )
 V=gpurun_variants
 case "$1" in
