@@ -156,7 +156,9 @@ def run_reference(args):
     from oracle import oracle as O
     from nans_projekat_b200 import scenes
     H = O.ref()
-    cfg = {"workload": "cube_pile", "bodies_per_world": args.bodies, "l2": "n/a (CPU)"}
+    # the same workload name as our arm's line (the reference can only run a sample of it: `sample` says which)
+    cfg = {"workload": "cube_pile_1M" if args.bodies == 1_000_000 else f"cube_pile_{args.bodies}",
+           "bodies_per_world": args.bodies, "l2": "n/a (CPU)"}
     # 16-cube sample: a 2x2 footprint, 4 layers of the same lattice, settled on the floor
     s = scenes.cube_pile(n_side=2, layers=4, seed=7)
     window = 25     # world steps per window; every window restarts from the same prepared state
