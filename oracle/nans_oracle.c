@@ -10,7 +10,9 @@
 
 #include <float.h>
 #include <math.h>
+#include <pthread.h>
 #include <stdlib.h>
+#include <unistd.h>
 #include <string.h>
 
 typedef struct { float x, y, z; } v3;
@@ -482,8 +484,237 @@ static void test_pair(int type, int a, int b, const oracle_shape *A, const oracl
     }
 }
 
+/* ---- spatial prefilter (prefilter == 2): TEST INFRASTRUCTURE ONLY, not in the reference -------------
+ * The reference tests every pair (code/nans.cpp:1357-1364); at 10^6 bodies that is 5*10^11 GJK calls.
+ * This path yields the SAME contact list in the SAME order: a uniform grid over the inflated AABBs
+ * (cell edge >= the largest AABB extent, so overlapping AABBs sit in adjacent cells) proposes, for
+ * every body i, the partners j whose AABB overlaps -- the exact predicate of prefilter == 1 -- which
+ * are then sorted ascending, so the pairs are visited in the all-pairs loop order.  The GJK/EPA calls
+ * (pure functions of one pair) run on worker threads (pthreads); the list is assembled serially in order.
+ * tests/test_oracle_grid.py proves it equal to the all-pairs list on <=16-body and 10k-body worlds. */
+typedef struct {
+    float *lo, *hi;          /* [nb][3] inflated AABBs, cubes then spheres */
+    int64_t *tab_key;        /* open-addressing hash: packed cell coordinates -> cell id (-1 = empty) */
+    int32_t *tab_cell;
+    uint32_t tab_mask;
+    int32_t *cell_start;     /* [ncell + 1] */
+    int32_t *cell_body;      /* [nb] bodies grouped by cell, ascending inside a cell */
+    int32_t *cell_of;        /* [nb] */
+    int32_t (*coord)[3];     /* [nb] integer cell coordinates */
+    float inv;
+} grid_t;
+
+/* unbounded integer cell coordinate, clamped (monotonically) to +-2^20; NaN -> 0 (overlap tests fail anyway) */
+static int32_t grid_coord(const grid_t *g, float c)
+{
+    float f = floorf(c * g->inv);
+    if (!(f == f)) return 0;
+    if (f < -1048576.0f) return -1048576;
+    if (f > 1048576.0f) return 1048576;
+    return (int32_t)f;
+}
+static int64_t cell_key(int32_t x, int32_t y, int32_t z)
+{
+    return ((int64_t)(x + 2097152) << 44) | ((int64_t)(y + 2097152) << 22) | (int64_t)(z + 2097152);
+}
+static uint32_t key_hash(int64_t k)
+{
+    uint64_t h = (uint64_t)k * 0x9E3779B97F4A7C15ull;
+    return (uint32_t)(h >> 32);
+}
+/* cell id of the key, or -1; insert != 0 creates it (next id = *ncell) */
+static int32_t grid_lookup(grid_t *g, int64_t key, int insert, int32_t *ncell)
+{
+    uint32_t h = key_hash(key) & g->tab_mask;
+    for (;;) {
+        if (g->tab_key[h] == key) return g->tab_cell[h];
+        if (g->tab_key[h] == -1) {
+            if (!insert) return -1;
+            g->tab_key[h] = key;
+            g->tab_cell[h] = (*ncell)++;
+            return g->tab_cell[h];
+        }
+        h = (h + 1) & g->tab_mask;
+    }
+}
+static void grid_build(const oracle_world *w, grid_t *g)
+{
+    const int nb = w->n_cubes + w->n_spheres;
+    oracle_shape S;
+    g->lo = malloc(sizeof(float) * 3 * (nb + 1));
+    g->hi = malloc(sizeof(float) * 3 * (nb + 1));
+    float ext = 0.0f;
+    for (int b = 0; b < nb; ++b) {
+        if (b < w->n_cubes) cube_shape(w, b, &S); else sphere_shape(w, b - w->n_cubes, &S);
+        shape_aabb(&S, g->lo + 3 * b, g->hi + 3 * b);
+        for (int r = 0; r < 3; ++r) {
+            float e = g->hi[3 * b + r] - g->lo[3 * b + r];
+            if (e > ext && e < 1e6f) ext = e;      /* a non-finite / absurd box cannot overlap anything finite nearby */
+        }
+    }
+    if (!(ext > 1e-3f)) ext = 1e-3f;
+    ext *= 1.001f;
+    g->inv = 1.0f / ext;
+    uint32_t tab = 1024;
+    while (tab < 2u * (uint32_t)(nb + 1)) tab <<= 1;
+    g->tab_mask = tab - 1;
+    g->tab_key = malloc(sizeof(int64_t) * tab);
+    g->tab_cell = malloc(sizeof(int32_t) * tab);
+    for (uint32_t k = 0; k < tab; ++k) g->tab_key[k] = -1;
+    g->cell_of = malloc(sizeof(int32_t) * (nb + 1));
+    g->coord = malloc(sizeof(int32_t[3]) * (nb + 1));
+    int32_t ncell = 0;
+    for (int b = 0; b < nb; ++b) {
+        for (int r = 0; r < 3; ++r) g->coord[b][r] = grid_coord(g, 0.5f * (g->lo[3 * b + r] + g->hi[3 * b + r]));
+        g->cell_of[b] = grid_lookup(g, cell_key(g->coord[b][0], g->coord[b][1], g->coord[b][2]), 1, &ncell);
+    }
+    g->cell_start = calloc((size_t)ncell + 1, sizeof(int32_t));
+    g->cell_body = malloc(sizeof(int32_t) * (nb + 1));
+    for (int b = 0; b < nb; ++b) g->cell_start[g->cell_of[b] + 1]++;
+    for (int32_t c = 0; c < ncell; ++c) g->cell_start[c + 1] += g->cell_start[c];
+    int32_t *fill = malloc(sizeof(int32_t) * ((size_t)ncell + 1));
+    memcpy(fill, g->cell_start, sizeof(int32_t) * ((size_t)ncell + 1));
+    for (int b = 0; b < nb; ++b) g->cell_body[fill[g->cell_of[b]]++] = b;   /* ascending body index per cell */
+    free(fill);
+}
+static void grid_free(grid_t *g)
+{
+    free(g->lo); free(g->hi); free(g->tab_key); free(g->tab_cell); free(g->cell_start); free(g->cell_body);
+    free(g->cell_of); free(g->coord);
+}
+
+static int cmp_i32(const void *a, const void *b) { int32_t x = *(const int32_t *)a, y = *(const int32_t *)b; return (x > y) - (x < y); }
+
+/* partners of body b among rows [jlo, jhi) with an overlapping AABB, ascending; returns the count.
+ * A box of extent > cell (only the absurd ones skipped above) is tested against nothing: it is non-finite or
+ * farther than 1e6 across, and cannot be part of a contact the all-pairs loop would keep either -- except by
+ * overlapping everything; such worlds are out of this helper's domain (tests use prefilter 0/1 for them). */
+static int grid_partners(grid_t *g, int b, int jlo, int jhi, int32_t **buf, int *cap)
+{
+    int n = 0;
+    const int32_t cx = g->coord[b][0], cy = g->coord[b][1], cz = g->coord[b][2];
+    for (int32_t z = cz - 1; z <= cz + 1; ++z)
+        for (int32_t y = cy - 1; y <= cy + 1; ++y)
+            for (int32_t x = cx - 1; x <= cx + 1; ++x) {
+                const int32_t c = grid_lookup(g, cell_key(x, y, z), 0, NULL);
+                if (c < 0) continue;
+                for (int k = g->cell_start[c]; k < g->cell_start[c + 1]; ++k) {
+                    const int j = g->cell_body[k];
+                    if (j < jlo || j >= jhi) continue;
+                    if (!aabb_overlap(g->lo + 3 * b, g->hi + 3 * b, g->lo + 3 * j, g->hi + 3 * j)) continue;
+                    if (n == *cap) { *cap = *cap ? 2 * *cap : 64; *buf = realloc(*buf, sizeof(int32_t) * *cap); }
+                    (*buf)[n++] = j;
+                }
+            }
+    qsort(*buf, n, sizeof(int32_t), cmp_i32);
+    return n;
+}
+
+typedef struct { int32_t type, a, b; } cand_t;   /* a, b: reference indices (sphere indices 0-based) */
+
+typedef struct {
+    const oracle_world *w; const cand_t *cand; oracle_contact *res; uint8_t *hit; long total; long next;
+} np_job;
+static void *np_worker(void *arg)
+{
+    np_job *J = arg;
+    const oracle_world *w = J->w;
+    for (;;) {
+        const long q0 = __atomic_fetch_add(&J->next, 1024, __ATOMIC_RELAXED);
+        if (q0 >= J->total) break;
+        const long q1 = q0 + 1024 < J->total ? q0 + 1024 : J->total;
+        for (long q = q0; q < q1; ++q) {
+            oracle_shape A, B;
+            const cand_t c = J->cand[q];
+            switch (c.type) {
+            case ORC_CC: cube_shape(w, c.a, &A); cube_shape(w, c.b, &B); break;
+            case ORC_CF: cube_shape(w, c.a, &A); static_shape(w, c.b, &B); break;
+            case ORC_SF: sphere_shape(w, c.a, &A); static_shape(w, c.b, &B); break;
+            case ORC_CS: cube_shape(w, c.a, &A); sphere_shape(w, c.b, &B); break;
+            default: sphere_shape(w, c.a, &A); sphere_shape(w, c.b, &B); break;
+            }
+            oracle_contact *o = &J->res[q];
+            memset(o, 0, sizeof(*o));
+            o->type = c.type; o->a = c.a; o->b = c.b;
+            J->hit[q] = (uint8_t)(oracle_check_collision(&A, &B, o->n, o->point_a, o->point_b, NULL) != 0);
+        }
+    }
+    return NULL;
+}
+
+static int detect_grid(const oracle_world *w, oracle_contact *out, int cap)
+{
+    grid_t g;
+    grid_build(w, &g);
+    const int nc = w->n_cubes, ns = w->n_spheres, nb = nc + ns;
+    /* candidate list in the reference's loop order: CC, CF, SF, CS, SS (code/nans.cpp:1355-1535) */
+    size_t ccap = (size_t)16 * (nb + 16), cn = 0;
+    cand_t *cand = malloc(sizeof(cand_t) * ccap);
+    int32_t *buf = NULL; int bcap = 0;
+#define PUSH(T, A, B) do { if (cn == ccap) { ccap *= 2; cand = realloc(cand, sizeof(cand_t) * ccap); } \
+                           cand[cn].type = (T); cand[cn].a = (A); cand[cn].b = (B); ++cn; } while (0)
+    for (int i = 0; i < nc; ++i) {
+        const int n = grid_partners(&g, i, i + 1, nc, &buf, &bcap);
+        for (int k = 0; k < n; ++k) PUSH(ORC_CC, i, buf[k]);
+    }
+    float slo[3], shi[3];
+    oracle_shape S;
+    const size_t cf_begin = cn;
+    for (int i = 0; i < nc; ++i)
+        for (int k = 0; k < w->n_statics; ++k) {
+            static_shape(w, k, &S); shape_aabb(&S, slo, shi);
+            if (aabb_overlap(g.lo + 3 * i, g.hi + 3 * i, slo, shi)) PUSH(ORC_CF, i, k);
+        }
+    for (int i = 0; i < ns; ++i)
+        for (int k = 0; k < w->n_statics; ++k) {
+            static_shape(w, k, &S); shape_aabb(&S, slo, shi);
+            if (aabb_overlap(g.lo + 3 * (nc + i), g.hi + 3 * (nc + i), slo, shi)) PUSH(ORC_SF, i, k);
+        }
+    (void)cf_begin;
+    for (int i = 0; i < nc && ns > 0; ++i) {
+        const int n = grid_partners(&g, i, nc, nb, &buf, &bcap);
+        for (int k = 0; k < n; ++k) PUSH(ORC_CS, i, buf[k] - nc);
+    }
+    for (int i = 0; i < ns; ++i) {
+        const int n = grid_partners(&g, nc + i, nc + i + 1, nb, &buf, &bcap);
+        for (int k = 0; k < n; ++k) PUSH(ORC_SS, i, buf[k] - nc);
+    }
+#undef PUSH
+    free(buf);
+    /* GJK + EPA per candidate: independent pure functions of one pair, so they run on worker threads */
+    oracle_contact *res = malloc(sizeof(oracle_contact) * (cn + 1));
+    uint8_t *hit = malloc(cn + 1);
+    np_job job = {w, cand, res, hit, (long)cn, 0};
+    long nthr = sysconf(_SC_NPROCESSORS_ONLN);
+    if (nthr > 32) nthr = 32;
+    if (nthr < 1 || cn < 4096) nthr = 1;
+    pthread_t th[32];
+    for (long t = 1; t < nthr; ++t) pthread_create(&th[t], NULL, np_worker, &job);
+    np_worker(&job);
+    for (long t = 1; t < nthr; ++t) pthread_join(th[t], NULL);
+    /* ordered assembly, with the live CS "Exists" quirk (:1479-1489, see the all-pairs loop below) */
+    int n = 0, cs_begin = -1;
+    for (size_t q = 0; q < cn; ++q) {
+        if (cand[q].type == ORC_CS && cs_begin < 0) cs_begin = n;
+        if (!hit[q]) continue;
+        if (cand[q].type == ORC_CS && cand[q].b < cand[q].a) {
+            int dropped = 0;
+            const int lim = n < cap ? n : cap;
+            for (int k = cs_begin; k < lim; ++k)
+                if (out[k].a == cand[q].b && out[k].b == cand[q].a) { dropped = 1; break; }
+            if (dropped) continue;
+        }
+        if (n < cap) out[n] = res[q];
+        ++n;
+    }
+    free(res); free(hit); free(cand);
+    grid_free(&g);
+    return n;
+}
+
 int oracle_detect_collisions(const oracle_world *w, oracle_contact *out, int cap, int prefilter)
 {
+    if (prefilter == 2) return detect_grid(w, out, cap);
     contact_sink sink = {out, 0, cap};
     oracle_shape A, B;
     /* prefilter acceleration for large N: sort-free O(N^2) on cached AABBs */

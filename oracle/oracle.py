@@ -124,6 +124,9 @@ class World:
         s = self.struct(); lib().oracle_rebuild_vertices(C.byref(s))
 
     def detect(self, cap=None, prefilter=False) -> np.ndarray:
+        """prefilter: False/0 = the reference's all-pairs loop; True/1 = all pairs, AABB-rejected; "grid"/2 = uniform
+        grid over the same AABB predicate (same list, same order; seconds at 10^6 bodies)."""
+        prefilter = 2 if prefilter == "grid" else int(prefilter)
         cap = cap or max(64, 16 * self.nb)
         out = np.zeros(cap, CONTACT_DTYPE)
         s = self.struct()
@@ -138,6 +141,7 @@ class World:
                                        len(contacts))
 
     def step(self, dt, prefilter=False, cap=None) -> np.ndarray:
+        prefilter = 2 if prefilter == "grid" else int(prefilter)
         cap = cap or max(64, 16 * self.nb)
         out = np.zeros(cap, CONTACT_DTYPE)
         s = self.struct()
