@@ -8,9 +8,14 @@
 A "step" is one pass of IntegrateForces -> DetectCollisions (broadphase + GJK/EPA) ->
 SolveConstraints -> IntegrateVelocities (+ vertex rebuild) over the whole world
 (reference code/nans.cpp:1758-1762).  Workload at N=1: the 1M-cube pile (BASELINE.json metric:
-"body-steps/sec at 1M cubes"), one world resident on one GPU.  At N>1 every rank steps its own
-independent 1M-cube world (north_star: "independent batched worlds ... shard embarrassingly
-across GPUs with no communication"), so scaling is weak and there is no data-path collective.
+"body-steps/sec at 1M cubes") in SURVEY.md 8(d)'s shape, 100 x 100 x 100 cubes, one world resident on
+one GPU; the flat 250 x 250 x 16 pile of round 1 is timed beside it (`alt_shapes`).  The same line
+carries the second half of the metric (config C3: GJK+EPA pairs/s on 16 Mi random pairs, flags
+checked against the reference binary), configs C2 and C4 as sub-records, and an in-run parity check
+of the headline state against the CPU oracle.  At N>1 every rank steps its own independent 1M-cube
+world (north_star: "independent batched worlds ... shard embarrassingly across GPUs with no
+communication"): weak scaling, no data-path collective; the `slab` sub-record is ONE world of
+N x 1M cubes in spatial x-slabs with an NCCL halo exchange (config C5).
 Prints ONE JSON line on rank 0.
 """
 import argparse
@@ -39,8 +44,10 @@ def parse():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--bodies", type=int, default=1_000_000, help="cubes per world (per rank)")
-    ap.add_argument("--side", type=int, default=250, help="pile footprint: side x side cubes per layer")
-    ap.add_argument("--settle", type=int, default=40, help="untimed scene-preparation steps before warm-up")
+    ap.add_argument("--side", type=int, default=100, help="pile footprint: side x side cubes per layer "
+                                                           "(100 -> 100x100x100, SURVEY 8d; 250 -> 250x250x16)")
+    ap.add_argument("--settle", type=int, default=-1, help="untimed scene-preparation steps before warm-up "
+                                                            "(-1: 80 for the 100^3 pile, 40 otherwise)")
     ap.add_argument("--window", type=int, default=20, help="steps between snapshot restores")
     ap.add_argument("--cpu-bodies", type=int, default=2048, help="size of the CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -50,9 +57,14 @@ def parse():
     ap.add_argument("--mode", default="worlds", choices=["worlds", "slab"],
                     help="N>1: 'worlds' = one independent world per GPU (weak scaling, no collective; default); "
                          "'slab' = ONE world split by body-index slabs with NCCL halo exchange (strong scaling)")
-    ap.add_argument("--c3", type=int, default=0, metavar="PAIRS",
-                    help="also run the GJK+EPA microbench (config C3) on this many random pairs (e.g. 16777216)")
-    return ap.parse_args()
+    ap.add_argument("--c3", type=int, default=-1, metavar="PAIRS",
+                    help="GJK+EPA microbench (config C3) on this many random pairs; -1 = 16777216 at N=1, off at N>1; 0 = off")
+    ap.add_argument("--c3-check", type=int, default=1 << 20, help="pairs of C3 whose flags are checked on the CPU")
+    ap.add_argument("--no-subrecords", action="store_true", help="skip alt shape, C2, C4 and the in-run parity check")
+    a = ap.parse_args()
+    if a.settle < 0:
+        a.settle = 80 if (a.workload == "pile" and a.side == 100) else 40
+    return a
 
 
 class ClockSampler:

@@ -8,7 +8,6 @@
 //                              the same over stand-alone shape pairs (nans_check_collision_batch/_device, config
 //                              C3), where half the pairs miss and GJK / EPA lengths are long-tailed: GJK capped,
 //                              stragglers and intersecting pairs compacted into lists, EPA over the lists.
-//   narrowphase_batch_kernel   the one-kernel form over stand-alone pairs (NANS_NP_SPLIT=0, A/B).
 //
 // FP32-pipe / divergence bound, not HBM bound: 216 B in + 48 B out per pair against ~1-5 kflop of unfused fp32
 // (SURVEY.md §8d).
@@ -58,12 +57,6 @@ __device__ __forceinline__ NpResult dispatch(bool a_sphere, bool b_sphere, NpSha
     return check_collision<true, true>(S, E, ovf, max_faces);
 }
 
-#ifndef NANS_NP_CHUNK2
-#define NANS_NP_CHUNK2 0   // 1: a warp takes 64 pairs per ticket, both index pairs arrive in one round trip and the
-#endif                     // second pair's shapes are prefetched to L2 during the first: measured slower (0.935 vs 0.902 ms)
-
-__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
-
 __device__ __forceinline__ void np_world_pair(const DeviceWorld &w, int p, int ra, int rb, NpShapes &S, EpaArena &E,
                                               int &ovf, int &max_faces, int &found)
 {
@@ -105,29 +98,14 @@ __global__ void __launch_bounds__(kNpThreads, NANS_NP_MINBLOCKS) narrowphase_wor
     const int n_pairs = w.counters->n_pairs;
     int ovf = 0, max_faces = 0, found = 0;
     NpShapes S;
-    constexpr int kPerTicket = NANS_NP_CHUNK2 ? 64 : 32;
+    constexpr int kPerTicket = 32;
     while (true) {
         int base = 0;
         if (lane == 0) base = atomicAdd(work_counter, kPerTicket);
         base = __shfl_sync(0xffffffffu, base, 0);
         if (base >= n_pairs) break;
         const int p = base + lane;
-#if NANS_NP_CHUNK2
-        const int p2 = p + 32;
-        int ra = 0, rb = 0, ra2 = 0, rb2 = 0;
-        if (p < n_pairs) { ra = w.pair_a[p]; rb = w.pair_b[p]; }
-        if (p2 < n_pairs) {
-            ra2 = w.pair_a[p2]; rb2 = w.pair_b[p2];
-            // the second pair's bodies: towards L2 now, wanted after the first pair's GJK + EPA
-            if (ra2 < w.n_cubes) { const char *q = (const char *)(w.verts + 6 * (size_t)ra2); prefetch_l2(q); prefetch_l2(q + 64); }
-            if (rb2 >= 0 && rb2 < w.n_cubes) { const char *q = (const char *)(w.verts + 6 * (size_t)rb2); prefetch_l2(q); prefetch_l2(q + 64); }
-        }
-        if (p < n_pairs) np_world_pair(w, p, ra, rb, S, E, ovf, max_faces, found);
-        __syncwarp();
-        if (p2 < n_pairs) np_world_pair(w, p2, ra2, rb2, S, E, ovf, max_faces, found);
-#else
         if (p < n_pairs) np_world_pair(w, p, w.pair_a[p], w.pair_b[p], S, E, ovf, max_faces, found);
-#endif
     }
     // per-warp stats
     found = __reduce_add_sync(0xffffffffu, found);
@@ -137,49 +115,6 @@ __global__ void __launch_bounds__(kNpThreads, NANS_NP_MINBLOCKS) narrowphase_wor
         if (found) atomicAdd(&w.counters->n_gjk_found, found);
         if (ovf) atomicOr(&w.counters->overflow, ovf);
         atomicMax(&w.counters->max_epa_faces, max_faces);
-    }
-}
-
-// stand-alone pairs (config C3): type per pair, shapes given explicitly
-__global__ void __launch_bounds__(kNpThreads, NANS_NP_MINBLOCKS) narrowphase_batch_kernel(
-    int n, const int32_t *__restrict__ type, const float4 *__restrict__ posrad_a,
-    const float4 *__restrict__ verts_a, const float4 *__restrict__ posrad_b,
-    const float4 *__restrict__ verts_b, int32_t *__restrict__ hit, int32_t *__restrict__ gjk,
-    float4 *__restrict__ out, int *work_counter, Counters *counters)
-{
-    EpaArena E;
-    const int lane = threadIdx.x & 31;
-    int ovf = 0, max_faces = 0;
-    NpShapes S;
-    while (true) {
-        int base = 0;
-        if (lane == 0) base = atomicAdd(work_counter, 32);
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (base >= n) break;
-        const int p = base + lane;
-        if (p < n) {
-            const int t = type[p];
-            const bool a_sphere = (t == NANS_SS || t == NANS_SF);
-            const bool b_sphere = (t == NANS_CS || t == NANS_SS);
-            const float4 pa = posrad_a[p], pb = posrad_b[p];
-            S.posA = V3(pa); S.radA = pa.w;
-            S.posB = V3(pb); S.radB = pb.w;
-            if (!a_sphere) load_box(0, verts_a + 6 * (size_t)p);
-            if (!b_sphere) load_box(1, verts_b + 6 * (size_t)p);
-            const NpResult r = dispatch(a_sphere, b_sphere, S, E, ovf, max_faces);
-            hit[p] = r.hit;
-            if (gjk) gjk[p] = r.gjk;
-            float4 *o = out + 3 * (size_t)p;
-            o[0] = make_float4(r.PA.x, r.PA.y, r.PA.z, 0.f);
-            o[1] = make_float4(r.PB.x, r.PB.y, r.PB.z, 0.f);
-            o[2] = make_float4(r.N.x, r.N.y, r.N.z, 0.f);
-        }
-    }
-    ovf = __reduce_or_sync(0xffffffffu, ovf);
-    max_faces = __reduce_max_sync(0xffffffffu, max_faces);
-    if (lane == 0 && counters) {
-        if (ovf) atomicOr(&counters->overflow, ovf);
-        atomicMax(&counters->max_epa_faces, max_faces);
     }
 }
 
@@ -374,74 +309,10 @@ __global__ void __launch_bounds__(kNpThreads, NANS_GJK_MINBLOCKS) gjk_split_kern
     }
 }
 
-#ifndef NANS_EPA_REFILL_MIN
-#define NANS_EPA_REFILL_MIN 32    // idle lanes of a warp before it fetches new pairs
-#endif
-
-// EPA over one class list.  A warp takes new pairs whenever NANS_EPA_REFILL_MIN of its lanes are idle.
-// 32 (= whole chunks of the COMPACTED list) measured best on config C3: 16 Mi pairs in 29.6 ms against 30.6
-// (16), 31.9 (8), 33.8 (4), 35.4 ms (1) and 40.9 ms for the one-kernel form -- lanes at different iteration
-// numbers carry polytopes of very different sizes, and in lock step every lane pays for the largest one in
-// its warp, which costs more than the idle lanes of a chunk do.  Also measured and dropped: iteration caps
-// with the long pairs deferred to a second list and restarted from their simplex next to pairs of their
-// own length (EPA lengths on random cube-sphere pairs: median 9, 99 % <= 24, up to 57): -5 % at best, the
-// repeated iterations cost what the better packing saves.
-template <bool AS, bool BS, typename Src>
-__device__ __noinline__ void epa_refill_list(const Src &src, const SplitScratch &sc, NpShapes &S, EpaArena &E,
-                                             int &ovf, int &max_faces)
-{
-    constexpr int cls = 2 * (int)AS + (int)BS;
-    constexpr unsigned kFull = 0xffffffffu;
-    const int lane = threadIdx.x & 31;
-    const int32_t *list = sc.list[cls];
-    const int count = sc.head[cls];
-    bool active = false, more = count > 0;
-    int p = 0;
-    EpaState st;
-    vec3 PA, PB, N;
-    while (true) {
-        __syncwarp();
-        const unsigned idle = __ballot_sync(kFull, !active);
-        if (more && (idle == kFull || __popc(idle) >= NANS_EPA_REFILL_MIN)) {
-            int base = 0;
-            if (lane == 0) base = atomicAdd(sc.head + 4 + cls, __popc(idle));
-            base = __shfl_sync(kFull, base, 0);
-            const int k = base + __popc(idle & ((1u << lane) - 1u));
-            if (!active && k < count) {
-                p = list[k];
-                src.load(p, AS, BS, S);
-                const float4 *r = sc.rec + 8 * (size_t)p;
-                GjkVertex<AS, BS> s[4];
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const vec3 sa = unpack_sup<AS>(S, 0, r[j], s[j].a);
-                    const vec3 sb = unpack_sup<BS>(S, 1, r[4 + j], s[j].b);
-                    s[j].P = sa - sb;                 // CalculateSupport's P, same operands, same bits
-                }
-                epa_begin<AS, BS>(s, E.g, st);
-                active = true;
-            }
-            more = base + __popc(idle) < count;
-        }
-        __syncwarp();
-        if (!__any_sync(kFull, active)) {
-            if (!more) break;
-            continue;
-        }
-        if (active) {
-            const int r = epa_step<AS, BS>(S, E.g, st, PA, PB, N, ovf, max_faces);
-            if (r != kEpaContinue) {
-                if (r) src.store_hit(p, PA, PB, N);
-                active = false;
-            }
-        }
-    }
-}
-
-// The same over whole chunks with the one-loop EPA (epa_resolve / epa_resolve_box): what NANS_EPA_REFILL_MIN = 32
-// amounts to, without the state-machine bookkeeping: 27.2 ms against 29.6 ms for 16 Mi pairs.  Default
-// (NANS_EPA_STEPPED = 0).  Resident CTAs per SM 2..5 make no difference (27.1-27.2 ms), 7 is slower (29.0);
-// the box-box arena (NANS_NP_BOX_EPA = 1) gives 26.9 ms.
+// EPA over one class list, whole 32-pair chunks of the COMPACTED list.  Measured on config C3 (16 Mi pairs) in round 1:
+// 27.2 ms, against 29.6-35.4 ms for a resumable per-iteration form with lane-level refill (lanes at different iteration
+// numbers carry polytopes of very different sizes and in lock step every lane pays for the largest) and 40.9 ms for
+// GJK + EPA in one kernel.  Resident CTAs per SM 2..5 make no difference.
 template <bool AS, bool BS, typename Src>
 __device__ __noinline__ void epa_chunk_list(const Src &src, const SplitScratch &sc, NpShapes &S, EpaArena &E,
                                             int &ovf, int &max_faces)
@@ -464,24 +335,11 @@ __device__ __noinline__ void epa_chunk_list(const Src &src, const SplitScratch &
             load_simplex<AS, BS>(S, sc.rec, p, s, n_, iter_);
             vec3 PA, PB, N;
             int hit;
-#if NANS_NP_BOX_EPA
-            if constexpr (!AS && !BS) hit = epa_resolve_box(S, s, E.b, PA, PB, N, ovf, max_faces);
-            else
-#endif
-                hit = epa_resolve<AS, BS>(S, s, E.g, PA, PB, N, ovf, max_faces);
+            hit = epa_resolve<AS, BS>(S, s, E, PA, PB, N, ovf, max_faces);
             if (hit) src.store_hit(p, PA, PB, N);
         }
     }
 }
-
-#ifndef NANS_EPA_STEPPED
-#define NANS_EPA_STEPPED 0
-#endif
-#if NANS_EPA_STEPPED
-#define NANS_EPA_LIST epa_refill_list
-#else
-#define NANS_EPA_LIST epa_chunk_list
-#endif
 
 template <typename Src>
 __global__ void __launch_bounds__(kNpThreads, NANS_EPA_MINBLOCKS) epa_refill_kernel(Src src, SplitScratch sc, Counters *counters)
@@ -489,10 +347,10 @@ __global__ void __launch_bounds__(kNpThreads, NANS_EPA_MINBLOCKS) epa_refill_ker
     EpaArena E;
     NpShapes S;
     int ovf = 0, max_faces = 0;
-    NANS_EPA_LIST<false, false>(src, sc, S, E, ovf, max_faces);
-    NANS_EPA_LIST<false, true>(src, sc, S, E, ovf, max_faces);
-    NANS_EPA_LIST<true, false>(src, sc, S, E, ovf, max_faces);
-    NANS_EPA_LIST<true, true>(src, sc, S, E, ovf, max_faces);
+    epa_chunk_list<false, false>(src, sc, S, E, ovf, max_faces);
+    epa_chunk_list<false, true>(src, sc, S, E, ovf, max_faces);
+    epa_chunk_list<true, false>(src, sc, S, E, ovf, max_faces);
+    epa_chunk_list<true, true>(src, sc, S, E, ovf, max_faces);
     ovf = __reduce_or_sync(0xffffffffu, ovf);
     max_faces = __reduce_max_sync(0xffffffffu, max_faces);
     if ((threadIdx.x & 31) == 0 && counters) {
@@ -556,16 +414,6 @@ int launch_narrowphase_batch(int n, const int32_t *type, const float4 *posrad_a,
                              float4 *out, int *work_counter, Counters *counters, cudaStream_t s)
 {
     if (n <= 0) return NANS_OK;
-    static int split = -1;
-    if (split < 0) { const char *e = getenv("NANS_NP_SPLIT"); split = (e && atoi(e) == 0) ? 0 : 1; }
-    if (!split) {
-        NANS_CUDA(cudaMemsetAsync(work_counter, 0, sizeof(int), s));
-        const int grid = np_grid(div_up(n, kNpThreads));
-        narrowphase_batch_kernel<<<grid, kNpThreads, 0, s>>>(n, type, posrad_a, verts_a, posrad_b, verts_b, hit, gjk,
-                                                             out, work_counter, counters);
-        NANS_LAUNCH_CHECK();
-        return NANS_OK;
-    }
     // at most kSplitChunk pairs per round (bounds the scratch: 144 B per pair)
     constexpr int kSplitChunk = 1 << 24;   // (scratch: 160 B per pair)
     static int gjk_per_sm = 0, epa_per_sm = 0;

@@ -367,6 +367,11 @@ static int resolve_collision(const oracle_shape *SA, const oracle_shape *SB, vtx
         }
         for (int i = 0; i < E.n; ++i) push_triangle(&T, ns, E.e[i].A, E.e[i].B);
         E.n = 0;
+        /* T.n == 0 here means the next iteration reads T.t[0] of an EMPTY list, exactly as the reference reads
+         * Triangle[0] of its emptied std::vector (:807-811): the storage still holds the last face, shifted down
+         * by the erases (memmove above == vector::erase).  nans.so does report hits this way (pinned by
+         * tests/golden/epa_emptied.npz); T.cap >= 16, so the read stays inside the allocation. */
+        if (st && T.n == 0) st->emptied++;
     }
 done:
     free(T.t);

@@ -60,6 +60,7 @@ typedef struct {
     int32_t gjk_iters;
     int32_t epa_iters;    /* 0 if EPA not entered */
     int32_t max_faces, max_edges; /* EPA high-water marks (capacity planning for the device arenas) */
+    int32_t emptied;      /* EPA iterations that left the triangle list EMPTY (the next one reads the stale Triangle[0]) */
 } oracle_np_stats;
 
 /* code/nans.cpp:907-966 (+ :572-769 GJK, :788-904 EPA). Returns the bool32 result. */

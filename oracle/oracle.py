@@ -54,7 +54,7 @@ CONTACT_DTYPE = np.dtype([("type", "<i4"), ("a", "<i4"), ("b", "<i4"),
 assert CONTACT_DTYPE.itemsize == 48
 
 NP_STATS_DTYPE = np.dtype([("gjk_result", "<i4"), ("gjk_iters", "<i4"), ("epa_iters", "<i4"),
-                           ("max_faces", "<i4"), ("max_edges", "<i4")])
+                           ("max_faces", "<i4"), ("max_edges", "<i4"), ("emptied", "<i4")])
 
 _lib = None
 

@@ -141,10 +141,31 @@ def gen_demo():
           "max contacts", max(ncontacts))
 
 
+def gen_epa_emptied(cases="/tmp/emptied_cases.npz"):
+    """EPA runs that empty the triangle list (the reference then reads the stale Triangle[0]): inputs found by
+    tests/golden/find_emptied_cases.py (or the previously committed fixture), outputs = nans.so's CheckCollision."""
+    dst = os.path.join(OUT, "epa_emptied.npz")
+    z = np.load(cases if os.path.exists(cases) else dst)
+    n = len(z["pos_a"])
+    p = dict(type=np.zeros(n, np.int32), pos_a=z["pos_a"].astype(np.float32), verts_a=z["verts_a"].astype(np.float32),
+             rad_a=np.zeros(n, np.float32), pos_b=z["pos_b"].astype(np.float32), verts_b=z["verts_b"].astype(np.float32),
+             rad_b=np.zeros(n, np.float32))
+    r = O.ref_check_collision_batch(p["type"], p["pos_a"], p["verts_a"], p["rad_a"], p["pos_b"], p["verts_b"], p["rad_b"])
+    o = O.check_collision_batch(p["type"], p["pos_a"], p["verts_a"], p["rad_a"], p["pos_b"], p["verts_b"], p["rad_b"],
+                                want_stats=True)
+    assert (o["stats"]["emptied"] > 0).all(), "every stored case must empty the triangle list"
+    np.savez_compressed(dst, **p, ref_hit=r["hit"], ref_N=r["N"], ref_PA=r["PA"], ref_PB=r["PB"])
+    print("epa_emptied:", n, "pairs,", int(r["hit"].sum()), "hits in the reference binary")
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "epa_emptied":
+        gen_epa_emptied()
+        sys.exit(0)
     gen_narrowphase()
     gen_stages()
     gen_demo()
+    gen_epa_emptied()
     for f in sorted(os.listdir(OUT)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(OUT, f)) // 1024, "KiB")

@@ -50,6 +50,18 @@ def test_narrowphase_golden(nb200, golden_dir, tag):
     assert rel_err(depth, depth_ref) <= 1e-4 and rel_err(r["N"][h], g("ref_N")[h]) <= 1e-4
 
 
+def test_narrowphase_emptied_polytope_golden(nb200, golden_dir):
+    """EPA runs that empty the reference's triangle list (it then reads the stale Triangle[0], code/nans.cpp:807-866;
+    found by the 1 M-cube parity test of round 2): flags and contacts as nans.so reports them, through both the
+    stand-alone batch path and (below, test_headline_gpu.py) the world kernel."""
+    z = np.load(os.path.join(golden_dir, "epa_emptied.npz"))
+    r = nb200.check_collision(z["type"], z["pos_a"], z["verts_a"], z["rad_a"], z["pos_b"], z["verts_b"], z["rad_b"])
+    assert np.array_equal(r["hit"], z["ref_hit"])
+    h = z["ref_hit"] == 1
+    for k in ("N", "PA", "PB"):
+        assert_bit_equal(r[k][h], z[f"ref_{k}"][h], f"emptied {k}")
+
+
 @pytest.mark.parametrize("rotated,n", [(True, 1 << 18), (False, 1 << 17)])
 def test_narrowphase_vs_oracle(nb200, oracle, rotated, n):
     """Config C3 at reduced size (CC/CS/SS strata 8:7:1): flags, GJK results and contacts bit-exact."""
