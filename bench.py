@@ -128,7 +128,7 @@ def build_workload(args, seed):
     if args.workload == "worlds4096":   # config C4: 4096 independent worlds x (48 cubes + 16 spheres)
         return scenes.batched_worlds(4096, 48, 16, seed=seed), 3, "batched_worlds_4096x64 (config C4)"
     scene, layers = build_pile(args.bodies, args.side, seed)
-    return scene, layers, ("cube_pile_1M" if scene.n_cubes == 1_000_000 else f"cube_pile_{scene.n_cubes}")
+    return scene, layers, ("cube_pile_1M" if scene.n_cubes == 1_000_000 else f"cube_pile_{scene.n_cubes}") + f"_{args.side}x{layers}x{args.side}"
 
 
 # --------------------------------------------------------------------------------------- CPU legs
@@ -174,8 +174,11 @@ def run_reference(args):
     from nans_projekat_b200 import scenes
     H = O.ref()
     # the same workload name as our arm's line (the reference can only run a sample of it: `sample` says which)
-    cfg = {"workload": "cube_pile_1M" if args.bodies == 1_000_000 else f"cube_pile_{args.bodies}",
-           "bodies_per_world": args.bodies, "l2": "n/a (CPU)"}
+    layers = max(1, (args.bodies + args.side * args.side - 1) // (args.side * args.side))
+    cfg = {"workload": ("cube_pile_1M" if args.bodies == 1_000_000 else f"cube_pile_{args.bodies}") + f"_{args.side}x{layers}x{args.side}",
+           "bodies_per_world": args.bodies, "l2": "n/a (CPU)",
+           "same_config": False,   # the reference binary is capped at 16 cubes (MAX_CUBE_COUNT, code/nans.h:52): it runs a SAMPLE
+           }
     # 16-cube sample: a 2x2 footprint, 4 layers of the same lattice, settled on the floor
     s = scenes.cube_pile(n_side=2, layers=4, seed=7)
     window = 25     # world steps per window; every window restarts from the same prepared state
@@ -243,27 +246,64 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
-def run_c3(n_pairs, device, reps=5):
-    """Config C3: GJK+EPA pairs/s on random cube/sphere pairs (strata CC:CS:SS = 8:7:1), device-resident
-    inputs, CUDA events; flags of a 64 Ki subsample are checked bit-exact against the CPU oracle."""
-    import ctypes as C
+def _c3_pairs_torch(n, seed, dev):
+    """Config C3 inputs generated ON THE DEVICE (synthetic input, not the product): strata CC:CS:SS = 8:7:1, shape A
+    at the origin, shape B centre U(-1.2,1.2)^3, unit cubes with Euler angles U(-pi,pi) (rotations in fp64, vertices
+    rounded to fp32: world-space vertices are the input), radii U(0.1,0.5)."""
     import torch
-    from nans_projekat_b200 import scenes, _lib
-    chunk = 1 << 20
-    parts = [scenes.narrowphase_pairs(min(chunk, n_pairs - o), seed=1234 + o) for o in range(0, n_pairs, chunk)]
-    cat = lambda k: np.concatenate([p[k] for p in parts])
-    t = cat("type")
-    posrad = lambda pk, rk: np.concatenate([cat(pk), cat(rk)[:, None]], 1).astype(np.float32)
+    g = torch.Generator(device=dev); g.manual_seed(seed)
+    n_cc, n_cs = int(round(n * 8 / 16)), int(round(n * 7 / 16))
+    t = torch.cat([torch.full((n_cc,), 0), torch.full((n_cs,), 1), torch.full((n - n_cc - n_cs,), 3)]).to(torch.int32).to(dev)
+    corners = torch.tensor([[.5, .5, .5], [.5, .5, -.5], [-.5, .5, .5], [-.5, .5, -.5],
+                            [.5, -.5, .5], [.5, -.5, -.5], [-.5, -.5, .5], [-.5, -.5, -.5]], dtype=torch.float64, device=dev)
+    out = {"type": t}
+    pos_b = (torch.rand((n, 3), generator=g, device=dev, dtype=torch.float64) * 2.4 - 1.2).float()
+    for side, pos in (("a", torch.zeros((n, 3), device=dev)), ("b", pos_b)):
+        verts = torch.empty((n, 8, 3), dtype=torch.float32, device=dev)
+        for o in range(0, n, 1 << 21):
+            m = min(1 << 21, n - o)
+            ang = (torch.rand((m, 3), generator=g, device=dev, dtype=torch.float64) * 2 - 1) * np.pi
+            c, s_ = torch.cos(ang), torch.sin(ang)
+            one, zero = torch.ones(m, device=dev, dtype=torch.float64), torch.zeros(m, device=dev, dtype=torch.float64)
+            rx = torch.stack([one, zero, zero, zero, c[:, 0], -s_[:, 0], zero, s_[:, 0], c[:, 0]], 1).view(m, 3, 3)
+            ry = torch.stack([c[:, 1], zero, s_[:, 1], zero, one, zero, -s_[:, 1], zero, c[:, 1]], 1).view(m, 3, 3)
+            rz = torch.stack([c[:, 2], -s_[:, 2], zero, s_[:, 2], c[:, 2], zero, zero, zero, one], 1).view(m, 3, 3)
+            r = rx @ ry @ rz
+            verts[o:o + m] = (torch.einsum("nij,kj->nki", r, corners) + pos[o:o + m, None, :].double()).float()
+        rad = (torch.rand(n, generator=g, device=dev, dtype=torch.float64) * 0.4 + 0.1).float()
+        out["posrad_" + side] = torch.cat([pos, rad[:, None]], 1).contiguous()
+        out["verts_" + side] = verts
+    return out
+
+
+def _ref_check_chunk(args):
+    """worker (separate process): CheckCollision of one chunk through the reference's own nans.so, else the oracle port"""
+    sys.path.insert(0, ROOT)
+    from oracle import oracle as O
+    t, pa, va, ra, pb, vb, rb = args
+    if O.ref() is not None:
+        return "reference", O.ref_check_collision_batch(t, pa, va, ra, pb, vb, rb)["hit"]
+    return "port", O.check_collision_batch(t, pa, va, ra, pb, vb, rb)["hit"]
+
+
+def run_c3(n_pairs, device, n_check, reps=3):
+    """Config C3: GJK+EPA pairs/s on random cube/sphere pairs, device-resident inputs, CUDA events.  The hit flags of
+    an evenly spaced subsample of `n_check` pairs are compared with CheckCollision of the reference's own binary
+    (oracle/_ref/nans.so, code/nans.cpp:907-966) run on the host cores in worker processes."""
+    import torch
+    from concurrent.futures import ProcessPoolExecutor
+    import multiprocessing as mp
+    from nans_projekat_b200 import _lib
     dev = torch.device("cuda", device)
-    d = {k: torch.from_numpy(np.ascontiguousarray(v)).to(dev) for k, v in
-         dict(type=t, pa=posrad("pos_a", "rad_a"), va=cat("verts_a"), pb=posrad("pos_b", "rad_b"), vb=cat("verts_b")).items()}
+    d = _c3_pairs_torch(n_pairs, 1234, dev)
     hit = torch.empty(n_pairs, dtype=torch.int32, device=dev)
     out = torch.empty((n_pairs, 12), dtype=torch.float32, device=dev)
     L = _lib.lib()
     stream = torch.cuda.current_stream(dev)
-    call = lambda: _lib.check(L.nans_check_collision_device(n_pairs, d["type"].data_ptr(), d["pa"].data_ptr(),
-                                                             d["va"].data_ptr(), d["pb"].data_ptr(), d["vb"].data_ptr(),
-                                                             hit.data_ptr(), out.data_ptr(), stream.cuda_stream))
+    call = lambda: _lib.check(L.nans_check_collision_device(n_pairs, d["type"].data_ptr(), d["posrad_a"].data_ptr(),
+                                                             d["verts_a"].data_ptr(), d["posrad_b"].data_ptr(),
+                                                             d["verts_b"].data_ptr(), hit.data_ptr(), out.data_ptr(),
+                                                             stream.cuda_stream))
     for _ in range(3):
         call()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -275,18 +315,34 @@ def run_c3(n_pairs, device, reps=5):
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / reps
     res = {"pairs": n_pairs, "ms": ms, "pairs_per_s": n_pairs / (ms * 1e-3), "hit_rate": float(hit.float().mean().item()),
-           "strata": "CC:CS:SS = 8:7:1, rotated unit cubes, r in [0.1,0.5], seed 1234 (+ chunk offset)",
-           "alg_bytes_per_pair": 264}
-    try:
-        from oracle import oracle as O
-        m = min(1 << 16, n_pairs)
-        idx = np.linspace(0, n_pairs - 1, m).astype(np.int64)
-        o = O.check_collision_batch(t[idx], cat("pos_a")[idx], cat("verts_a")[idx], cat("rad_a")[idx],
-                                    cat("pos_b")[idx], cat("verts_b")[idx], cat("rad_b")[idx])
-        res["flags_bit_exact_vs_oracle"] = bool(np.array_equal(hit.cpu().numpy()[idx], o["hit"]))
-        res["checked"] = int(m)
-    except Exception as ex:  # the oracle is optional here
-        res["flags_bit_exact_vs_oracle"] = f"not checked ({ex})"
+           "strata": "CC:CS:SS = 8:7:1, rotated unit cubes, r in [0.1,0.5], seed 1234, generated on the device",
+           "alg_bytes_per_pair": 264, "hbm_frac": 264 * n_pairs / (ms * 1e-3) / 1e9 / load_peaks()[0],
+           "bound": "fp32 issue / divergence (GJK+EPA), not HBM", "l2": "inputs larger than L2 (3.5 GB)"}
+    m = min(n_check, n_pairs)
+    if m > 0:
+        t0 = time.perf_counter()
+        idx = torch.linspace(0, n_pairs - 1, m, device=dev).long()
+        host = lambda k: d[k][idx].cpu().numpy()
+        t, pra, prb = host("type"), host("posrad_a"), host("posrad_b")
+        va, vb = host("verts_a"), host("verts_b")
+        h_gpu = hit[idx].cpu().numpy()
+        workers = max(1, min(os.cpu_count() or 1, 32))
+        cuts = np.linspace(0, m, 4 * workers + 1).astype(int)
+        jobs = [(t[a:b], np.ascontiguousarray(pra[a:b, :3]), va[a:b], np.ascontiguousarray(pra[a:b, 3]),
+                 np.ascontiguousarray(prb[a:b, :3]), vb[a:b], np.ascontiguousarray(prb[a:b, 3]))
+                for a, b in zip(cuts[:-1], cuts[1:]) if b > a]
+        try:
+            with ProcessPoolExecutor(workers, mp_context=mp.get_context("spawn")) as ex:
+                got = list(ex.map(_ref_check_chunk, jobs))
+            kinds = sorted({k for k, _ in got})
+            h_ref = np.concatenate([h for _, h in got])
+            res.update(checked=int(m), checker="oracle/_ref/nans.so CheckCollision" if kinds == ["reference"] else "oracle port",
+                       flags_bit_exact=bool(np.array_equal(h_gpu, h_ref)), mismatches=int((h_gpu != h_ref).sum()),
+                       check_seconds=time.perf_counter() - t0, check_workers=workers)
+        except Exception as ex:  # the checker is optional here; the -m gpu tests are the gate
+            res["flags_bit_exact"] = f"not checked ({type(ex).__name__}: {ex})"
+    del d, hit, out
+    torch.cuda.empty_cache()
     return res
 
 
@@ -345,6 +401,118 @@ def main_slab(args):
 
 
 # --------------------------------------------------------------------------------------- our arm
+FULL = ("pos", "vel", "force", "ang", "angvel", "torque", "verts")
+
+
+def prepare_world(scene, local, stream, settle):
+    """World on the device, vertices rebuilt, `settle` free-running steps, snapshot taken."""
+    from nans_projekat_b200.world import World
+    world = World(scene, device=local, stream=stream.cuda_stream)
+    world.rebuild_vertices()
+    for _ in range(settle):        # scene preparation: let the pile come into contact
+        world.step(DT)
+    world.synchronize()
+    world.snapshot()
+    return world
+
+
+def run_steps(world, n, window, step_fn):
+    """n steps; every `window` steps the world returns to the snapshot (inside whatever is being timed)."""
+    for k in range(n):
+        if k % window == 0:
+            world.restore()
+        step_fn()
+
+
+def time_steps(world, stream, steps, warmup, window, barrier=lambda: None):
+    """ms for `steps` steps, CUDA events on the launching stream, after `warmup` untimed ones."""
+    import torch
+    run_steps(world, warmup, window, lambda: world.step(DT))
+    world.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier(); torch.cuda.synchronize()
+    t_begin = time.time()
+    e0.record(stream)
+    run_steps(world, steps, window, lambda: world.step(DT))
+    e1.record(stream)
+    torch.cuda.synchronize(); barrier()
+    return e0.elapsed_time(e1), t_begin, time.time()
+
+
+def profile_stages(world, n_prof, window):
+    """per-stage ms (CUDA events between the stages) and mean pair / contact / DAG-depth counts over n_prof steps"""
+    stage, acc = {}, {"pairs": 0.0, "contacts": 0.0, "levels": 0.0}
+
+    def prof_step():
+        m = world.step_profiled(DT)
+        for k, v in m.items():
+            stage[k] = stage.get(k, 0.0) + v / n_prof
+        s_ = world.stats()
+        acc["pairs"] += s_["n_pairs"] / n_prof
+        acc["contacts"] += s_["n_contacts"] / n_prof
+        acc["levels"] += s_["solver_levels"] / n_prof
+    run_steps(world, n_prof, window, prof_step)
+    return stage, acc
+
+
+def stage_roofline(stage, acc, nb, peak):
+    alg = {"integrate_forces": nb * BYTES["integrate_forces"],
+           "broadphase": nb * (BYTES["aabb_key"] + BYTES["radix_sort"]) + acc["pairs"] * BYTES["pair_emit"],
+           "narrowphase": acc["pairs"] * BYTES["narrowphase"],
+           "solver": acc["contacts"] * BYTES["solver"],
+           "integrate_velocities": nb * BYTES["integrate_velocities"]}
+    per = {k: {"ms": stage[k], "alg_bytes": alg[k], "gbs": alg[k] / (stage[k] * 1e-3) / 1e9,
+               "frac": alg[k] / (stage[k] * 1e-3) / 1e9 / peak} for k in alg}
+    return alg, per
+
+
+def parity_in_run(world, scene, prepared):
+    """One step of the headline state on the GPU and on the CPU oracle (grid prefilter = the reference's all-pairs
+    list, tests/test_oracle_grid.py): contact list and post-step state must be bit-identical.  The oracle is the
+    CHECKER here; nothing it computes enters a timed region."""
+    from oracle import oracle as O
+    t0 = time.perf_counter()
+    w = O.World(scene.n_cubes, scene.n_spheres, scene.n_statics)
+    for f in scene.ARRAYS:
+        getattr(w, f)[...] = getattr(scene, f)
+    w.rebuild_vertices()
+    for f in FULL:
+        getattr(w, f)[...] = getattr(prepared, f)
+    world.restore()
+    world.step(DT)
+    gc = world.contacts()
+    d = world.download(fields=FULL)
+    oc = w.step(DT, prefilter="grid", cap=max(8 * scene.nb, 1 << 20))
+    same_c = gc.tobytes() == oc.tobytes()
+    bad = [f for f in ("pos", "vel", "ang", "angvel", "verts") if getattr(d, f).tobytes() != getattr(w, f).tobytes()]
+    world.restore()
+    return {"checked": "one step from the prepared state, GPU vs CPU oracle (oracle/nans_oracle.c, pinned to the "
+                       "reference's nans.so), contact list in reference order + pos/vel/ang/angvel/verts of every body",
+            "contacts": int(len(oc)), "contact_list_bit_exact": bool(same_c), "state_bit_exact": not bad,
+            "fields_differing": bad, "seconds": time.perf_counter() - t0}
+
+
+def sub_record(scene, name, local, settle, window, steps, warmup, shard_note=None, barrier=lambda: None, reduce_max=None):
+    """a secondary workload: device-timed body-steps/s + stage split (no e2e, no CPU leg)"""
+    import torch
+    stream = torch.cuda.Stream()
+    world = prepare_world(scene, local, stream, settle)
+    ms, _, _ = time_steps(world, stream, steps, warmup, window, barrier)
+    if reduce_max is not None:
+        ms = reduce_max(ms)
+    stage, acc = profile_stages(world, min(steps, window), window)
+    st = world.stats()
+    world.close()
+    torch.cuda.empty_cache()
+    rec = {"workload": name, "bodies": scene.nb, "ms_per_step": ms / steps, "body_steps_per_s": scene.nb * steps / (ms * 1e-3),
+           "settle_steps": settle, "window": window, "steps": steps, "pairs_per_step": acc["pairs"],
+           "contacts_per_step": acc["contacts"], "contacts_per_body": acc["contacts"] / max(scene.nb, 1),
+           "solver_dag_depth": acc["levels"], "stages_ms": stage, "overflow": st["overflow"]}
+    if shard_note:
+        rec["sharding"] = shard_note
+    return rec
+
+
 def main():
     args = parse()
     if args.impl == "reference":
@@ -355,8 +523,9 @@ def main():
         return
     import torch
     import torch.distributed as dist
-    from nans_projekat_b200.world import World, kernel_launches
+    from nans_projekat_b200.world import kernel_launches
     from nans_projekat_b200.scenes import Scene
+    from nans_projekat_b200 import scenes
 
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -370,101 +539,81 @@ def main():
         if world_size > 1:
             dist.barrier()
 
+    def reduce_max(x):
+        t = torch.tensor([x], device="cuda", dtype=torch.float64)
+        if world_size > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
     warmup = max(args.warmup, 3)
     scene, layers, workload_name = build_workload(args, seed=7 + rank)
     nb = scene.nb
     stream = torch.cuda.Stream()
-    world = World(scene, device=local, stream=stream.cuda_stream)
-    world.rebuild_vertices()
-    FULL = ("pos", "vel", "force", "ang", "angvel", "torque", "verts")
-    for _ in range(args.settle):        # scene preparation: let the pile come into contact
-        world.step(DT)
-    world.synchronize()
     # The measured window is steps [settle, settle + window) of the simulation, the contact-rich phase
     # of the pile.  The reference's bug-compatible solver (minus sign in the angular JMJ term, one
     # Gauss-Seidel pass) eventually blows a large pile apart, so every `window` steps
     # the world returns to the prepared state by a device-to-device snapshot restore (an episode
     # reset, RL-style).  The restore is INSIDE the timed region; it is ~0.2 GB of D2D copy per window.
-    world.snapshot()
+    world = prepare_world(scene, local, stream, args.settle)
     prepared = world.download(fields=FULL)
     window = args.window
-
-    def run_steps(n, step_fn):
-        for k in range(n):
-            if k % window == 0:
-                world.restore()
-            step_fn()
-
-    run_steps(warmup, lambda: world.step(DT))
-    world.synchronize()
 
     # ---- timed region: device-resident, CUDA events on the launching stream ----------------
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
         time.sleep(0.5)          # let nvidia-smi start sampling before the timed region
+    run_steps(world, warmup, window, lambda: world.step(DT))
+    world.synchronize()
     launches0 = kernel_launches()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier(); torch.cuda.synchronize()
     t_begin = time.time()
     e0.record(stream)
-    run_steps(args.steps, lambda: world.step(DT))
+    run_steps(world, args.steps, window, lambda: world.step(DT))
     e1.record(stream)
     torch.cuda.synchronize(); barrier()
     t_end = time.time()
     ms = e0.elapsed_time(e1)
     launches = kernel_launches() - launches0
     clocks = sampler.stop(t_begin, t_end) if rank == 0 else None
-    st1 = world.stats()          # raises on capacity overflow: a truncated step is not a valid step
-    t = torch.tensor([ms], device="cuda", dtype=torch.float64)
-    if world_size > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_max = float(t.item())
+    world.stats()          # raises on capacity overflow: a truncated step is not a valid step
+    ms_max = reduce_max(ms)
     value = nb * world_size * args.steps / (ms_max * 1e-3)
 
     # ---- per-stage pass over the same window: CUDA events between the stages ----------------
-    stage = {}
-    acc = {"pairs": 0.0, "contacts": 0.0, "levels": 0.0}
-    n_prof = min(args.steps, 2 * window)
-
-    def prof_step():
-        m = world.step_profiled(DT)
-        for k, v in m.items():
-            stage[k] = stage.get(k, 0.0) + v / n_prof
-        s_ = world.stats()
-        acc["pairs"] += s_["n_pairs"] / n_prof
-        acc["contacts"] += s_["n_contacts"] / n_prof
-        acc["levels"] += s_["solver_levels"] / n_prof
-    run_steps(n_prof, prof_step)
+    stage, acc = profile_stages(world, min(args.steps, 2 * window), window)
     pairs_acc, contacts_acc = acc["pairs"], acc["contacts"]
     peak, peak_src = load_peaks()
-    alg = {"integrate_forces": nb * BYTES["integrate_forces"],
-           "broadphase": nb * (BYTES["aabb_key"] + BYTES["radix_sort"]) + pairs_acc * BYTES["pair_emit"],
-           "narrowphase": pairs_acc * BYTES["narrowphase"],
-           "solver": contacts_acc * BYTES["solver"],
-           "integrate_velocities": nb * BYTES["integrate_velocities"]}
+    alg, per_stage = stage_roofline(stage, acc, nb, peak)
     dom = max(alg, key=lambda k: stage[k])
     ach = alg[dom] / (stage[dom] * 1e-3) / 1e9
     traffic, traffic_src, pipes = None, None, None
-    try:   # DRAM bytes per launch of the dominant kernel, from the committed `ncu --set full` capture
+    try:   # DRAM bytes per launch + pipe utilisation of the dominant kernel from the committed `ncu --set full` capture:
+        # only when the capture was taken on THIS workload (else null: a capture of another scene says nothing here)
         tj = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
-        kname = {"narrowphase": "narrowphase_world_kernel", "solver": "solve_versioned_kernel",
-                 "integrate_forces": "integrate_forces_kernel", "integrate_velocities": "integrate_velocities_kernel",
-                 "broadphase": "pair_count_kernel"}[dom]
-        traffic, traffic_src = tj["dram_bytes_per_launch"].get(kname), tj["source"] + " : " + kname
-        pipes = tj.get("pipes", {}).get(kname)
+        if tj.get("workload") == workload_name:
+            kname = {"narrowphase": "narrowphase_world_kernel", "solver": "solve_versioned_kernel",
+                     "integrate_forces": "integrate_forces_kernel", "integrate_velocities": "integrate_velocities_kernel",
+                     "broadphase": "pair_count_kernel"}[dom]
+            traffic, traffic_src = tj["dram_bytes_per_launch"].get(kname), tj["source"] + " : " + kname
+            pipes = tj.get("pipes", {}).get(kname)
     except Exception:
         pass
+    limiter = {"narrowphase": "FP32 issue slots / divergence / local-memory latency of GJK+EPA (not HBM): see pipes_ncu",
+               "solver": "dependency depth of the exact-order sweep (depth x store->poll->apply hop), not HBM",
+               "broadphase": "L2 latency of the cell-hash probes + launch count", "integrate_forces": "HBM",
+               "integrate_velocities": "HBM"}[dom]
     roofline = {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                 "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                 "share_of_step": stage[dom] / stage["step"],
+                "limited_by": limiter,
                 "pipes_ncu": pipes,   # FMA / ALU pipe and issue-slot utilisation, active lanes per instruction (same capture)
-                "per_stage": {k: {"ms": stage[k], "alg_bytes": alg[k], "gbs": alg[k] / (stage[k] * 1e-3) / 1e9,
-                                  "frac": alg[k] / (stage[k] * 1e-3) / 1e9 / peak} for k in alg},
-                "note": "stage = all kernels of that stage (CUDA events between stages on the launching stream); "
-                        "narrowphase (GJK+EPA) is FP32-latency/divergence bound and the solver is bound by the "
-                        "dependency depth of the exact-order sweep (depth x store->poll->apply hop), their HBM "
-                        "fractions are reported for completeness; pairs/s = %.3g" % (pairs_acc / (stage["narrowphase"] * 1e-3))}
+                "per_stage": per_stage,
+                "note": "`bound` names the accounting (algorithmic bytes / stage time / measured HBM copy peak, as the "
+                        "bench contract asks), `limited_by` what actually limits the dominant stage; stage = all kernels "
+                        "of that stage (CUDA events between stages on the launching stream); pairs/s = %.3g"
+                        % (pairs_acc / (stage["narrowphase"] * 1e-3))}
 
     # ---- e2e: through the public API with HOST buffers, H2D + D2H inside the timed region ----
     e2e = None
@@ -476,15 +625,12 @@ def main():
         io.force, io.torque, io.pos, io.ang = pinned((nb, 3)), pinned((nb, 3)), pinned((nb, 3)), pinned((nb, 3))
 
         def timed(step_fn):
-            run_steps(warmup, step_fn)
+            run_steps(world, warmup, window, step_fn)
             barrier(); torch.cuda.synchronize()
             t0 = time.perf_counter()
-            run_steps(args.steps, step_fn)
+            run_steps(world, args.steps, window, step_fn)
             torch.cuda.synchronize()
-            el = torch.tensor([time.perf_counter() - t0], device="cuda", dtype=torch.float64)
-            if world_size > 1:
-                dist.all_reduce(el, op=dist.ReduceOp.MAX)
-            return nb * world_size * args.steps / float(el.item())
+            return nb * world_size * args.steps / reduce_max(time.perf_counter() - t0)
 
         def e2e_step():
             world.upload_async(io, fields=("force", "torque"))  # this frame's external forces/torques
@@ -538,17 +684,23 @@ def main():
         t0 = time.perf_counter()
         run_pipe(args.steps)
         torch.cuda.synchronize()
-        elp = torch.tensor([time.perf_counter() - t0], device="cuda", dtype=torch.float64)
-        if world_size > 1:
-            dist.all_reduce(elp, op=dist.ReduceOp.MAX)
-        e2e["pipelined"] = {"value": nb * world_size * args.steps / float(elp.item()), "unit": "body-steps/s",
+        elp = reduce_max(time.perf_counter() - t0)
+        e2e["pipelined"] = {"value": nb * world_size * args.steps / elp, "unit": "body-steps/s",
                             "api": "World.upload_async(force,torque) -> World.step -> World.download_async(pos,ang) -> "
                                    "World.wait(ticket of the previous frame): same bytes per step, copies on their own "
                                    "streams, poses consumed one frame late"}
         assert np.isfinite(outs[0].pos).all() and np.isfinite(outs[1].pos).all()
 
+    single = rank == 0 and world_size == 1
+    subs = not args.no_subrecords
+    parity = None
+    if single and subs:
+        try:
+            parity = parity_in_run(world, scene, prepared)
+        except Exception as ex:   # the -m gpu tests are the gate; a missing checker must not lose the bench line
+            parity = {"checked": f"not checked ({type(ex).__name__}: {ex})"}
     cpu = None
-    if rank == 0 and world_size == 1 and not args.no_cpu_baseline and args.workload == "pile":
+    if single and not args.no_cpu_baseline and args.workload == "pile":
         state = prepared.copy()
         for f in ("scale", "mass", "moi", "st_pos", "st_ang", "st_scale", "st_mass", "st_moi"):
             getattr(state, f)[...] = getattr(scene, f)
@@ -556,31 +708,62 @@ def main():
         world.download_into(sv, ("st_verts",))
         state.st_verts[...] = sv.st_verts
         cpu = cpu_port_baseline(state, args.cpu_bodies)
+    world.close()
+    del world
+    torch.cuda.empty_cache()
 
-    c3 = run_c3(args.c3, local) if (args.c3 and rank == 0) else None
+    # ---- sub-records: the other configurations of BASELINE.json, same harness, shorter runs ----
+    extra = {}
+    if subs and args.workload == "pile":
+        if single:
+            alt_side = 250 if args.side == 100 else 100
+            alt_scene, alt_layers = build_pile(args.bodies, alt_side, seed=7)
+            extra["alt_shapes"] = [dict(sub_record(alt_scene, f"cube_pile_1M_{alt_side}x{alt_side}x{alt_layers}", local,
+                                                   80 if alt_side == 100 else 40, window, args.steps, warmup),
+                                        shape=f"{alt_side}x{alt_layers}x{alt_side}")]
+            del alt_scene
+            # steps [50, 70): the drop's contact-rich phase BEFORE the reference's one-pass solver blows it apart (from
+            # step ~60 velocities grow without bound in the oracle and on the GPU alike; by step 150 the
+            # cubes are a dispersed cloud 10^6 units wide, which is not a collision workload any more)
+            extra["c2_drop10k"] = sub_record(scenes.cube_drop(n=10000, seed=1), "cube_drop_10k (config C2)", local, 50, 20,
+                                             max(args.steps, 40), warmup)
+        # config C4: a FIXED batch of 4096 worlds x (48 cubes + 16 spheres), 4096 / N worlds per GPU, no communication
+        if 4096 % world_size == 0:
+            per = 4096 // world_size
+            c4 = scenes.batched_worlds(per, 48, 16, seed=1 + rank)
+            r = sub_record(c4, f"batched_worlds_{per}x64 per GPU (config C4: 4096 worlds over {world_size} GPU)", local, 30, 20,
+                           max(args.steps, 40), warmup, barrier=barrier, reduce_max=reduce_max,
+                           shard_note=f"4096/{world_size} worlds per GPU, strong scaling of a fixed batch, no collective")
+            r["body_steps_per_s"] = 4096 * 64 * r["steps"] / (r["ms_per_step"] * r["steps"] * 1e-3)
+            r["bodies_total"] = 4096 * 64
+            extra["c4_worlds4096"] = r
+    c3_pairs = args.c3 if args.c3 >= 0 else (16777216 if single else 0)
+    c3 = run_c3(c3_pairs, local, args.c3_check) if (c3_pairs and rank == 0 and subs) else None
     if rank == 0:
+        shape = f"{args.side}x{layers}x{args.side}"
         line = {"metric": "body-steps/s", "value": value, "unit": "body-steps/s", "n_gpus": world_size,
                 "steps": args.steps, "warmup": warmup, "ms_per_step": ms_max / args.steps,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
                 "data": "synthetic",
-                "config": {"workload": workload_name,
+                "config": {"workload": workload_name, "shape": shape,
                            "bodies_per_world": nb, "worlds": world_size, "footprint": f"{args.side}x{args.side}",
-                           "layers": layers, "spacing": 1.02, "dt": float(DT), "settle_steps": args.settle,
+                           "layers": layers, "spacing": 1.02, "jitter": 0.005, "dt": float(DT), "settle_steps": args.settle,
                            "parallelism": "1 world per GPU, no collective" if world_size > 1 else "1 world on 1 GPU",
-                           "l2": "inputs larger than L2 (>= 1 GB of world state touched per step vs 126 MB L2)",
+                           "l2": "inputs larger than L2 (>= 0.6 GB of world state touched per step vs 126 MB L2)",
                            "window": f"steps [{args.settle}, {args.settle + window}) of the simulation, restored from a "
                                      f"device snapshot every {window} steps inside the timed region",
                            "solver": "exact reference order (versioned body rows: value + version in one 128-bit row)",
                            "pairs_per_step": pairs_acc, "contacts_per_step": contacts_acc,
-                           "solver_dag_depth": acc["levels"]},
+                           "contacts_per_body": contacts_acc / nb, "solver_dag_depth": acc["levels"]},
                 "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
                 "clocks": clocks,
                 "stages_ms": stage, "narrowphase_pairs_per_s": pairs_acc / (stage["narrowphase"] * 1e-3),
+                "parity_in_run": parity,
                 "host": {"nproc": os.cpu_count()}}
+        line.update(extra)
         if c3:
             line["c3_narrowphase"] = c3
         print(json.dumps(line), flush=True)
-    world.close()
     if world_size > 1:
         dist.destroy_process_group()
 
