@@ -54,9 +54,6 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--workload", default="pile", choices=["pile", "drop10k", "worlds4096"],
                     help="pile = 1M-cube pile (BASELINE metric; default); drop10k = config C2; worlds4096 = config C4")
-    ap.add_argument("--mode", default="worlds", choices=["worlds", "slab"],
-                    help="N>1: 'worlds' = one independent world per GPU (weak scaling, no collective; default); "
-                         "'slab' = ONE world split by body-index slabs with NCCL halo exchange (strong scaling)")
     ap.add_argument("--c3", type=int, default=-1, metavar="PAIRS",
                     help="GJK+EPA microbench (config C3) on this many random pairs; -1 = 16777216 at N=1, off at N>1; 0 = off")
     ap.add_argument("--c3-check", type=int, default=1 << 20, help="pairs of C3 whose flags are checked on the CPU")
@@ -346,58 +343,57 @@ def run_c3(n_pairs, device, n_check, reps=3):
     return res
 
 
-def main_slab(args):
-    """ONE 1M-cube world over N GPUs (config C5): slab decomposition + NCCL halo exchange, exact."""
+def slab_record(args, rank, local, size, dist, reduce_max, barrier, single_ms_per_step, warmup):
+    """Config C5: ONE world of size x 1M cubes in x-slabs (100 x 100 x 100 cubes per GPU), NCCL halo exchange +
+    cross-GPU dataflow solve over NVLink peer memory (csrc/slab.cu), exact reference order.  Weak scaling of one
+    world: efficiency = ms/step of one GPU stepping 1M cubes / ms/step of N GPUs stepping N x 1M."""
     import torch
-    import torch.distributed as dist
-    from nans_projekat_b200.slab import SlabWorld, CudaEngine
-    from nans_projekat_b200.world import kernel_launches
-    rank, local, size = int(os.environ["RANK"]), int(os.environ["LOCAL_RANK"]), int(os.environ["WORLD_SIZE"])
-    torch.cuda.set_device(local)
-    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    scene, layers = build_pile(args.bodies, args.side, seed=7)
-    eng = CudaEngine(scene, rank, size, local)
-    eng.rebuild_vertices()
-    sw = SlabWorld(eng, rank, size, dist)
-    warmup = max(args.warmup, 3)
-    for _ in range(args.settle):
+    from nans_projekat_b200 import scenes
+    from nans_projekat_b200.slab import SlabWorld
+    side_x, ny, nz = 100, 100, 100
+    m = side_x * ny * nz
+    owned = scenes.cube_pile_slabs(n_slabs=size, side_x=side_x, ny=ny, nz=nz, seed=7, slab=rank)
+    halo_cap = 4 * ny * nz
+    stream = torch.cuda.Stream()
+    sw = SlabWorld(owned, rank, size, dist, local, gid_base=rank * m, halo_cap=halo_cap, capacity=m + halo_cap,
+                   stream=stream.cuda_stream)
+    sw.rebuild_vertices()
+    settle, window = 80, args.window
+    for _ in range(settle):
         sw.step(DT)
-    eng.set_ghosts(0)
-    eng.world.snapshot()
+    sw.world.synchronize()
+    sw.world.snapshot()
 
-    def run_steps(n):
+    def run(n):
         for k in range(n):
-            if k % args.window == 0:
-                eng.world.restore()
+            if k % window == 0:
+                sw.world.restore()
             sw.step(DT)
-    run_steps(warmup)
-    torch.cuda.synchronize(); dist.barrier()
-    launches0 = kernel_launches()
+    run(warmup)
+    torch.cuda.synchronize(); barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(eng.stream)
-    run_steps(args.steps)
-    e1.record(eng.stream)
-    torch.cuda.synchronize(); dist.barrier()
-    t = torch.tensor([e0.elapsed_time(e1)], device="cuda", dtype=torch.float64)
-    dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    st = eng.world.stats()
+    e0.record(stream)
+    run(args.steps)
+    e1.record(stream)
+    torch.cuda.synchronize(); barrier()
+    ms = reduce_max(e0.elapsed_time(e1)) / args.steps
+    st = sw.status()            # raises if the exchange pattern was violated (the world would not be exact)
+    ws = sw.world.stats()
     info = [None] * size
-    dist.all_gather_object(info, {"owned": eng.n_owned, "ghosts": sw.n_ghosts, "halo_bytes": sw.halo_bytes,
-                                  "contacts": st["n_contacts"], "pairs": st["n_pairs"]})
-    if rank == 0:
-        ms = float(t.item())
-        line = {"metric": "body-steps/s", "value": scene.n_cubes * args.steps / (ms * 1e-3), "unit": "body-steps/s",
-                "n_gpus": size, "steps": args.steps, "warmup": warmup, "ms_per_step": ms / args.steps,
-                "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": {"workload": "cube_pile_1M_one_world" if scene.n_cubes == 1_000_000 else f"cube_pile_{scene.n_cubes}_one_world",
-                           "bodies": scene.n_cubes, "footprint": f"{args.side}x{args.side}", "layers": layers,
-                           "parallelism": f"{size} slabs by body index (layers), NCCL halo exchange, exact-order solve "
-                                          f"pipelined over ranks", "settle_steps": args.settle, "window": args.window,
-                           "l2": "inputs larger than L2", "per_rank": info},
-                "gpu_launches": int(kernel_launches() - launches0), "roofline": None, "cpu_baseline": None, "e2e": None}
-        print(json.dumps(line), flush=True)
-    eng.close()
-    dist.destroy_process_group()
+    dist.all_gather_object(info, {"ghosts": st["ghosts"], "contacts": ws["n_contacts"], "pairs": ws["n_pairs"],
+                                  "solver_levels": ws["solver_levels"]})
+    sw.close()
+    torch.cuda.empty_cache()
+    return {"workload": f"cube_pile_{size}M_one_world ({size * side_x}x{ny}x{nz} cubes in {size} x-slabs, config C5)",
+            "bodies": size * m, "n_gpus": size, "ms_per_step": ms, "body_steps_per_s": size * m / (ms * 1e-3),
+            "scaling": "weak (one world grows with the GPU count: 1M cubes per GPU)",
+            "efficiency_vs_one_gpu_1M": (single_ms_per_step / ms) if single_ms_per_step else None,
+            "one_gpu_1M_ms_per_step": single_ms_per_step,
+            "halo_message_bytes": st["halo_message_bytes"], "per_rank": info, "settle_steps": settle, "window": window,
+            "exchange": "per step: ncclAllGather of the slab boxes (32 B/rank), one fixed-capacity ncclSend/ncclRecv of halo "
+                        "bodies to the lower / from the upper neighbour, boundary velocities handed to their owner by peer "
+                        "stores over NVLink from inside the solve kernel; no host round trip; exact (bit-identical to one "
+                        "GPU: tools/slab_check.py, profiles/)"}
 
 
 # --------------------------------------------------------------------------------------- our arm
@@ -517,9 +513,6 @@ def main():
     args = parse()
     if args.impl == "reference":
         run_reference(args)
-        return
-    if args.mode == "slab" and int(os.environ.get("WORLD_SIZE", "1")) > 1:
-        main_slab(args)
         return
     import torch
     import torch.distributed as dist
@@ -693,6 +686,38 @@ def main():
 
     single = rank == 0 and world_size == 1
     subs = not args.no_subrecords
+    # ---- throughput solver mode: the same Gauss-Seidel pass in a shuffled sweep order (NOT the reference's results) ----
+    solver_modes = None
+    if subs:
+        def vel_after_one_step():
+            world.restore(); world.step(DT)
+            d_ = world.download(fields=("vel", "angvel"))
+            return d_.vel.astype(np.float64), d_.angvel.astype(np.float64)
+        v_ex, w_ex = vel_after_one_step()
+        world.set_solver("shuffled")
+        v_sh, w_sh = vel_after_one_step()
+        ms_sh, _, _ = time_steps(world, stream, args.steps, warmup, window, barrier)
+        ms_sh = reduce_max(ms_sh)
+        stage_sh, acc_sh = profile_stages(world, min(args.steps, window), window)
+        world.set_solver("exact")
+        world.restore()
+        rel = lambda a, b: np.abs(a - b) / np.maximum(np.abs(b), 1.0)
+        dv, dw = rel(v_sh, v_ex), rel(w_sh, w_ex)
+        touched = (dv.max(1) > 0) | (dw.max(1) > 0)
+        solver_modes = {
+            "exact": {"ms_per_step": ms_max / args.steps, "solver_ms": stage["solver"], "dag_depth": acc["levels"],
+                      "results": "bit-identical to the reference's sequential sweep (parity tests)"},
+            "shuffled": {"ms_per_step": ms_sh / args.steps, "solver_ms": stage_sh["solver"], "dag_depth": acc_sh["levels"],
+                         "body_steps_per_s": nb * world_size * args.steps / (ms_sh * 1e-3),
+                         "results": "one Gauss-Seidel pass of the same Constraint in a fixed pseudo-random order "
+                                    "(bit-identical to the oracle sweeping the list in that order: tests/test_solver_gpu.py); "
+                                    "NOT the reference's list order",
+                         "deviation_from_exact_after_one_step": {
+                             "max_rel_vel": float(dv.max()), "max_rel_angvel": float(dw.max()),
+                             "mean_rel_vel": float(dv.mean()), "bodies_differing_frac": float(touched.mean()),
+                             "how": "|x_shuffled - x_exact| / max(|x_exact|, 1), same prepared state, one step"}},
+            "speedup_step": (ms_max / args.steps) / (ms_sh / args.steps),
+            "headline_uses": "exact"}
     parity = None
     if single and subs:
         try:
@@ -737,6 +762,13 @@ def main():
             r["body_steps_per_s"] = 4096 * 64 * r["steps"] / (r["ms_per_step"] * r["steps"] * 1e-3)
             r["bodies_total"] = 4096 * 64
             extra["c4_worlds4096"] = r
+    if world_size > 1 and subs and args.workload == "pile":
+        try:
+            extra["slab"] = slab_record(args, rank, local, world_size, dist, reduce_max, barrier,
+                                        ms_max / args.steps if args.side == 100 else None, warmup)
+        except Exception as ex:
+            if world_size > 1:
+                raise               # a failed collective would hang the other ranks: fail the whole job loudly
     c3_pairs = args.c3 if args.c3 >= 0 else (16777216 if single else 0)
     c3 = run_c3(c3_pairs, local, args.c3_check) if (c3_pairs and rank == 0 and subs) else None
     if rank == 0:
@@ -758,7 +790,7 @@ def main():
                 "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
                 "clocks": clocks,
                 "stages_ms": stage, "narrowphase_pairs_per_s": pairs_acc / (stage["narrowphase"] * 1e-3),
-                "parity_in_run": parity,
+                "parity_in_run": parity, "solver_modes": solver_modes,
                 "host": {"nproc": os.cpu_count()}}
         line.update(extra)
         if c3:

@@ -126,18 +126,37 @@ int nans_world_wait(nans_world *w, int32_t ticket);   /* ticket < 0: everything 
 int nans_world_snapshot(nans_world *w);
 int nans_world_restore(nans_world *w);
 
-/* ---- one world over several GPUs, split by contiguous body-index ranges (cube-only worlds).
- * No reference counterpart (the reference is one process); the multi-GPU result is bit-identical to
- * the single-GPU one.  Rows [0, n_owned) are owned, rows [n_owned, n_owned+n_ghosts) are copies of
- * higher-rank bodies; buffers are DEVICE pointers (the exchange is NCCL, driven by the host):
- * halo record = 160 B/body (pos, vel, angvel, 8 vertices, global id), velocity record = 32 B/body. */
-int nans_world_set_partition(nans_world *w, int32_t n_owned, int32_t n_ghosts);
-int nans_world_bounds(nans_world *w, float out_lo_hi[6]);           /* AABB of the owned bodies (synchronises) */
-int nans_slab_pack_halo(nans_world *w, const float box_lo_hi[6], int32_t gid_base, void *d_out, int32_t cap,
-                        int32_t list_offset, int32_t *count);         /* owned bodies reaching into the box, in row order */
-int nans_slab_unpack_halo(nans_world *w, const void *d_in, int32_t count, int32_t row0);
-int nans_slab_pack_ghost_vel(nans_world *w, int32_t row0, int32_t count, void *d_out);
-int nans_slab_unpack_owned_vel(nans_world *w, int32_t list_offset, int32_t count, const void *d_in);
+/* ---- ONE world over several GPUs of a box (config C5): spatial slabs, one process (or thread) per GPU.
+ * No reference counterpart (the reference is one process capped at 16 cubes, code/nans.h:52-53); the decomposed
+ * world is bit-identical to the same world on one GPU.  Bodies are numbered slab-major: rank r owns the global index
+ * range [gid_base, gid_base + n_owned), laid out by the scene as a slab along x; rows [n_owned, n_owned + halo_cap)
+ * of its world receive, every step, copies of the upper neighbour's bodies that reach into its bounding box.
+ * Exchange: NCCL (all-gather of the slab boxes, fixed-capacity halo send/recv, all on the world's stream, no host
+ * round trip), and the solve runs as ONE dataflow across the GPUs through peer stores over NVLink (csrc/slab.cu,
+ * csrc/solver.cu).  Every rank must create its world with the SAME capacities (cube-only, n_cubes >= n_owned +
+ * halo_cap, library-owned arena).  Set-up, with the two blobs carried between the ranks by the host
+ * (torch.distributed, MPI, a file: INTEGRATION.md):
+ *   rank 0: nans_slab_unique_id(id)            -> broadcast id (128 bytes)
+ *   all:    nans_slab_init(w, rank, n, id, ...) ; nans_slab_ipc_handle(w, blob) -> all-gather the blobs (128 bytes each)
+ *   all:    nans_slab_connect(w, blobs)        ; then nans_slab_step(w, dt) per frame. */
+int nans_slab_unique_id(void *out128);
+int nans_slab_init(nans_world *w, int32_t rank, int32_t nranks, const void *unique_id128, int32_t n_owned,
+                   int32_t gid_base, int32_t halo_cap);
+int nans_slab_ipc_handle(nans_world *w, void *out128);
+int nans_slab_connect(nans_world *w, const void *blobs /* [nranks][128] */);
+int nans_slab_step(nans_world *w, float dt);   /* the step of code/nans.cpp:1758-1762 on this rank's share; asynchronous */
+/* synchronises; err_bits (sticky): 1 = halo larger than halo_cap, 2 = a body reaches into a rank other than the lower
+ * neighbour (either makes the call return NANS_ERR_STATE: the world is no longer exact); live_rows = owned + ghosts */
+int nans_slab_status(nans_world *w, int32_t *err_bits, int32_t *live_rows, int64_t *halo_bytes_per_message);
+int nans_slab_row_gids(nans_world *w, int32_t *out, int32_t cap, int32_t *count);   /* global ids of the live rows */
+
+/* Sweep order of SolveConstraints (code/nans.cpp:1539-1548).  EXACT (default): the reference's list order, results
+ * bit-identical to it.  SHUFFLED: the same single Gauss-Seidel pass in a fixed pseudo-random order, whose dependency
+ * graph is ~10 levels deep instead of ~100 (a greedy graph colouring in random order): faster, deterministic,
+ * atomics-free, but NOT the reference's results wherever contacts share bodies (DESIGN.md states the measured
+ * deviation).  Not available for slab-partitioned worlds. */
+enum { NANS_SOLVER_EXACT = 0, NANS_SOLVER_SHUFFLED = 1 };
+int nans_world_set_solver(nans_world *w, int32_t mode);
 
 /* ---- the four stages, one entry per reference function (asynchronous on the world's stream) */
 int nans_integrate_forces(nans_world *w, float dt);     /* IntegrateForces     code/nans.cpp:975  */

@@ -52,17 +52,9 @@ struct Staging {            // per-field upload/download slots (device), carved 
     int32_t *wid;           // [nb]
 };
 
-struct SlabBufs {
-    int32_t *sent_rows;      // [nb] rows of the halo lists sent to lower ranks, concatenated
-    float *bounds_scratch;   // [6 * 1024] partial bounds
-    float *bounds;           // [8] lo.xyz hi.xyz
-    int32_t *count;          // [8] device-side counts
-};
-
 struct Layout {
     DeviceWorld d;
     Staging st;
-    SlabBufs slab;
     float4 *snap;
     size_t bytes;
 };
@@ -89,10 +81,8 @@ static Layout carve(const nans_world_desc &desc, char *base)
     d.world_id = b.take<int32_t>(nb);
     d.gid = b.take<int32_t>(nb);
     d.n_owned = d.nb;
-    L.slab.sent_rows = b.take<int32_t>(nb);
-    L.slab.bounds_scratch = b.take<float>(6 * 1024);
-    L.slab.bounds = b.take<float>(8);
-    L.slab.count = b.take<int32_t>(8);
+    d.sent_mark = b.take<int32_t>(nb);
+    d.ghost_owner_row = b.take<int32_t>(nb);
     d.st_pos = b.take<float4>(ns); d.st_ang = b.take<float4>(ns); d.st_scale = b.take<float4>(ns);
     d.st_verts = b.take<float4>(6 * ns); d.st_aabb = b.take<float4>(2 * ns);
     d.aabb_lo = b.take<float4>(nb); d.aabb_hi = b.take<float4>(nb);
@@ -112,9 +102,9 @@ static Layout carve(const nans_world_desc &desc, char *base)
     d.c_pa = b.take<float4>(mc); d.c_pb = b.take<float4>(mc); d.c_n = b.take<float4>(mc);
     d.deg = b.take<uint32_t>(nb + 1); d.cursor = b.take<uint32_t>(nb);
     d.inc = b.take<int32_t>(2 * mc);
-    d.succ_a = b.take<int32_t>(mc); d.succ_b = b.take<int32_t>(mc); d.indeg = b.take<int32_t>(mc);
-    for (int k = 0; k < 3; ++k) d.frontier[k] = b.take<int32_t>(mc);
-    d.crec = b.take<float4>(11 * mc);
+    d.succ_a = b.take<int32_t>(mc); d.succ_b = b.take<int32_t>(mc); d.run_flag = b.take<int32_t>(mc);
+    d.run_start = b.take<int32_t>(mc); d.trace_level = b.take<int32_t>(mc);
+    d.row_v = b.take<float4>(nb); d.row_w = b.take<float4>(nb);
     size_t scan_n = mp + 1;
     if (5 * nb + 1 > scan_n) scan_n = 5 * nb + 1;
     if (256 * radix_blocks > scan_n) scan_n = 256 * radix_blocks;
@@ -143,7 +133,6 @@ struct IoPipe {               // pipelined host I/O: copies on their own streams
 struct WorldImpl : World {
     IoPipe io;
     Staging st;
-    SlabBufs slab;
     int32_t cap_nb;          // capacity of the body arrays (slab mode varies nb below it)
     float4 *snap;
     bool has_world_id;
@@ -259,7 +248,6 @@ int nans_world_create(const nans_world_desc *desc, nans_world **out)
     Layout L = carve(*desc, (char *)w->arena);
     w->d = L.d;
     w->st = L.st;
-    w->slab = L.slab;
     w->cap_nb = L.d.nb;
     w->snap = L.snap;
     w->d_world_id_storage = L.d.world_id;
@@ -280,6 +268,7 @@ void nans_world_destroy(nans_world *h)
     WorldImpl *w = impl(h);
     cudaSetDevice(w->device);
     cudaStreamSynchronize(w->stream);
+    slab_destroy(w);
     if (w->graph_exec) cudaGraphExecDestroy(w->graph_exec);
     if (w->graph_exec_b) cudaGraphExecDestroy(w->graph_exec_b);
     if (w->io.init) {
@@ -604,78 +593,6 @@ static int snapshot_copy(WorldImpl *w, bool restore)
 int nans_world_snapshot(nans_world *h) { return h ? snapshot_copy(impl(h), false) : fail(NANS_ERR_ARG, "null world"); }
 int nans_world_restore(nans_world *h) { return h ? snapshot_copy(impl(h), true) : fail(NANS_ERR_ARG, "null world"); }
 
-// ---- slab decomposition (one world over several GPUs by body-index ranges; see slab.cu) ----------
-int nans_world_set_partition(nans_world *h, int32_t n_owned, int32_t n_ghosts)
-{
-    if (!h) return fail(NANS_ERR_ARG, "null world");
-    WorldImpl *w = impl(h);
-    if (w->d.n_spheres != 0) return fail(NANS_ERR_ARG, "slab mode supports cube-only worlds");
-    if (n_owned < 0 || n_ghosts < 0 || n_owned + n_ghosts > w->cap_nb)
-        return fail(NANS_ERR_CAPACITY, "nans_world_set_partition: owned + ghosts exceed the world's capacity");
-    if (w->d.n_owned != n_owned || w->d.nb != n_owned + n_ghosts) graph_invalidate(w);
-    w->d.n_owned = n_owned;
-    w->d.nb = n_owned + n_ghosts;
-    w->d.n_cubes = w->d.nb;
-    return NANS_OK;
-}
-
-int nans_world_bounds(nans_world *h, float out_lo_hi[6])
-{
-    if (!h || !out_lo_hi) return fail(NANS_ERR_ARG, "null argument");
-    WorldImpl *w = impl(h);
-    NANS_CUDA(cudaSetDevice(w->device));
-    int rc = launch_aabb_only(w);
-    if (rc) return rc;
-    rc = slab_bounds(w, w->slab.bounds_scratch, w->slab.bounds);
-    if (rc) return rc;
-    NANS_CUDA(cudaMemcpyAsync(out_lo_hi, w->slab.bounds, sizeof(float) * 6, cudaMemcpyDeviceToHost, w->stream));
-    NANS_CUDA(cudaStreamSynchronize(w->stream));
-    return NANS_OK;
-}
-
-int nans_slab_pack_halo(nans_world *h, const float box_lo_hi[6], int32_t gid_base, void *d_out, int32_t cap,
-                        int32_t list_offset, int32_t *count)
-{
-    if (!h || !box_lo_hi || !d_out || !count) return fail(NANS_ERR_ARG, "null argument");
-    WorldImpl *w = impl(h);
-    { const int frc = flush_deferred(w); if (frc) return frc; }
-    NANS_CUDA(cudaSetDevice(w->device));
-    if (list_offset < 0 || list_offset > w->cap_nb) return fail(NANS_ERR_ARG, "bad list offset");
-    const int room = w->cap_nb - list_offset;
-    int rc = slab_pack_halo(w, box_lo_hi, gid_base, (float4 *)d_out, w->slab.sent_rows + list_offset,
-                            cap < room ? cap : room, w->slab.count);
-    if (rc) return rc;
-    NANS_CUDA(cudaMemcpyAsync(count, w->slab.count, sizeof(int32_t), cudaMemcpyDeviceToHost, w->stream));
-    NANS_CUDA(cudaStreamSynchronize(w->stream));
-    if (*count > cap || *count > room) return fail(NANS_ERR_CAPACITY, "nans_slab_pack_halo: halo buffer too small");
-    return NANS_OK;
-}
-
-int nans_slab_unpack_halo(nans_world *h, const void *d_in, int32_t count, int32_t row0)
-{
-    if (!h) return fail(NANS_ERR_ARG, "null world");
-    WorldImpl *w = impl(h);
-    { const int frc = flush_deferred(w); if (frc) return frc; }
-    NANS_CUDA(cudaSetDevice(w->device));
-    if (row0 < 0 || count < 0 || row0 + count > w->cap_nb) return fail(NANS_ERR_CAPACITY, "ghost rows exceed capacity");
-    return slab_unpack_halo(w, (const float4 *)d_in, count, row0, w->d.gid);
-}
-
-int nans_slab_pack_ghost_vel(nans_world *h, int32_t row0, int32_t count, void *d_out)
-{
-    if (!h) return fail(NANS_ERR_ARG, "null world");
-    NANS_CUDA(cudaSetDevice(impl(h)->device));
-    return slab_pack_ghost_vel(impl(h), row0, count, (float4 *)d_out);
-}
-
-int nans_slab_unpack_owned_vel(nans_world *h, int32_t list_offset, int32_t count, const void *d_in)
-{
-    if (!h) return fail(NANS_ERR_ARG, "null world");
-    WorldImpl *w = impl(h);
-    NANS_CUDA(cudaSetDevice(w->device));
-    return slab_unpack_owned_vel(w, w->slab.sent_rows + list_offset, count, (const float4 *)d_in);
-}
-
 // ---- stages ------------------------------------------------------------------------------------
 int nans_integrate_forces(nans_world *h, float dt)
 {
@@ -707,6 +624,17 @@ int nans_solve_constraints(nans_world *h, float dt)
     if (!w->have_contacts) return fail(NANS_ERR_STATE, "nans_solve_constraints: no contact list (call detect or set_contacts)");
     NANS_CUDA(cudaSetDevice(w->device));
     return launch_solver(w, dt);
+}
+
+int nans_world_set_solver(nans_world *h, int32_t mode)
+{
+    if (!h) return fail(NANS_ERR_ARG, "null world");
+    if (mode != NANS_SOLVER_EXACT && mode != NANS_SOLVER_SHUFFLED) return fail(NANS_ERR_ARG, "nans_world_set_solver: unknown mode");
+    WorldImpl *w = impl(h);
+    if (mode == NANS_SOLVER_SHUFFLED && w->slab) return fail(NANS_ERR_STATE, "a slab-partitioned world runs the exact order only");
+    if (w->solver_mode != mode) graph_invalidate(w);
+    w->solver_mode = mode;
+    return NANS_OK;
 }
 
 int nans_integrate_velocities(nans_world *h, float dt)
@@ -950,7 +878,7 @@ int nans_debug_solver_trace(nans_world *h, uint64_t *times, int32_t *levels, int
     NANS_CUDA(cudaSetDevice(w->device));
     NANS_CUDA(cudaStreamSynchronize(w->stream));
     if (times) NANS_CUDA(cudaMemcpy(times, w->d.pair_out, sizeof(uint64_t) * 4 * cap, cudaMemcpyDeviceToHost));   // 4 slots per contact
-    if (levels) NANS_CUDA(cudaMemcpy(levels, w->d.frontier[1], sizeof(int32_t) * cap, cudaMemcpyDeviceToHost));
+    if (levels) NANS_CUDA(cudaMemcpy(levels, w->d.trace_level, sizeof(int32_t) * cap, cudaMemcpyDeviceToHost));
     return NANS_OK;
 }
 

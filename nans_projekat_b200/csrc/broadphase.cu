@@ -110,7 +110,7 @@ __global__ void __launch_bounds__(256) aabb_kernel(DeviceWorld w)
     }
     float ext = 0.f;
     float ctr[3] = {FLT_MAX, FLT_MAX, FLT_MAX};
-    if (i < w.nb) {
+    if (i < live_nb(w)) {
         float lo[3], hi[3];
         if (i < w.n_cubes) {
             box_aabb(w.verts + 6 * (size_t)i, lo, hi);
@@ -167,7 +167,7 @@ __global__ void __launch_bounds__(256) aabb_kernel(DeviceWorld w)
 __global__ void __launch_bounds__(256) key_kernel(DeviceWorld w)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= w.nb) return;
+    if (i >= live_nb(w)) return;
     float cell = __uint_as_float((unsigned int)w.counters->pad[2]) * 1.0001f + 1e-4f;
     if (!isfinite(cell)) cell = w.cell_size;             // overflowed vertices: static bound (box diagonal)
     cell = fmaxf(cell, 0.05f);
@@ -224,9 +224,11 @@ constexpr int kRadixTile = kRadixThreads * kRadixItems;  // 4096 keys per block
 
 __global__ void __launch_bounds__(kRadixThreads) radix_hist_kernel(const uint32_t *__restrict__ keys, int n,
                                                                    int shift, uint32_t *__restrict__ hist,
-                                                                   int n_blocks, const int32_t *__restrict__ max_key)
+                                                                   int n_blocks, const int32_t *__restrict__ max_key,
+                                                                   const int32_t *__restrict__ live)
 {
     if (shift && ((uint32_t)*max_key >> shift) == 0u) return;   // nothing but zero digits: pass skipped
+    if (live) n = *live;
     __shared__ uint32_t h[256];
     h[threadIdx.x] = 0;
     __syncthreads();
@@ -243,9 +245,11 @@ __global__ void __launch_bounds__(kRadixThreads) radix_hist_kernel(const uint32_
 __global__ void __launch_bounds__(kRadixThreads) radix_scatter_kernel(
     const uint32_t *__restrict__ keys_in, const uint32_t *__restrict__ vals_in,
     uint32_t *__restrict__ keys_out, uint32_t *__restrict__ vals_out, int n, int shift,
-    const uint32_t *__restrict__ hist_scanned, int n_blocks, const int32_t *__restrict__ max_key)
+    const uint32_t *__restrict__ hist_scanned, int n_blocks, const int32_t *__restrict__ max_key,
+    const int32_t *__restrict__ live)
 {
     if (shift && ((uint32_t)*max_key >> shift) == 0u) return;
+    if (live) n = *live;
     __shared__ uint32_t base_off[256];            // running global offset per digit for this block
     __shared__ uint32_t warp_cnt[kRadixThreads / 32][256];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -293,7 +297,8 @@ __global__ void __launch_bounds__(kRadixThreads) radix_scatter_kernel(
 __global__ void __launch_bounds__(256) gather_sorted_kernel(DeviceWorld w)
 {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= w.nb) return;
+    const int nb = live_nb(w);
+    if (t >= nb) return;
     const int fb = sorted_buf(w);
     const uint32_t *__restrict__ keys = w.key[fb];
     const uint32_t *__restrict__ vals = w.val[fb];
@@ -307,7 +312,7 @@ __global__ void __launch_bounds__(256) gather_sorted_kernel(DeviceWorld w)
     // cell table: heads write start, tails write end (both find-or-insert, so no ordering race)
     const uint32_t key = keys[t];
     const bool head = (t == 0) || (keys[t - 1] != key);
-    const bool tail = (t == w.nb - 1) || (keys[t + 1] != key);
+    const bool tail = (t == nb - 1) || (keys[t + 1] != key);
     if (head || tail) {
         uint32_t h = key * 0x9E3779B1u;
         uint32_t slot = (h ^ (h >> 15)) & w.cell_mask;
@@ -416,7 +421,8 @@ constexpr int kPairSlots = 24;
 __global__ void __launch_bounds__(128, NANS_PC_MINBLOCKS) pair_count_kernel(DeviceWorld w)
 {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= w.nb) return;
+    const int nb_live = live_nb(w);
+    if (t >= nb_live) return;
     const int fb = sorted_buf(w);
     const uint32_t *__restrict__ keys = w.key[fb];
     uint32_t *__restrict__ fill = w.key[fb ^ 1];
@@ -464,7 +470,7 @@ __global__ void __launch_bounds__(128, NANS_PC_MINBLOCKS) pair_count_kernel(Devi
     };
 
     // the rest of the own cell
-    for (uint32_t u = (uint32_t)t + 1; u < (uint32_t)w.nb && keys[u] == key; ++u) visit(u);
+    for (uint32_t u = (uint32_t)t + 1; u < (uint32_t)nb_live && keys[u] == key; ++u) visit(u);
     // the 13 cells after it in (z, y, x) order.  Neighbour keys by arithmetic on the interleaved key itself
     // (x lives in bits 2, 5, ..., y in 1, 4, ..., z in 0, 3, ...): +1 on a field = add its lowest bit with the
     // other fields' bits set so the carry runs through them, -1 = subtract with them cleared; a field of all
@@ -533,7 +539,7 @@ __global__ void __launch_bounds__(128, NANS_PC_MINBLOCKS) pair_count_kernel(Devi
 __global__ void __launch_bounds__(128) pair_emit_kernel(DeviceWorld w)
 {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= w.nb) return;
+    if (t >= live_nb(w)) return;
     const uint32_t *__restrict__ keys = w.key[sorted_buf(w)];
     const float4 alo = w.sbox[2 * (size_t)t], ahi = w.sbox[2 * (size_t)t + 1];
     const int row = __float_as_int(alo.w);
@@ -621,14 +627,14 @@ int launch_broadphase(World *w)
     NANS_LAUNCH_CHECK();
     for (int pass = 0; pass < 4; ++pass) {
         const int src = pass & 1, dst = src ^ 1;
-        radix_hist_kernel<<<n_blocks, kRadixThreads, 0, s>>>(d.key[src], nb, pass * 8, d.radix_hist, n_blocks, max_key);
+        radix_hist_kernel<<<n_blocks, kRadixThreads, 0, s>>>(d.key[src], nb, pass * 8, d.radix_hist, n_blocks, max_key, d.live);
         NANS_LAUNCH_CHECK();
         int rc = pass == 0 ? exclusive_scan_u32(d.radix_hist, d.radix_hist, 256 * n_blocks, d.scan_block, s)
                            : exclusive_scan_u32_dn(d.radix_hist, d.radix_hist, 256 * n_blocks,
                                                    &d.counters->pad[kPassLen + pass - 1], 0, d.scan_block, s);
         if (rc) return rc;
         radix_scatter_kernel<<<n_blocks, kRadixThreads, 0, s>>>(d.key[src], d.val[src], d.key[dst], d.val[dst],
-                                                                nb, pass * 8, d.radix_hist, n_blocks, max_key);
+                                                                nb, pass * 8, d.radix_hist, n_blocks, max_key, d.live);
         NANS_LAUNCH_CHECK();
     }
     NANS_CUDA(cudaMemsetAsync(d.cell_tab, 0xff, sizeof(uint4) * ((size_t)d.cell_mask + 1), s));

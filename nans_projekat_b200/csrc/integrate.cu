@@ -18,7 +18,7 @@ namespace nans {
 __global__ void __launch_bounds__(256) integrate_forces_kernel(DeviceWorld w, float dt)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= w.nb) return;
+    if (i >= w.n_owned) return;      // == nb unless the world is one rank's slab (ghost rows belong to their owner)
     const float4 p = w.pos[i];      // w = Mass
     float4 v = w.vel[i];            // w = 1/Mass
     float4 a = w.angvel[i];         // w = 1/MOI
@@ -42,7 +42,7 @@ __device__ __forceinline__ void store_verts(float4 *dst, const float v[24])
 __global__ void __launch_bounds__(128) integrate_velocities_kernel(DeviceWorld w, float dt)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= w.nb) return;
+    if (i >= w.n_owned) return;
     float4 p = w.pos[i];
     float4 a = w.ang[i];
     const float4 v = w.vel[i];

@@ -28,13 +28,17 @@ struct Counters {
     int32_t solver_levels;
     int32_t overflow;
     int32_t max_epa_faces;
-    int32_t frontier_n[3];   // solver frontier sizes (level L reads L%3, fills (L+1)%3, clears (L+2)%3)
-    int32_t pad[11];         // [0] narrowphase work counter, [1] solver abort flag, [2] max AABB extent bits,
+    int32_t frontier_n[3];   // solver: [0] sweep tickets issued, [1] number of runs
+    int32_t pad[11];         // [0] narrowphase work counter, [1] solver abort flag (watchdog), [2] max AABB extent bits,
                              // [3] largest Morton key, [4..6] histogram length of sort passes 1..3 (0 = skipped),
-                             // [7..9] smallest AABB centre per axis (order-encoded, complemented: 0 = none yet)
+                             // [7..9] smallest AABB centre per axis (order-encoded, complemented: 0 = none yet),
+                             // [10] slab error bits (SLAB_ERR_*)
 };
 
 constexpr int kMaxKey = 3, kPassLen = 4, kMinCentre = 7;   // Counters::pad slots used by the broadphase
+constexpr int kSlabErr = 10;                               // Counters::pad slot of the slab error bits
+enum { SLAB_ERR_HALO_CAP = 1,      // more halo bodies than the fixed-capacity message holds
+       SLAB_ERR_NOT_ADJACENT = 2 };// an owned body reaches into the box of a rank other than the lower neighbour
 
 // All pointers are DEVICE pointers into the arena.
 struct DeviceWorld {
@@ -81,10 +85,16 @@ struct DeviceWorld {
     uint32_t *deg;                      // [nb + 1] incidence counts -> offsets
     uint32_t *cursor;                   // [nb]
     int32_t *inc;                       // [2 * max_contacts] contact ids grouped by body
-    int32_t *succ_a, *succ_b;           // [max_contacts] next contact touching body A / B (-1 none)
-    int32_t *indeg;                     // [max_contacts]
-    float4 *crec;                       // [11 * max_contacts] velocity-independent part of each Constraint
-    int32_t *frontier[3];               // [max_contacts] each
+    int32_t *succ_a, *succ_b;           // [max_contacts] the contact's position in body A's / B's contact sequence
+    int32_t *run_flag;                  // [max_contacts] 1 where a run of contacts on the same body A starts
+    int32_t *run_start;                 // [max_contacts] first contact of every run
+    int32_t *trace_level;               // [max_contacts] DAG level per contact (NANS_SOLVER_TRACE only)
+    float4 *row_v, *row_w;              // [nb] versioned rows of the solve: (V.xyz, version), (W.xyz, version | level << 20)
+    // --- one world over several GPUs (slab.cu); all null / unused otherwise
+    const int32_t *live;                // device-side count of live body rows (owned + this step's ghosts); null = nb
+    int32_t *sent_mark;                 // [nb] 1 = the row went to the lower neighbour this step (released remotely)
+    int32_t *ghost_owner_row;           // [nb] a ghost row's row index on its owner rank
+    float4 *peer_row_v, *peer_row_w;    // the UPPER neighbour's row_v / row_w (peer memory over NVLink)
     // --- scan scratch
     uint32_t *scan_block;               // block sums
     Counters *counters;
@@ -100,6 +110,8 @@ struct World {
     cudaStream_t stream;
     bool owns_stream;
     bool have_contacts;
+    int solver_mode;            // NANS_SOLVER_EXACT / NANS_SOLVER_SHUFFLED
+    void *slab;                 // SlabState (slab.cu) when the world is one rank's share of a larger world
     // whole-step CUDA graph (captured on the 2nd step with an unchanged dt; any change of the launch
     // parameters -- body counts, cell size, world ids -- invalidates it)
     cudaGraphExec_t graph_exec;     // detection (broadphase, narrowphase, contact list)
@@ -128,6 +140,9 @@ extern unsigned long long g_launches;
 #define NANS_LAUNCH_CHECK()                                                                  \
     do { ++nans::g_launches; NANS_CUDA(cudaGetLastError()); } while (0)
 
+// live body rows: everything a kernel of the detection phase may touch (slab mode: owned + received ghosts)
+__device__ __forceinline__ int live_nb(const DeviceWorld &w) { return w.live ? *w.live : w.nb; }
+
 inline int div_up(int a, int b) { return (a + b - 1) / b; }
 inline int div_up_sz(size_t a, size_t b) { return (int)((a + b - 1) / b); }
 
@@ -141,12 +156,7 @@ int launch_contacts(World *w);
 int launch_solver(World *w, float dt);
 int solver_accum_fallbacks(World *w, int32_t *out);
 int launch_aabb_only(World *w);
-int slab_bounds(World *w, float *scratch, float *out6_dev);
-int slab_pack_halo(World *w, const float box[6], int gid_base, float4 *out, int32_t *sent_rows, int cap,
-                   int32_t *count_dev);
-int slab_unpack_halo(World *w, const float4 *in, int count, int row0, int32_t *gid);
-int slab_pack_ghost_vel(World *w, int row0, int count, float4 *out);
-int slab_unpack_owned_vel(World *w, const int32_t *rows, int count, const float4 *in);
+void slab_destroy(World *w);
 int exclusive_scan_u32(const uint32_t *in, uint32_t *out, int n, uint32_t *block_scratch, cudaStream_t s);
 int exclusive_scan_u32_dn(const uint32_t *in, uint32_t *out, int cap_n, const int32_t *d_n, int extra,
                           uint32_t *block_scratch, cudaStream_t s);

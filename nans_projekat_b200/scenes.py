@@ -157,6 +157,29 @@ def cube_pile(n_side=100, seed=7, spacing=1.02, jitter=0.005, n=None, layers=Non
     return s
 
 
+def cube_pile_slabs(n_slabs=2, side_x=100, ny=100, nz=100, seed=7, spacing=1.02, jitter=0.005, slab=None) -> Scene:
+    """Config C5 for several GPUs: ONE pile of ``n_slabs * side_x`` x ``ny`` x ``nz`` unit cubes, numbered
+    SLAB-MAJOR: slab r (x in [r*side_x, (r+1)*side_x)) holds the contiguous global indices
+    [r*m, (r+1)*m), m = side_x*ny*nz, ordered inside like :func:`cube_pile` (layer by layer).  Contiguous index
+    ranges are therefore spatial x-slabs, which is what csrc/slab.cu's exact decomposition needs.  ``slab=r``
+    returns only that slab's bodies (each slab draws its jitter from its own stream, so a rank can build its share
+    without the rest); the floor slab spans the whole pile either way."""
+    m = side_x * ny * nz
+    which = range(n_slabs) if slab is None else [slab]
+    s = Scene(m * len(which), 0, 1)
+    for k, r in enumerate(which):
+        rng = np.random.default_rng([seed, r])
+        s.pos[k * m:(k + 1) * m] = _lattice(m, (side_x, ny, nz), spacing, jitter, rng,
+                                            (0.5 + r * side_x * spacing, 0.52, 0.5))
+    s.mass[:] = 1.0
+    s.moi[:] = F32(F32(1.0) / F32(12.0)) * F32(2.0)
+    s.scale[:] = 1.0
+    ext_x, ext_z = n_slabs * side_x * spacing, nz * spacing
+    size = float(2 ** np.ceil(np.log2(max(ext_x, ext_z) + 16.0)))
+    s.set_static(0, (ext_x / 2 + 0.13, -0.5, ext_z / 2 + 0.07), (size, 1.0, size), size_for_moi=size)
+    return s
+
+
 def batched_worlds(n_worlds=4096, cubes_per=48, spheres_per=16, seed=0) -> Scene:
     """Config C4: independent worlds (RL-style batch), each ``cubes_per`` cubes + ``spheres_per``
     spheres over the same floor; bodies of different worlds never interact (``world_id``)."""

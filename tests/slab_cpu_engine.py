@@ -1,12 +1,12 @@
-"""CPU engine for the slab protocol (tests only): the oracle restatement as the per-rank stepping
-primitive, halo / velocity records as CPU torch tensors, so that nans_projekat_b200.slab.SlabWorld
-— the same protocol code the GPUs run — can be exercised over gloo."""
+"""CPU engine for the slab protocol model (tests only): the oracle restatement as the per-rank stepping
+primitive, halo / velocity records as CPU torch tensors (tests/slab_protocol_model.py, over gloo)."""
 import contextlib
 
 import numpy as np
 import torch
 
-from nans_projekat_b200.slab import HALO_FLOATS, VEL_FLOATS, partition
+from nans_projekat_b200.slab import partition
+from slab_protocol_model import HALO_FLOATS, VEL_FLOATS
 
 
 class OracleEngine:

@@ -1,6 +1,7 @@
-"""The multi-GPU slab protocol (nans_projekat_b200/slab.py) on CPU: world_size-2 and -3 gloo process
-groups, the oracle as the per-rank engine.  The decomposed world must stay BIT-IDENTICAL to the same
-world stepped as one piece (this is the ordering argument of DESIGN.md §6 under test)."""
+"""The ordering argument of the multi-GPU slab decomposition (csrc/slab.cu) on CPU: world_size-2
+and -3 gloo process groups, the oracle as the per-rank engine (tests/slab_protocol_model.py).  The decomposed
+world must stay BIT-IDENTICAL to the same world stepped as one piece.  Scene: the slab-major numbered pile the
+GPU path uses (index ranges = spatial x-slabs)."""
 import os
 import sys
 
@@ -16,12 +17,11 @@ def _worker(rank, size, port, steps, q):
     import torch.distributed as dist
     from oracle import oracle as O
     from nans_projekat_b200 import scenes
-    from nans_projekat_b200.slab import SlabWorld
+    from slab_protocol_model import SlabProtocolModel as SlabWorld
     from slab_cpu_engine import OracleEngine
     from helpers import world_from_scene
     dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=size)
-    scene = scenes.cube_pile(n_side=6, layers=6, seed=3, jitter=0.02)
-    scene.pos[:, 1] -= 0.0
+    scene = scenes.cube_pile_slabs(n_slabs=size, side_x=3, ny=6, nz=5, seed=3, jitter=0.02)
     whole = world_from_scene(O, scene); whole.rebuild_vertices()
     scene.verts[:] = whole.verts; scene.st_verts[:] = whole.st_verts
     eng = OracleEngine(O, scene, rank, size)
@@ -74,3 +74,18 @@ def test_partition_and_local_scene():
     s = scenes.cube_pile(n_side=4, layers=4)
     ls = local_scene(s, 16, 32, 8)
     assert ls.n_cubes == 24 and np.array_equal(ls.pos[:16], s.pos[16:32]) and (ls.pos[16:, 1] < -1e5).all()
+    assert local_scene(s, 16, 32, 8, capacity=40).n_cubes == 40
+
+
+def test_slab_major_pile_numbering():
+    """cube_pile_slabs: contiguous index ranges are x-slabs, and a rank can build its own slab alone."""
+    from nans_projekat_b200 import scenes
+    full = scenes.cube_pile_slabs(n_slabs=3, side_x=4, ny=3, nz=5, seed=11)
+    m = 4 * 3 * 5
+    assert full.n_cubes == 3 * m
+    for r in range(3):
+        part = scenes.cube_pile_slabs(n_slabs=3, side_x=4, ny=3, nz=5, seed=11, slab=r)
+        assert np.array_equal(part.pos, full.pos[r * m:(r + 1) * m])
+        assert np.array_equal(part.st_pos, full.st_pos) and np.array_equal(part.st_scale, full.st_scale)
+        x = full.pos[r * m:(r + 1) * m, 0]
+        assert x.min() > 0.5 + (4 * r - 0.5) * 1.02 and x.max() < 0.5 + (4 * r + 3.5) * 1.02
