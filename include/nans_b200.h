@@ -167,6 +167,11 @@ int nans_integrate_velocities(nans_world *w, float dt); /* IntegrateVelocities c
 /* the draw section's model rebuild on its own (code/nans.cpp:1870-1881,1913-1941 + UpdateVertices
  * :395-407): Model = T*Rx*Ry*Rz*S -> 8 world vertices for every cube and static, from the pose */
 int nans_rebuild_vertices(nans_world *w);
+/* the draw section's per-body "Model" uniform (code/nans.cpp:1870-1881 floor, :1913-1941 cubes, :1971-1990 spheres)
+ * for every body at once, as instanced draw data: [(n_cubes + n_spheres + n_statics)][16] floats, column-major like
+ * glm::mat4 (bit-identical to the reference's matrices).  d_out: a device buffer (e.g. a CUDA-GL interop VBO bound
+ * as a per-instance mat4 attribute), h_out: a host buffer; either may be NULL. */
+int nans_world_models(nans_world *w, void *d_out, float *h_out);
 /* the step as SimUpdateAndRender runs it (code/nans.cpp:1758-1762).  Queued as DetectCollisions, then
  * IntegrateForces, SolveConstraints, IntegrateVelocities: detection reads positions/vertices only and
  * IntegrateForces writes velocities and clears forces only, so the result is bit-identical to the reference's
@@ -200,6 +205,10 @@ int nans_check_collision_device(int32_t n, const int32_t *d_type,
                                 const float *d_posrad_a, const float *d_verts_a,
                                 const float *d_posrad_b, const float *d_verts_b,
                                 int32_t *d_hit, float *d_out, void *stream);
+
+/* EPA-arena overflow bits of the nans_check_collision_device calls on the current device since the last query
+ * (NANS_ERR_CAPACITY if any: an overflowing pair is reported as a miss); synchronises the device */
+int nans_check_collision_device_status(int32_t *overflow_bits);
 
 /* debug aid: per-contact start time (ns) and dependency level of the last solve (NANS_SOLVER_TRACE=1) */
 int nans_debug_solver_trace(nans_world *w, uint64_t *times, int32_t *levels, int32_t cap);

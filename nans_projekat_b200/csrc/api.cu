@@ -110,6 +110,8 @@ static Layout carve(const nans_world_desc &desc, char *base)
     if (256 * radix_blocks > scan_n) scan_n = 256 * radix_blocks;
     d.scan_block = b.take<uint32_t>((size_t)scan_scratch_elems((int)scan_n) + 8);
     d.counters = b.take<Counters>(1);
+    d.dt = b.take<float>(1);
+    d.sticky = b.take<int32_t>(4);
     for (int k = 0; k < 7; ++k) L.st.vec[k] = b.take<float>(3 * nb);
     for (int k = 0; k < 6; ++k) L.st.dvec[k] = b.take<float>(3 * nb);
     for (int k = 0; k < 3; ++k) L.st.scal[k] = b.take<float>(nb);
@@ -154,6 +156,20 @@ __global__ void pack_vec3_kernel(const float4 *__restrict__ src, float *__restri
     if (i >= n) return;
     const float4 v = src[i];
     dst[3 * i] = v.x; dst[3 * i + 1] = v.y; dst[3 * i + 2] = v.z;
+}
+// up to 7 fields in ONE pass, written straight into the caller's pinned (device-mapped) host buffers: no staging
+// slot, no per-field memcpy -- the stores travel over PCIe as the kernel produces them
+struct PackMany { const float4 *src[7]; float *dst[7]; int n_fields; };
+__global__ void __launch_bounds__(256) pack_vec3_many_kernel(PackMany p, int n)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+#pragma unroll 1
+    for (int k = 0; k < p.n_fields; ++k) {
+        const float4 v = p.src[k][i];
+        float *d = p.dst[k] + 3 * (size_t)i;
+        d[0] = v.x; d[1] = v.y; d[2] = v.z;
+    }
 }
 // which: 0 mass -> pos.w, vel.w = 1/m ; 1 moi -> ang.w, angvel.w = 1/moi ; 2 radius -> scale.w
 __global__ void unpack_scalar_kernel(const float *__restrict__ src, DeviceWorld w, int which)
@@ -253,11 +269,22 @@ int nans_world_create(const nans_world_desc *desc, nans_world **out)
     w->d_world_id_storage = L.d.world_id;
     w->d.world_id = nullptr;
     w->has_world_id = false;
-    if (desc->stream) { w->stream = (cudaStream_t)desc->stream; w->owns_stream = false; }
-    else { NANS_CUDA(cudaStreamCreateWithFlags(&w->stream, cudaStreamNonBlocking)); w->owns_stream = true; }
-    NANS_CUDA(cudaMemsetAsync(w->arena, 0, need, w->stream));
-    NANS_CUDA(cudaMallocHost((void **)&w->h_counters, sizeof(Counters)));
-    NANS_CUDA(cudaStreamSynchronize(w->stream));
+    auto finish = [&]() -> int {
+        if (desc->stream) { w->stream = (cudaStream_t)desc->stream; w->owns_stream = false; }
+        else { NANS_CUDA(cudaStreamCreateWithFlags(&w->stream, cudaStreamNonBlocking)); w->owns_stream = true; }
+        NANS_CUDA(cudaMemsetAsync(w->arena, 0, need, w->stream));
+        NANS_CUDA(cudaMallocHost((void **)&w->h_counters, sizeof(Counters) + 64));
+        NANS_CUDA(cudaStreamSynchronize(w->stream));
+        return NANS_OK;
+    };
+    const int frc = finish();
+    if (frc) {                      // nothing leaks on a failed create (the arena, the stream, the host mirror)
+        char keep[sizeof(g_err)];
+        memcpy(keep, g_err, sizeof(keep));
+        nans_world_destroy(reinterpret_cast<nans_world *>(w));
+        memcpy(g_err, keep, sizeof(keep));
+        return frc;
+    }
     *out = reinterpret_cast<nans_world *>(w);
     return NANS_OK;
 }
@@ -267,7 +294,7 @@ void nans_world_destroy(nans_world *h)
     if (!h) return;
     WorldImpl *w = impl(h);
     cudaSetDevice(w->device);
-    cudaStreamSynchronize(w->stream);
+    if (w->stream) cudaStreamSynchronize(w->stream);
     slab_destroy(w);
     if (w->graph_exec) cudaGraphExecDestroy(w->graph_exec);
     if (w->graph_exec_b) cudaGraphExecDestroy(w->graph_exec_b);
@@ -278,7 +305,7 @@ void nans_world_destroy(nans_world *h)
         for (auto &e : w->io.ev_down) cudaEventDestroy(e);
     }
     if (w->owns_arena) cudaFree(w->arena);
-    if (w->owns_stream) cudaStreamDestroy(w->stream);
+    if (w->owns_stream && w->stream) cudaStreamDestroy(w->stream);
     if (w->h_counters) cudaFreeHost(w->h_counters);
     delete w;
 }
@@ -386,6 +413,27 @@ int nans_world_download(nans_world *h, nans_scene_view *sc)
     float *vdst[7] = {sc->pos, sc->vel, sc->force, sc->ang, sc->angvel, sc->torque, sc->scale};
     const float4 *vsrc[7] = {d.pos, d.vel, d.force, d.ang, d.angvel, d.torque, d.scale};
     if (w->io.init) { NANS_CUDA(cudaStreamSynchronize(w->io.up)); NANS_CUDA(cudaStreamSynchronize(w->io.down)); }
+    // zero-copy path: every requested [nb][3] field lives in pinned, device-mapped host memory
+    bool direct = nb > 0;
+    PackMany pm;
+    pm.n_fields = 0;
+    for (int k = 0; k < 7 && direct; ++k) {
+        if (!vdst[k]) continue;
+        cudaPointerAttributes at;
+        if (cudaPointerGetAttributes(&at, vdst[k]) != cudaSuccess || at.type != cudaMemoryTypeHost || !at.devicePointer) {
+            cudaGetLastError();
+            direct = false;
+            break;
+        }
+        pm.src[pm.n_fields] = vsrc[k];
+        pm.dst[pm.n_fields] = (float *)at.devicePointer;
+        ++pm.n_fields;
+    }
+    if (direct && pm.n_fields > 0) {
+        pack_vec3_many_kernel<<<grid, 256, 0, s>>>(pm, nb);
+        NANS_LAUNCH_CHECK();
+        for (int k = 0; k < 7; ++k) vdst[k] = nullptr;       // done
+    }
     if (nb > 0) {
         for (int k = 0; k < 7; ++k) {
             if (!vdst[k]) continue;
@@ -406,7 +454,11 @@ int nans_world_download(nans_world *h, nans_scene_view *sc)
     if (sc->st_verts && d.n_statics > 0)
         NANS_CUDA(cudaMemcpyAsync(sc->st_verts, d.st_verts, sizeof(float) * 24 * (size_t)d.n_statics,
                                   cudaMemcpyDeviceToHost, s));
+    // sticky errors ride along: a stalled solve (watchdog) must not look like a finished step
+    int32_t *sticky = w->h_counters + sizeof(Counters) / sizeof(int32_t);
+    NANS_CUDA(cudaMemcpyAsync(sticky, d.sticky, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
     NANS_CUDA(cudaStreamSynchronize(s));
+    if (*sticky & 1) return fail(NANS_ERR_STATE, "solver: dependency schedule stalled in an earlier step (watchdog); velocities are partially solved");
     return NANS_OK;
 }
 
@@ -599,7 +651,8 @@ int nans_integrate_forces(nans_world *h, float dt)
     if (!h) return fail(NANS_ERR_ARG, "null world");
     NANS_CUDA(cudaSetDevice(impl(h)->device));
     { const int frc = flush_deferred(impl(h)); if (frc) return frc; }
-    return launch_integrate_forces(impl(h), dt);
+    { const int rc = launch_set_dt(impl(h), dt); if (rc) return rc; }
+    return launch_integrate_forces(impl(h));
 }
 
 int nans_detect_collisions(nans_world *h)
@@ -623,7 +676,8 @@ int nans_solve_constraints(nans_world *h, float dt)
     WorldImpl *w = impl(h);
     if (!w->have_contacts) return fail(NANS_ERR_STATE, "nans_solve_constraints: no contact list (call detect or set_contacts)");
     NANS_CUDA(cudaSetDevice(w->device));
-    return launch_solver(w, dt);
+    { const int rc = launch_set_dt(w, dt); if (rc) return rc; }
+    return launch_solver(w);
 }
 
 int nans_world_set_solver(nans_world *h, int32_t mode)
@@ -641,7 +695,8 @@ int nans_integrate_velocities(nans_world *h, float dt)
 {
     if (!h) return fail(NANS_ERR_ARG, "null world");
     NANS_CUDA(cudaSetDevice(impl(h)->device));
-    return launch_integrate_velocities(impl(h), dt);
+    { const int rc = launch_set_dt(impl(h), dt); if (rc) return rc; }
+    return launch_integrate_velocities(impl(h));
 }
 
 int nans_rebuild_vertices(nans_world *h)
@@ -649,7 +704,29 @@ int nans_rebuild_vertices(nans_world *h)
     if (!h) return fail(NANS_ERR_ARG, "null world");
     WorldImpl *w = impl(h);
     NANS_CUDA(cudaSetDevice(w->device));
-    return launch_integrate_velocities(w, 0.0f);   // Position += 0*V is exact for finite V; rebuilds every Model
+    { const int rc = launch_set_dt(w, 0.0f); if (rc) return rc; }
+    return launch_integrate_velocities(w);   // Position += 0*V is exact for finite V; rebuilds every Model
+}
+
+// Draw data: Model matrices of every body, built on the device (code/nans.cpp:1870-1881, 1913-1941, 1971-1990).
+// d_out (device, e.g. a CUDA-GL interop buffer) and/or h_out (host): [(nb + n_statics)][16] floats, column-major.
+int nans_world_models(nans_world *h, void *d_out, float *h_out)
+{
+    if (!h || (!d_out && !h_out)) return fail(NANS_ERR_ARG, "nans_world_models: no output buffer");
+    WorldImpl *w = impl(h);
+    NANS_CUDA(cudaSetDevice(w->device));
+    { const int frc = flush_deferred(w); if (frc) return frc; }
+    const size_t n = (size_t)w->d.nb + (size_t)w->d.n_statics;
+    // without a device buffer of the caller's the matrices are staged in the narrowphase output block (idle here)
+    if (!d_out && 4 * n > 3 * (size_t)w->d.max_pairs) return fail(NANS_ERR_CAPACITY, "nans_world_models: pass a device buffer for a world this size");
+    float4 *dst = d_out ? (float4 *)d_out : w->d.pair_out;
+    const int rc = launch_models(w, dst);
+    if (rc) return rc;
+    if (h_out) {
+        NANS_CUDA(cudaMemcpyAsync(h_out, dst, sizeof(float) * 16 * n, cudaMemcpyDeviceToHost, w->stream));
+        NANS_CUDA(cudaStreamSynchronize(w->stream));
+    }
+    return NANS_OK;
 }
 
 // One step = IntegrateForces, DetectCollisions, SolveConstraints, IntegrateVelocities (code/nans.cpp:1758-1762).
@@ -657,25 +734,27 @@ int nans_rebuild_vertices(nans_world *h)
 // the two commute bit for bit; the step runs detection FIRST, so that a force/torque upload still in flight
 // (nans_world_upload_async) overlaps broadphase + narrowphase and is unpacked just before integrate-forces.
 static int step_phase_a(nans_world *h) { return nans_detect_collisions(h); }
-static int step_phase_b(nans_world *h, float dt)
+static int step_phase_b(nans_world *h)       // dt is already in device memory (launch_set_dt)
 {
     // (forking integrate-forces onto a side stream next to the solver's schedule kernels was measured:
     // 1.813 vs 1.808 ms per step, the fork/join costs what the overlap saves)
     // (seeding the solver's velocity rows from integrate-forces and consuming them in integrate-velocities --
     // two launches and 130 MB of traffic fewer -- was measured too: 1.7936 vs 1.7944 ms, not kept)
-    int rc = launch_integrate_forces(impl(h), dt);
+    WorldImpl *w = impl(h);
+    int rc = launch_integrate_forces(w);
     if (rc) return rc;
-    rc = nans_solve_constraints(h, dt);
+    if (!w->have_contacts) return fail(NANS_ERR_STATE, "no contact list");
+    rc = launch_solver(w);
     if (rc) return rc;
-    return nans_integrate_velocities(h, dt);
+    return launch_integrate_velocities(w);
 }
-static int step_eager(nans_world *h, float dt)
+static int step_eager(nans_world *h)
 {
     int rc = step_phase_a(h);
     if (rc) return rc;
     rc = flush_deferred(impl(h));
     if (rc) return rc;
-    return step_phase_b(h, dt);
+    return step_phase_b(h);
 }
 
 static void graph_invalidate(WorldImpl *w)
@@ -685,18 +764,21 @@ static void graph_invalidate(WorldImpl *w)
     if (w->graph_state > 0) w->graph_state = 0;
 }
 
-// The step is ~46 launches whose parameters do not change from frame to frame (all sizes that vary
-// live in device memory), so it is captured once into a CUDA graph and replayed: one launch per
-// frame instead of 46.  First step with a given dt runs eagerly (it also warms the static launch
-// configuration caches), the second is captured.  NANS_GRAPH=0 disables.
+// The step is ~35 launches whose parameters do not change from frame to frame -- every size that varies, and dt
+// itself, lives in device memory -- so it is captured once into two CUDA graphs and replayed.  The first step runs
+// eagerly (it also warms the static launch-configuration caches), the second is captured; a dt that changes every
+// frame (the reference host passes the measured frame time, code/sdl_nans.cpp:999) does not invalidate the graphs.
+// NANS_GRAPH=0 disables.
 int nans_step(nans_world *h, float dt)
 {
     if (!h) return fail(NANS_ERR_ARG, "null world");
     WorldImpl *w = impl(h);
+    if (w->slab) return fail(NANS_ERR_STATE, "this world is one rank's slab of a larger world: use nans_slab_step");
     static int enabled = -1;
     if (enabled < 0) { const char *e = getenv("NANS_GRAPH"); enabled = (e && atoi(e) == 0) ? 0 : 1; }
-    if (!enabled || w->graph_state < 0 || w->d.nb == 0) return step_eager(h, dt);
     NANS_CUDA(cudaSetDevice(w->device));
+    { const int rc = launch_set_dt(w, dt); if (rc) return rc; }
+    if (!enabled || w->graph_state < 0 || w->d.nb == 0) return step_eager(h);
     auto replay = [&]() -> int {
         NANS_CUDA(cudaGraphLaunch(w->graph_exec, w->stream));
         const int rc = flush_deferred(w);            // waits for the upload stream, unpacks forces/torques
@@ -706,14 +788,15 @@ int nans_step(nans_world *h, float dt)
         w->have_contacts = true;
         return NANS_OK;
     };
-    if (w->graph_state == 2 && w->graph_dt == dt) return replay();
-    if (w->graph_state == 1 && w->graph_dt == dt) {
+    if (w->graph_state == 2) return replay();
+    if (w->graph_state == 1) {
         // two graphs: detection, and everything that follows the (uncaptured) deferred-input unpack
         const unsigned long long before = g_launches;
         auto capture = [&](cudaGraphExec_t *exec, bool phase_b) -> bool {
             cudaGraph_t graph = nullptr;
             if (cudaStreamBeginCapture(w->stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) return false;
-            const int rc = phase_b ? step_phase_b(h, dt) : step_phase_a(h);
+            if (phase_b) w->have_contacts = true;
+            const int rc = phase_b ? step_phase_b(h) : step_phase_a(h);
             const cudaError_t ee = cudaStreamEndCapture(w->stream, &graph);
             const bool ok = !rc && ee == cudaSuccess && graph && cudaGraphInstantiate(exec, graph, 0) == cudaSuccess;
             if (graph) cudaGraphDestroy(graph);
@@ -727,15 +810,13 @@ int nans_step(nans_world *h, float dt)
             cudaGetLastError();
             graph_invalidate(w);
             w->graph_state = -1;            // capture not possible here: stay eager
-            return step_eager(h, dt);
+            return step_eager(h);
         }
         w->graph_state = 2;
         return replay();
     }
-    graph_invalidate(w);
-    w->graph_dt = dt;
     w->graph_state = 1;
-    return step_eager(h, dt);
+    return step_eager(h);
 }
 
 // One step with a CUDA event between every stage (on the world's stream); stage_ms[8]:
@@ -752,8 +833,9 @@ int nans_step_profiled(nans_world *h, float dt, float *stage_ms)
     cudaStream_t s = w->stream;
     int rc;
     if ((rc = flush_deferred(w))) return rc;
+    if ((rc = launch_set_dt(w, dt))) return rc;
     NANS_CUDA(cudaEventRecord(ev[0], s));
-    if ((rc = launch_integrate_forces(w, dt))) return rc;
+    if ((rc = launch_integrate_forces(w))) return rc;
     NANS_CUDA(cudaEventRecord(ev[1], s));
     if ((rc = launch_broadphase(w))) return rc;
     NANS_CUDA(cudaEventRecord(ev[2], s));
@@ -762,9 +844,9 @@ int nans_step_profiled(nans_world *h, float dt, float *stage_ms)
     if ((rc = launch_contacts(w))) return rc;
     w->have_contacts = true;
     NANS_CUDA(cudaEventRecord(ev[4], s));
-    if ((rc = launch_solver(w, dt))) return rc;
+    if ((rc = launch_solver(w))) return rc;
     NANS_CUDA(cudaEventRecord(ev[5], s));
-    if ((rc = launch_integrate_velocities(w, dt))) return rc;
+    if ((rc = launch_integrate_velocities(w))) return rc;
     NANS_CUDA(cudaEventRecord(ev[6], s));
     NANS_CUDA(cudaEventSynchronize(ev[6]));
     for (int k = 0; k < 6; ++k) NANS_CUDA(cudaEventElapsedTime(&stage_ms[k], ev[k], ev[k + 1]));
@@ -785,7 +867,7 @@ int nans_get_stats(nans_world *h, nans_step_stats *out)
     out->n_pairs = c->n_pairs; out->n_contacts = c->n_contacts; out->n_gjk_found = c->n_gjk_found;
     out->solver_levels = c->solver_levels; out->overflow = c->overflow; out->max_epa_faces = c->max_epa_faces;
     { const int frc = solver_accum_fallbacks(w, &out->accum_fallbacks); if (frc) return frc; }
-    if (c->pad[1]) return fail(NANS_ERR_STATE, "solver: dependency schedule stalled (spin cap hit)");
+    if (c->pad[1]) return fail(NANS_ERR_STATE, "solver: dependency schedule stalled (watchdog: no row arrived for seconds)");
     if (c->overflow) {
         snprintf(g_err, sizeof(g_err), "capacity exceeded (overflow bits 0x%x: 1 pairs, 2 contacts, 4 EPA faces, 8 EPA edges)",
                  c->overflow);
@@ -900,18 +982,40 @@ int nans_get_pairs(nans_world *h, int32_t *pa, int32_t *pb, int32_t cap, int32_t
 }
 
 // ---- stand-alone narrowphase ---------------------------------------------------------------------
+static char *g_np_dev_block[64] = {nullptr};   // per device: work counter + Counters of the device-resident batch entry
 int nans_check_collision_device(int32_t n, const int32_t *d_type, const float *d_posrad_a, const float *d_verts_a,
                                 const float *d_posrad_b, const float *d_verts_b, int32_t *d_hit, float *d_out,
                                 void *stream)
 {
-    static int *d_works[64] = {nullptr};      // one work counter per device (the caller's current device)
     int dev = 0;
     NANS_CUDA(cudaGetDevice(&dev));
-    int *&d_work = d_works[(dev >= 0 && dev < 64) ? dev : 0];
-    if (!d_work) NANS_CUDA(cudaMalloc(&d_work, 256));
+    char *&blk = g_np_dev_block[(dev >= 0 && dev < 64) ? dev : 0];   // work counter at +0, Counters at +256
+    if (!blk) { NANS_CUDA(cudaMalloc(&blk, 512)); NANS_CUDA(cudaMemsetAsync(blk, 0, 512, (cudaStream_t)stream)); }
     return launch_narrowphase_batch(n, d_type, (const float4 *)d_posrad_a, (const float4 *)d_verts_a,
                                     (const float4 *)d_posrad_b, (const float4 *)d_verts_b, d_hit, nullptr,
-                                    (float4 *)d_out, d_work, nullptr, (cudaStream_t)stream);
+                                    (float4 *)d_out, (int *)blk, (Counters *)(blk + 256), (cudaStream_t)stream);
+}
+
+// EPA-arena overflow bits accumulated by nans_check_collision_device on the current device since the last call
+// (an overflowing pair is otherwise indistinguishable from a miss); synchronises the device.
+int nans_check_collision_device_status(int32_t *overflow_bits)
+{
+    if (!overflow_bits) return fail(NANS_ERR_ARG, "null argument");
+    int dev = 0;
+    NANS_CUDA(cudaGetDevice(&dev));
+    char *blk = g_np_dev_block[(dev >= 0 && dev < 64) ? dev : 0];
+    *overflow_bits = 0;
+    if (!blk) return NANS_OK;
+    Counters c;
+    NANS_CUDA(cudaDeviceSynchronize());
+    NANS_CUDA(cudaMemcpy(&c, blk + 256, sizeof(c), cudaMemcpyDeviceToHost));
+    NANS_CUDA(cudaMemset(blk + 256, 0, sizeof(c)));
+    *overflow_bits = c.overflow;
+    if (c.overflow) {
+        snprintf(g_err, sizeof(g_err), "EPA arena capacity exceeded (bits 0x%x)", c.overflow);
+        return NANS_ERR_CAPACITY;
+    }
+    return NANS_OK;
 }
 
 int nans_check_collision_batch(int32_t n, const int32_t *type, const float *pos_a, const float *verts_a,

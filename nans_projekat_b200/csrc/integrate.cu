@@ -15,8 +15,9 @@
 
 namespace nans {
 
-__global__ void __launch_bounds__(256) integrate_forces_kernel(DeviceWorld w, float dt)
+__global__ void __launch_bounds__(256) integrate_forces_kernel(DeviceWorld w)
 {
+    const float dt = *w.dt;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= w.n_owned) return;      // == nb unless the world is one rank's slab (ghost rows belong to their owner)
     const float4 p = w.pos[i];      // w = Mass
@@ -39,8 +40,9 @@ __device__ __forceinline__ void store_verts(float4 *dst, const float v[24])
     for (int q = 0; q < 6; ++q) dst[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
 }
 
-__global__ void __launch_bounds__(128) integrate_velocities_kernel(DeviceWorld w, float dt)
+__global__ void __launch_bounds__(128) integrate_velocities_kernel(DeviceWorld w)
 {
+    const float dt = *w.dt;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= w.n_owned) return;
     float4 p = w.pos[i];
@@ -68,18 +70,61 @@ __global__ void rebuild_statics_kernel(DeviceWorld w)
     store_verts(w.st_verts + 6 * k, verts);
 }
 
-int launch_integrate_forces(World *w, float dt)
+// Instanced draw data: the Model matrix the reference's draw section builds per cube / sphere / floor
+// and uploads as the "Model" uniform (code/nans.cpp:1870-1881, 1913-1941, 1971-1990), here for EVERY body in one
+// pass, column-major like glm::mat4, so a renderer can bind `out` as a per-instance mat4 attribute buffer.
+// rows: cubes, spheres (scale = Radius), then the statics.
+__global__ void __launch_bounds__(128) models_kernel(DeviceWorld w, float4 *__restrict__ out)
 {
-    if (w->d.nb == 0) return NANS_OK;
-    integrate_forces_kernel<<<div_up(w->d.nb, 256), 256, 0, w->stream>>>(w->d, dt);
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= w.nb + w.n_statics) return;
+    vec3 pos, ang, scale;
+    if (i < w.nb) {
+        pos = V3(w.pos[i]); ang = V3(w.ang[i]);
+        const float4 sc = w.scale[i];
+        scale = i < w.n_cubes ? V3(sc) : V3(sc.w, sc.w, sc.w);
+    } else {
+        const int k = i - w.nb;
+        pos = V3(w.st_pos[k]); ang = V3(w.st_ang[k]); scale = V3(w.st_scale[k]);
+    }
+    mat4 m;
+    model_matrix(pos, ang, scale, m);
+#pragma unroll
+    for (int c = 0; c < 4; ++c) out[4 * (size_t)i + c] = make_float4(m.c[c][0], m.c[c][1], m.c[c][2], m.c[c][3]);
+}
+
+int launch_models(World *w, float4 *d_out)
+{
+    const int n = w->d.nb + w->d.n_statics;
+    if (n == 0) return NANS_OK;
+    models_kernel<<<div_up(n, 128), 128, 0, w->stream>>>(w->d, d_out);
     NANS_LAUNCH_CHECK();
     return NANS_OK;
 }
 
-int launch_integrate_velocities(World *w, float dt)
+__global__ void set_dt_kernel(float *dst, float dt) { *dst = dt; }
+
+// dt lives in device memory so that the captured step graph is independent of it: the reference host passes the
+// MEASURED frame time, which changes every frame (code/sdl_nans.cpp:986,999)
+int launch_set_dt(World *w, float dt)
+{
+    set_dt_kernel<<<1, 1, 0, w->stream>>>(w->d.dt, dt);
+    NANS_LAUNCH_CHECK();
+    return NANS_OK;
+}
+
+int launch_integrate_forces(World *w)
 {
     if (w->d.nb == 0) return NANS_OK;
-    integrate_velocities_kernel<<<div_up(w->d.nb, 128), 128, 0, w->stream>>>(w->d, dt);
+    integrate_forces_kernel<<<div_up(w->d.nb, 256), 256, 0, w->stream>>>(w->d);
+    NANS_LAUNCH_CHECK();
+    return NANS_OK;
+}
+
+int launch_integrate_velocities(World *w)
+{
+    if (w->d.nb == 0) return NANS_OK;
+    integrate_velocities_kernel<<<div_up(w->d.nb, 128), 128, 0, w->stream>>>(w->d);
     NANS_LAUNCH_CHECK();
     // the draw section also refreshes the Floor's Model and vertices every frame (:1870-1881)
     return launch_rebuild_statics(w);

@@ -64,10 +64,10 @@ __device__ __forceinline__ void glm_rotate(mat4 &m, float angle, vec3 axis_in)
         for (int r = 0; r < 4; ++r) m.c[i][r] = o.c[i][r];
 }
 
-// Model = T(pos) * Rx(radians(ang.x)) * Ry(..y) * Rz(..z) * S(scale); out = 8 world vertices
-__device__ __forceinline__ void model_vertices(vec3 pos, vec3 ang, vec3 scale, float out[24])
+// Model = T(pos) * Rx(radians(ang.x)) * Ry(..y) * Rz(..z) * S(scale): the draw section's rebuild
+// (code/nans.cpp:1870-1881 floor, :1913-1941 cubes, :1971-1984 spheres), glm's operation order
+__device__ __forceinline__ void model_matrix(vec3 pos, vec3 ang, vec3 scale, mat4 &m)
 {
-    mat4 m;
 #pragma unroll
     for (int c = 0; c < 4; ++c)
 #pragma unroll
@@ -85,6 +85,13 @@ __device__ __forceinline__ void model_vertices(vec3 pos, vec3 ang, vec3 scale, f
         m.c[1][r] = fmul(m.c[1][r], scale.y);
         m.c[2][r] = fmul(m.c[2][r], scale.z);
     }
+}
+
+// out = the 8 world vertices of the unit cube under Model (UpdateVertices, code/nans.cpp:395-407)
+__device__ __forceinline__ void model_vertices(vec3 pos, vec3 ang, vec3 scale, float out[24])
+{
+    mat4 m;
+    model_matrix(pos, ang, scale, m);
     // UpdateVertices: vec3(Model * vec4(+-.5, +-.5, +-.5, 1)) = (m0*x + m1*y) + (m2*z + m3*w)
 #pragma unroll
     for (int k = 0; k < 8; ++k) {

@@ -376,7 +376,8 @@ int nans_slab_step(nans_world *h, float dt)
     int rc;
     slab_begin_kernel<<<1, 1, 0, s>>>(d, S->live);                      // live rows = owned rows
     NANS_LAUNCH_CHECK();
-    if ((rc = launch_integrate_forces(w, dt))) return rc;
+    if ((rc = launch_set_dt(w, dt))) return rc;
+    if ((rc = launch_integrate_forces(w))) return rc;
     if ((rc = launch_aabb_only(w))) return rc;                          // owned rows (live = n_owned)
     const int n = d.n_owned;
     const int blocks = n > 0 ? min(div_up(n, kBoundsThreads), 1024) : 0;
@@ -401,8 +402,8 @@ int nans_slab_step(nans_world *h, float dt)
     if ((rc = launch_narrowphase(w))) return rc;
     if ((rc = launch_contacts(w))) return rc;
     w->have_contacts = true;
-    if ((rc = launch_solver(w, dt))) return rc;
-    return launch_integrate_velocities(w, dt);
+    if ((rc = launch_solver(w))) return rc;
+    return launch_integrate_velocities(w);
 }
 
 // synchronises; err_bits: SLAB_ERR_* (sticky), live_rows: owned + ghosts of the last step

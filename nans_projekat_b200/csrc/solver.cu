@@ -217,6 +217,7 @@ __global__ void __launch_bounds__(256) ver_seed_kernel(DeviceWorld w)
 __global__ void __launch_bounds__(256) ver_finish_kernel(DeviceWorld w)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0 && w.counters->pad[1]) atomicOr(w.sticky, 1);   // the watchdog fired: reported by the next download / stats
     if (i >= w.nb) return;
     float4 v, a;
     if (w.live && w.sent_mark[i]) {
@@ -224,7 +225,7 @@ __global__ void __launch_bounds__(256) ver_finish_kernel(DeviceWorld w)
         while (true) {
             v = ld_row<true>(w.row_v + i); a = ld_row<true>(w.row_w + i);
             if (__float_as_int(v.w) != kPendingTag && (__float_as_int(a.w) & kVerMask) != kPendingTag) break;
-            if ((long long)(global_ns() - t0) > kWatchdogNs || *(volatile int *)&w.counters->pad[1]) { w.counters->pad[1] = 1; return; }
+            if ((long long)(global_ns() - t0) > kWatchdogNs || *(volatile int *)&w.counters->pad[1]) { w.counters->pad[1] = 1; atomicOr(w.sticky, 1); return; }
         }
     } else {
         v = w.row_v[i]; a = w.row_w[i];
@@ -239,8 +240,9 @@ __global__ void __launch_bounds__(256) ver_finish_kernel(DeviceWorld w)
 // along the run and only body B's rows go through memory, and the lanes of a warp fire together.
 // trace (debug, NANS_SOLVER_TRACE=1): per contact {fire ns, stored ns, ticket ns, cycles}; trace_level = DAG level
 template <bool SHUFFLED, bool SLAB>
-__global__ void __launch_bounds__(kVerThreads, NANS_VER_MINBLOCKS) solve_versioned_kernel(DeviceWorld w, float dt, unsigned long long *trace)
+__global__ void __launch_bounds__(kVerThreads, NANS_VER_MINBLOCKS) solve_versioned_kernel(DeviceWorld w, unsigned long long *trace)
 {
+    const float dt = *w.dt;
     const int n = w.counters->n_contacts;
     const int kbits = order_bits_for(n);
     const int n_tickets = SHUFFLED ? (n > 0 ? (int)min((unsigned long long)1 << kbits, (unsigned long long)0x7fffffff) : 0)
@@ -365,7 +367,7 @@ __global__ void __launch_bounds__(kVerThreads, NANS_VER_MINBLOCKS) solve_version
     if (lane == 0 && max_level) atomicMax(&w.counters->solver_levels, max_level);
 }
 
-int launch_solver(World *w, float dt)
+int launch_solver(World *w)
 {
     DeviceWorld &d = w->d;
     if (d.nb == 0) return NANS_OK;
@@ -424,9 +426,9 @@ int launch_solver(World *w, float dt)
     static int ver_trace = -1;
     if (ver_trace < 0) ver_trace = getenv("NANS_SOLVER_TRACE") ? 1 : 0;
     unsigned long long *trace = ver_trace ? (unsigned long long *)d.pair_out : nullptr;
-    if (variant == 0) solve_versioned_kernel<false, false><<<ver_blocks[0], kVerThreads, 0, s>>>(d, dt, trace);
-    else if (variant == 1) solve_versioned_kernel<false, true><<<ver_blocks[1], kVerThreads, 0, s>>>(d, dt, trace);
-    else solve_versioned_kernel<true, false><<<ver_blocks[2], kVerThreads, 0, s>>>(d, dt, trace);
+    if (variant == 0) solve_versioned_kernel<false, false><<<ver_blocks[0], kVerThreads, 0, s>>>(d, trace);
+    else if (variant == 1) solve_versioned_kernel<false, true><<<ver_blocks[1], kVerThreads, 0, s>>>(d, trace);
+    else solve_versioned_kernel<true, false><<<ver_blocks[2], kVerThreads, 0, s>>>(d, trace);
     NANS_LAUNCH_CHECK();
     ver_finish_kernel<<<div_up(d.nb, 256), 256, 0, s>>>(d);
     NANS_LAUNCH_CHECK();

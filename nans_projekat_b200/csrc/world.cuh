@@ -98,6 +98,8 @@ struct DeviceWorld {
     // --- scan scratch
     uint32_t *scan_block;               // block sums
     Counters *counters;
+    float *dt;                          // this step's dt, in device memory: the captured step graph does not depend on it
+    int32_t *sticky;                    // sticky error bits (survive the per-step counter reset): 1 = solver schedule stalled
 };
 
 // host-side bookkeeping
@@ -147,13 +149,15 @@ inline int div_up(int a, int b) { return (a + b - 1) / b; }
 inline int div_up_sz(size_t a, size_t b) { return (int)((a + b - 1) / b); }
 
 // stage launchers (each file owns its kernels)
-int launch_integrate_forces(World *w, float dt);
-int launch_integrate_velocities(World *w, float dt);
+int launch_set_dt(World *w, float dt);          // every stage reads dt from device memory (DeviceWorld::dt)
+int launch_integrate_forces(World *w);
+int launch_integrate_velocities(World *w);
 int launch_rebuild_statics(World *w);
+int launch_models(World *w, float4 *d_out);
 int launch_broadphase(World *w);
 int launch_narrowphase(World *w);
 int launch_contacts(World *w);
-int launch_solver(World *w, float dt);
+int launch_solver(World *w);
 int solver_accum_fallbacks(World *w, int32_t *out);
 int launch_aabb_only(World *w);
 void slab_destroy(World *w);

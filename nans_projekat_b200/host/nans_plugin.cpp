@@ -172,6 +172,12 @@ void Init(memory *Memory, plugin_state *S)
     float *verts = t; t += 24 * (size_t)S->n_cubes;
     float *st_verts = t; t += 24;
     float *st_ang = t; t += 3;
+    if ((uint64_t)((char *)t - (char *)Memory->TransientStorage) > Memory->TransientStorageSize)
+    {
+        fprintf(stderr, "nans plugin: scene scratch does not fit the host's TransientStorage block "
+                        "(reduce NANS_SCENE or grow the block)\n");
+        abort();
+    }
     memset(Memory->TransientStorage, 0, (char *)t - (char *)Memory->TransientStorage);
     if (side) pile_scene(b, side, 1.02f, 0.005f); else demo_scene(b);
 

@@ -149,6 +149,18 @@ class World:
     def step(self, dt):
         _lib.check(_lib.lib().nans_step(self._h, dt))
 
+    def models(self, device_ptr: int | None = None) -> np.ndarray | None:
+        """Model matrices of every body (cubes, spheres, statics), column-major like glm::mat4: the "Model" uniform
+        of the reference's draw section (code/nans.cpp:1870-1881, 1913-1941, 1971-1990) as instanced draw data.
+        With ``device_ptr`` they are written there (a renderer's instance buffer) and nothing is copied back."""
+        n = self.nb + self.n_statics
+        if device_ptr is not None:
+            _lib.check(_lib.lib().nans_world_models(self._h, C.c_void_p(device_ptr), None))
+            return None
+        out = np.zeros((n, 16), np.float32)
+        _lib.check(_lib.lib().nans_world_models(self._h, None, _fp(out)))
+        return out
+
     SOLVER_EXACT, SOLVER_SHUFFLED = 0, 1
 
     def set_solver(self, mode):

@@ -517,6 +517,30 @@ def test_c2_full_size_drop_scene(nb200, oracle):
     gw.close()
 
 
+def test_model_matrices_instanced_draw_data(nb200, oracle):
+    """nans_world_models: the draw section's Model = T*Rx*Ry*Rz*S (code/nans.cpp:1870-1881, 1913-1941, 1971-1990)
+    for every cube, sphere and static, bit-identical to the oracle's (which is pinned to nans.so's Models)."""
+    from nans_projekat_b200 import scenes
+    rng = np.random.default_rng(3)
+    s = scenes.random_small_world(rng, 16, 16)
+    s.scale[3] = (0.5, 1.0, 0.5)                 # the reference's squashed debug box
+    big = scenes.batched_worlds(n_worlds=64, cubes_per=48, spheres_per=16, seed=2)
+    big.ang[:] = rng.uniform(-400, 400, big.ang.shape).astype(np.float32)
+    for sc in (s, big):
+        gw = nb200.World(sc)
+        m = gw.models()
+        assert m.shape == (sc.nb + sc.n_statics, 16)
+        idx = np.arange(sc.nb) if sc.nb < 100 else rng.choice(sc.nb, 400, replace=False)
+        for i in idx:
+            scale = sc.scale[i] if i < sc.n_cubes else (sc.radius[i],) * 3
+            want = oracle.model_vertices(sc.pos[i], sc.ang[i], scale)[0].reshape(16)
+            assert_bit_equal(m[i], want, f"Model of body {i}")
+        for k in range(sc.n_statics):
+            want = oracle.model_vertices(sc.st_pos[k], sc.st_ang[k], sc.st_scale[k])[0].reshape(16)
+            assert_bit_equal(m[sc.nb + k], want, f"Model of static {k}")
+        gw.close()
+
+
 def test_pipelined_io_matches_synchronous_io(nb200, oracle):
     """upload_async / download_async / wait (copies overlapping the step on their own streams) must give
     exactly the states the synchronous upload / step / download sequence gives; snapshot/restore returns
