@@ -25,11 +25,14 @@ dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 m = side_x * ny * nz
 owned = scenes.cube_pile_slabs(n_slabs=size, side_x=side_x, ny=ny, nz=nz, seed=7, slab=rank, spacing=spacing, jitter=0.004)
 halo_cap = max(1024, 4 * ny * nz)
-sw = SlabWorld(owned, rank, size, dist, local, gid_base=rank * m, halo_cap=halo_cap, capacity=m + halo_cap)
+# the squeezed pile reaches > 8 contacts per body: explicit capacities (the same on every rank), checked below
+caps = dict(max_pairs=64 * (m + halo_cap), max_contacts=24 * (m + halo_cap))
+sw = SlabWorld(owned, rank, size, dist, local, gid_base=rank * m, halo_cap=halo_cap, capacity=m + halo_cap, **caps)
 sw.rebuild_vertices()
 ref = None
 if rank == 0:
-    ref = World(scenes.cube_pile_slabs(n_slabs=size, side_x=side_x, ny=ny, nz=nz, seed=7, spacing=spacing, jitter=0.004), device=local)
+    ref = World(scenes.cube_pile_slabs(n_slabs=size, side_x=side_x, ny=ny, nz=nz, seed=7, spacing=spacing, jitter=0.004), device=local,
+                max_pairs=size * caps["max_pairs"], max_contacts=size * caps["max_contacts"])
     ref.rebuild_vertices()
 dt = np.float32(1 / 60.)
 bad, max_ghosts, max_cross = 0, 0, 0
@@ -38,35 +41,46 @@ for k in range(settle + steps):
     sw.step(dt)
     if ref is not None:
         ref.step(dt)
-    if k < settle and k % every:
+    if k < settle and k % every and not os.environ.get("SLAB_DIAG"):
         continue
+    if bad >= 2 and os.environ.get("SLAB_DIAG"):
+        break
     st = sw.status()
+    st["stats"] = sw.world.stats(strict=False)
     o = sw.download_owned()
     cg = sw.contacts_global()
     parts = [None] * size
     dist.all_gather_object(parts, (rank * m, (rank + 1) * m, {f: getattr(o, f) for f in ("pos", "vel", "ang", "angvel", "verts")},
-                                   cg, st["ghosts"]))
+                                   cg, st["ghosts"], st["stats"]))
     if rank == 0:
         full = ref.download()
+        assert ref.stats()["overflow"] == 0 and all(p[5]["overflow"] == 0 for p in parts), "capacity overflow: enlarge the check's capacities"
         rc = ref.contacts()
         ok = True
-        for lo, hi, fields, _, _ in parts:
+        for lo, hi, fields, _, _, _ in parts:
             for f, a in fields.items():
                 if not np.array_equal(a.view(np.uint32), getattr(full, f)[lo:hi].view(np.uint32)):
                     ok = False
-                    print(f"step {k}: rank range [{lo},{hi}) field {f} differs from the single-GPU world", flush=True)
+                    rows = np.nonzero((a.view(np.uint32) != getattr(full, f)[lo:hi].view(np.uint32)).reshape(hi - lo, -1).any(1))[0]
+                    print(f"step {k}: rank range [{lo},{hi}) field {f} differs from the single-GPU world on {len(rows)} rows, "
+                          f"first {rows[:6] + lo}", flush=True)
         allc = np.concatenate([p[3] for p in parts])
         allc = allc[np.lexsort((allc["b"], allc["a"], allc["type"] != 0))]   # CC first, then CF; by (a, b)
         if allc.tobytes() != rc.tobytes():
             ok = False
-            print(f"step {k}: contact lists differ ({len(allc)} vs {len(rc)})", flush=True)
+            n_ = min(len(allc), len(rc))
+            key = lambda c: np.stack([c["type"][:n_], c["a"][:n_], c["b"][:n_]], 1)
+            d_ = np.nonzero((key(allc) != key(rc)).any(1))[0]
+            print(f"step {k}: contact lists differ ({len(allc)} vs {len(rc)}); first differing key at {d_[:1]}: "
+                  f"{allc[d_[0]] if len(d_) else None} vs {rc[d_[0]] if len(d_) else None}", flush=True)
         cross = int(((allc["type"] == 0) & (allc["a"] // m != allc["b"] // m)).sum())
         bad += (not ok)
         max_cross = max(max_cross, cross)
         max_ghosts = max(max_ghosts, max(p[4] for p in parts))
         if k % every == 0 or not ok:
             print(f"step {k:3d} ok={ok} contacts={len(rc)} cross-slab contacts={cross} ghosts/rank={[p[4] for p in parts]} "
-                  f"levels={ref.stats()['solver_levels']}", flush=True)
+                  f"levels={ref.stats()['solver_levels']} overflow/rank={[p[5]['overflow'] for p in parts]} "
+                  f"contacts/rank={[p[5]['n_contacts'] for p in parts]}", flush=True)
 if rank == 0:
     if max_cross == 0:
         bad += 1
