@@ -89,11 +89,14 @@ static Layout carve(const nans_world_desc &desc, char *base)
     d.sbox = b.take<float4>(2 * nb);
     d.pair_tmp = b.take<uint32_t>(24 * nb);
     for (int k = 0; k < 2; ++k) { d.key[k] = b.take<uint32_t>(nb); d.val[k] = b.take<uint32_t>(nb); }
-    const size_t radix_blocks = (nb + 4095) / 4096;
-    d.radix_hist = b.take<uint32_t>(256 * radix_blocks);
     const uint32_t table = pow2_at_least((uint32_t)(2 * nb));
     d.cell_mask = table - 1;
+    d.cell_bits = 0;
+    while ((1u << d.cell_bits) < table) ++d.cell_bits;
+    d.n_seg = desc.n_spheres > 0 ? 5 : 2;
     d.cell_tab = b.take<uint4>(table);
+    d.cell_count = b.take<uint32_t>((size_t)table + 1);
+    d.pair_fill = b.take<uint32_t>(nb);
     d.pair_count = b.take<uint32_t>(5 * nb + 1);
     d.pair_a = b.take<int32_t>(mp); d.pair_b = b.take<int32_t>(mp);
     d.pair_hit = b.take<int32_t>(mp + 1); d.pair_hit_scan = b.take<uint32_t>(mp + 1);
@@ -107,7 +110,7 @@ static Layout carve(const nans_world_desc &desc, char *base)
     d.row_v = b.take<float4>(nb); d.row_w = b.take<float4>(nb);
     size_t scan_n = mp + 1;
     if (5 * nb + 1 > scan_n) scan_n = 5 * nb + 1;
-    if (256 * radix_blocks > scan_n) scan_n = 256 * radix_blocks;
+    if ((size_t)table + 1 > scan_n) scan_n = (size_t)table + 1;
     d.scan_block = b.take<uint32_t>((size_t)scan_scratch_elems((int)scan_n) + 8);
     d.counters = b.take<Counters>(1);
     d.dt = b.take<float>(1);

@@ -7,10 +7,15 @@
 //
 //   aabb_kernel          AABB per body (8 vertices / centre +- radius) + this step's largest extent
 //   key_kernel           30-bit Morton key of the cell (edge = largest extent) holding the AABB centre
-//   radix sort           4 x 8-bit LSD passes (histogram -> scan -> stable scatter), key+row payload
-//   gather_sorted_kernel AABBs permuted into Morton order as 32-byte records (neighbour scans read
-//                        contiguous ranges) + open-addressing hash table cell key -> [start, end)
-//   pair_count_kernel    per body ONE 27-cell scan: counts per (type, body) + partners parked in slots
+//   cell_insert_kernel   counting sort, pass 1: the body's cell is found-or-inserted in the cell table (open
+//                        addressing; slot = the Morton key itself while it fits the table, so slot order IS
+//                        Morton order) and the body takes a rank inside the cell (one atomicAdd)
+//   (exclusive scan)     cell sizes -> cell start offsets
+//   cell_scatter_kernel  pass 2: AABBs into cell order as 32-byte records {lo.xyz,row}{hi.xyz,world} (neighbour
+//                        scans read contiguous ranges); the table entry becomes {key, start, end}
+//                        (round 1 sorted with a 3-4 pass LSD radix sort + a gather: 13 launches, ~190 us at 1 M
+//                        bodies; the order INSIDE a cell is irrelevant -- the emit pass sorts every run)
+//   pair_count_kernel    per body ONE half-neighbourhood scan: counts per (type, body) + partners parked in slots
 //   (exclusive scan)     offsets in reference order
 //   pair_emit_kernel     moves the parked partners to their offsets, sorts each short run ascending
 //
@@ -192,145 +197,54 @@ __global__ void __launch_bounds__(256) key_kernel(DeviceWorld w)
     }
     const uint32_t key = morton30((uint32_t)cx, (uint32_t)cy, (uint32_t)cz);
     w.key[0][i] = key;
-    w.val[0][i] = (uint32_t)i;
-    // the largest key of the step decides how many 8-bit sort passes are needed (kMaxKey)
-    const uint32_t m = __reduce_max_sync(__activemask(), key);
-    unsigned int *slot = (unsigned int *)&w.counters->pad[kMaxKey];
-    if ((threadIdx.x & 31) == 0 && m > *(volatile unsigned int *)slot) atomicMax(slot, m);   // rarely improves it
-}
-
-// Sort passes that only see zero digits are skipped (a 250 x 16 x 250-cell world has 24-bit keys,
-// a 10 k-cube world 15-bit ones), so the sorted data ends in buffer 0 or 1 depending on the
-// step: the consumers pick the buffer with sorted_buf().  pad[kPassLen + p - 1] = histogram length
-// of pass p (0 when skipped), for the scan's device-side length.
-__device__ __forceinline__ int sorted_passes(const DeviceWorld &w)
-{
-    const uint32_t mk = (uint32_t)w.counters->pad[kMaxKey];
-    return 1 + (mk >= (1u << 8)) + (mk >= (1u << 16)) + (mk >= (1u << 24));
-}
-__device__ __forceinline__ int sorted_buf(const DeviceWorld &w) { return sorted_passes(w) & 1; }
-
-__global__ void radix_plan_kernel(DeviceWorld w, int hist_len)
-{
-    const int p = threadIdx.x + 1;   // passes 1..3
-    if (p <= 3) w.counters->pad[kPassLen + p - 1] = p < sorted_passes(w) ? hist_len : 0;
 }
 
 // ---------------------------------------------------------------------------------------------
-// LSD radix sort, 8 bits per pass.  (kMaxKey / kPassLen: slots of Counters::pad, see world.cuh.)
-constexpr int kRadixThreads = 256;
-constexpr int kRadixItems = 16;
-constexpr int kRadixTile = kRadixThreads * kRadixItems;  // 4096 keys per block
-
-__global__ void __launch_bounds__(kRadixThreads) radix_hist_kernel(const uint32_t *__restrict__ keys, int n,
-                                                                   int shift, uint32_t *__restrict__ hist,
-                                                                   int n_blocks, const int32_t *__restrict__ max_key,
-                                                                   const int32_t *__restrict__ live)
-{
-    if (shift && ((uint32_t)*max_key >> shift) == 0u) return;   // nothing but zero digits: pass skipped
-    if (live) n = *live;
-    __shared__ uint32_t h[256];
-    h[threadIdx.x] = 0;
-    __syncthreads();
-    const int base = blockIdx.x * kRadixTile;
-#pragma unroll 4
-    for (int k = 0; k < kRadixItems; ++k) {
-        const int i = base + k * kRadixThreads + threadIdx.x;
-        if (i < n) atomicAdd(&h[(keys[i] >> shift) & 255u], 1u);
-    }
-    __syncthreads();
-    hist[threadIdx.x * n_blocks + blockIdx.x] = h[threadIdx.x];  // digit-major: one scan gives offsets
-}
-
-__global__ void __launch_bounds__(kRadixThreads) radix_scatter_kernel(
-    const uint32_t *__restrict__ keys_in, const uint32_t *__restrict__ vals_in,
-    uint32_t *__restrict__ keys_out, uint32_t *__restrict__ vals_out, int n, int shift,
-    const uint32_t *__restrict__ hist_scanned, int n_blocks, const int32_t *__restrict__ max_key,
-    const int32_t *__restrict__ live)
-{
-    if (shift && ((uint32_t)*max_key >> shift) == 0u) return;
-    if (live) n = *live;
-    __shared__ uint32_t base_off[256];            // running global offset per digit for this block
-    __shared__ uint32_t warp_cnt[kRadixThreads / 32][256];
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    base_off[threadIdx.x] = hist_scanned[threadIdx.x * n_blocks + blockIdx.x];
-    const int tile = blockIdx.x * kRadixTile;
-    for (int k = 0; k < kRadixItems; ++k) {
-#pragma unroll
-        for (int q = 0; q < 8; ++q) warp_cnt[wid][q * 32 + lane] = 0;
-        __syncthreads();
-        const int i = tile + k * kRadixThreads + threadIdx.x;   // chunk k is contiguous: stable order
-        const bool valid = i < n;
-        uint32_t key = 0, val = 0, digit = 0;
-        if (valid) { key = keys_in[i]; val = vals_in[i]; digit = (key >> shift) & 255u; }
-        // rank among same-digit lanes of this warp (invalid lanes use a private pseudo-digit)
-        const uint32_t peers = __match_any_sync(0xffffffffu, valid ? digit : 0x100u + lane);
-        const uint32_t rank = __popc(peers & ((1u << lane) - 1u));
-        if (valid && rank == 0) warp_cnt[wid][digit] = __popc(peers);
-        __syncthreads();
-        // thread d: exclusive prefix of digit d over the warps, then advance the block base
-        {
-            const int d = threadIdx.x;
-            uint32_t run = base_off[d];
-#pragma unroll
-            for (int q = 0; q < kRadixThreads / 32; ++q) {
-                const uint32_t c = warp_cnt[q][d];
-                warp_cnt[q][d] = run;
-                run += c;
-            }
-            base_off[d] = run;
-        }
-        __syncthreads();
-        if (valid) {
-            const uint32_t dst = warp_cnt[wid][digit] + rank;
-            keys_out[dst] = key;
-            vals_out[dst] = val;
-        }
-        __syncthreads();
-    }
-}
-
-// ---------------------------------------------------------------------------------------------
-// After the sort: AABBs in Morton order as one 32-byte record per body (one L2 sector per
-// candidate test): {lo.xyz, row} {hi.xyz, world id}; and the hash table of cells, one 16-byte
-// entry {key, start, end, -} per slot (one sector per probe).
-__global__ void __launch_bounds__(256) gather_sorted_kernel(DeviceWorld w)
-{
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    const int nb = live_nb(w);
-    if (t >= nb) return;
-    const int fb = sorted_buf(w);
-    const uint32_t *__restrict__ keys = w.key[fb];
-    const uint32_t *__restrict__ vals = w.val[fb];
-    w.key[fb ^ 1][t] = 0u;                    // the spare key buffer becomes the pair-slot cursors
-    const uint32_t row = vals[t];
-    float4 lo = w.aabb_lo[row], hi = w.aabb_hi[row];
-    lo.w = __int_as_float((int)row);
-    hi.w = __int_as_float(w.world_id ? w.world_id[row] : 0);
-    w.sbox[2 * (size_t)t] = lo;
-    w.sbox[2 * (size_t)t + 1] = hi;
-    // cell table: heads write start, tails write end (both find-or-insert, so no ordering race)
-    const uint32_t key = keys[t];
-    const bool head = (t == 0) || (keys[t - 1] != key);
-    const bool tail = (t == nb - 1) || (keys[t + 1] != key);
-    if (head || tail) {
-        uint32_t h = key * 0x9E3779B1u;
-        uint32_t slot = (h ^ (h >> 15)) & w.cell_mask;
-        while (true) {
-            const uint32_t prev = atomicCAS(&w.cell_tab[slot].x, kEmptyKey, key);
-            if (prev == kEmptyKey || prev == key) break;
-            slot = (slot + 1) & w.cell_mask;
-        }
-        if (head) w.cell_tab[slot].y = (uint32_t)t;
-        if (tail) w.cell_tab[slot].z = (uint32_t)t + 1u;
-    }
-}
-
+// Counting sort by cell.  The cell table is open-addressed by slot = key while the key fits the table (keys are
+// anchored at the world's smallest cell, so a 100^3-cube pile has 18-bit keys against a 2^21-slot table: every
+// cell owns its slot, no probing, and slot order is Morton order); the bits above the table size are hashed
+// in, so huge or batched worlds (30-bit keys) spread instead of aliasing.
 __device__ __forceinline__ uint32_t cell_slot(const DeviceWorld &w, uint32_t key)
 {
-    const uint32_t h = key * 0x9E3779B1u;
-    return (h ^ (h >> 15)) & w.cell_mask;
+    const uint32_t hi = key >> w.cell_bits;
+    return (key ^ (hi * 0x9E3779B1u)) & w.cell_mask;
 }
+
+__global__ void __launch_bounds__(256) cell_insert_kernel(DeviceWorld w)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= live_nb(w)) return;
+    const uint32_t key = w.key[0][i];
+    uint32_t slot = cell_slot(w, key);
+    while (true) {
+        const uint32_t prev = atomicCAS(&w.cell_tab[slot].x, kEmptyKey, key);
+        if (prev == kEmptyKey || prev == key) break;
+        slot = (slot + 1) & w.cell_mask;
+    }
+    w.val[0][i] = slot;
+    w.val[1][i] = atomicAdd(&w.cell_count[slot], 1u);     // rank inside the cell (arbitrary, see the emit pass)
+}
+
+__global__ void __launch_bounds__(256) cell_scatter_kernel(DeviceWorld w)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= live_nb(w)) return;
+    const uint32_t slot = w.val[0][i], rank = w.val[1][i];
+    const uint32_t start = w.cell_count[slot];            // scanned: first sorted position of the cell
+    const uint32_t t = start + rank;
+    float4 lo = w.aabb_lo[i], hi = w.aabb_hi[i];
+    lo.w = __int_as_float(i);
+    hi.w = __int_as_float(w.world_id ? w.world_id[i] : 0);
+    w.sbox[2 * (size_t)t] = lo;
+    w.sbox[2 * (size_t)t + 1] = hi;
+    w.key[1][t] = w.key[0][i];                            // keys in cell order
+    w.pair_fill[t] = 0u;                                  // pair-slot cursors of the counting pass
+    if (rank == 0) {
+        w.cell_tab[slot].y = start;
+        w.cell_tab[slot].z = w.cell_count[slot + 1];
+    }
+}
+
 __device__ __forceinline__ bool cell_lookup(const DeviceWorld &w, uint32_t key, uint32_t &start, uint32_t &end)
 {
     uint32_t slot = cell_slot(w, key);
@@ -423,9 +337,8 @@ __global__ void __launch_bounds__(128, NANS_PC_MINBLOCKS) pair_count_kernel(Devi
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     const int nb_live = live_nb(w);
     if (t >= nb_live) return;
-    const int fb = sorted_buf(w);
-    const uint32_t *__restrict__ keys = w.key[fb];
-    uint32_t *__restrict__ fill = w.key[fb ^ 1];
+    const uint32_t *__restrict__ keys = w.key[1];
+    uint32_t *__restrict__ fill = w.pair_fill;
     const float4 alo = w.sbox[2 * (size_t)t], ahi = w.sbox[2 * (size_t)t + 1];
     const int row = __float_as_int(alo.w);
     const int wid = __float_as_int(ahi.w);
@@ -540,12 +453,12 @@ __global__ void __launch_bounds__(128) pair_emit_kernel(DeviceWorld w)
 {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= live_nb(w)) return;
-    const uint32_t *__restrict__ keys = w.key[sorted_buf(w)];
+    const uint32_t *__restrict__ keys = w.key[1];
     const float4 alo = w.sbox[2 * (size_t)t], ahi = w.sbox[2 * (size_t)t + 1];
     const int row = __float_as_int(alo.w);
     if (row >= w.n_owned) {
         if (t == 0) {
-            const uint32_t total = w.pair_count[(size_t)5 * w.nb];
+            const uint32_t total = w.pair_count[(size_t)w.n_seg * w.nb];
             w.counters->n_pairs = (int32_t)min(total, (uint32_t)w.max_pairs);
             if (total > (uint32_t)w.max_pairs) atomicOr(&w.counters->overflow, OVF_PAIRS);
         }
@@ -590,7 +503,7 @@ __global__ void __launch_bounds__(128) pair_emit_kernel(DeviceWorld w)
         }
     }
     if (t == 0) {
-        const uint32_t total = w.pair_count[(size_t)5 * w.nb];
+        const uint32_t total = w.pair_count[(size_t)w.n_seg * w.nb];
         w.counters->n_pairs = (int32_t)min(total, cap);
         if (total > cap) atomicOr(&w.counters->overflow, OVF_PAIRS);
     }
@@ -619,32 +532,21 @@ int launch_broadphase(World *w)
     key_kernel<<<div_up(nb, 256), 256, 0, s>>>(d);
     NANS_LAUNCH_CHECK();
 
-    // radix sort on key[0]/val[0] <-> key[1]/val[1]; up to 4 passes of 8 bits, the top ones skipped on
-    // the device when the step's largest key has no bits there
-    const int n_blocks = div_up(nb, kRadixTile);
-    const int32_t *max_key = &d.counters->pad[kMaxKey];
-    radix_plan_kernel<<<1, 32, 0, s>>>(d, 256 * n_blocks);
+    // counting sort by cell: table + cell sizes cleared, insert, scan, scatter
+    const size_t table = (size_t)d.cell_mask + 1;
+    NANS_CUDA(cudaMemsetAsync(d.cell_tab, 0xff, sizeof(uint4) * table, s));
+    NANS_CUDA(cudaMemsetAsync(d.cell_count, 0, sizeof(uint32_t) * (table + 1), s));
+    cell_insert_kernel<<<div_up(nb, 256), 256, 0, s>>>(d);
     NANS_LAUNCH_CHECK();
-    for (int pass = 0; pass < 4; ++pass) {
-        const int src = pass & 1, dst = src ^ 1;
-        radix_hist_kernel<<<n_blocks, kRadixThreads, 0, s>>>(d.key[src], nb, pass * 8, d.radix_hist, n_blocks, max_key, d.live);
-        NANS_LAUNCH_CHECK();
-        int rc = pass == 0 ? exclusive_scan_u32(d.radix_hist, d.radix_hist, 256 * n_blocks, d.scan_block, s)
-                           : exclusive_scan_u32_dn(d.radix_hist, d.radix_hist, 256 * n_blocks,
-                                                   &d.counters->pad[kPassLen + pass - 1], 0, d.scan_block, s);
-        if (rc) return rc;
-        radix_scatter_kernel<<<n_blocks, kRadixThreads, 0, s>>>(d.key[src], d.val[src], d.key[dst], d.val[dst],
-                                                                nb, pass * 8, d.radix_hist, n_blocks, max_key, d.live);
-        NANS_LAUNCH_CHECK();
-    }
-    NANS_CUDA(cudaMemsetAsync(d.cell_tab, 0xff, sizeof(uint4) * ((size_t)d.cell_mask + 1), s));
-    gather_sorted_kernel<<<div_up(nb, 256), 256, 0, s>>>(d);
+    int rc = exclusive_scan_u32(d.cell_count, d.cell_count, (int)table + 1, d.scan_block, s);
+    if (rc) return rc;
+    cell_scatter_kernel<<<div_up(nb, 256), 256, 0, s>>>(d);
     NANS_LAUNCH_CHECK();
-    // counts and slot cursors are accumulated with atomics; the cursors live in the sort's spare key buffer (zeroed by the gather)
-    NANS_CUDA(cudaMemsetAsync(d.pair_count, 0, sizeof(uint32_t) * ((size_t)5 * nb + 1), s));
+    // counts per (type, body) are accumulated with atomics; a cube-only world only has the CC and CF segments
+    NANS_CUDA(cudaMemsetAsync(d.pair_count, 0, sizeof(uint32_t) * ((size_t)d.n_seg * nb + 1), s));
     pair_count_kernel<<<div_up(nb, 128), 128, 0, s>>>(d);
     NANS_LAUNCH_CHECK();
-    int rc = exclusive_scan_u32(d.pair_count, d.pair_count, 5 * nb + 1, d.scan_block, s);
+    rc = exclusive_scan_u32(d.pair_count, d.pair_count, d.n_seg * nb + 1, d.scan_block, s);
     if (rc) return rc;
     pair_emit_kernel<<<div_up(nb, 128), 128, 0, s>>>(d);
     NANS_LAUNCH_CHECK();

@@ -10,34 +10,31 @@
 //
 // accumulate_literal   the reference's statements one by one (used when an increment is NaN, and as the
 //                      fallback and the test oracle of the fast form).
-// accumulate_fast      same bits without the two fp64 conversions per iteration that bound the literal loop
-//                      (XU pipe; the solver's critical path is depth x this loop).  M_k is only needed exactly
-//                      where it decides a result bit, so iterations 1..68 carry each tangent sum as an
-//                      INTERVAL [tl, th] under the rigorous fp32 bounds
-//                          lo_k = fl(cLo * N_k) <= M_k <= fl(cHi * N_k) = hi_k,
-//                      cLo / cHi = the floats just below / above the fp64 friction constant (cLo * N_k is
-//                      exact in fp64 and both roundings are monotone, hence the inequalities), and iterations
-//                      69 and 70 use the exact M_k.  fl(x + LT) and the clamp are monotone in x, the clamp is
-//                      monotone in M on either side of zero, so the true sum always lies in the interval.  A
-//                      contact is in practice either never clamped (the interval stays a point) or clamped
-//                      every iteration (it collapses to +-M_69, +-M_70 at the end); if an interval is still
-//                      open after iteration 70, or both sums are zero (sign of zero undecided), the literal
-//                      loop is run instead.  Closed forms: LN <= 0 keeps N = M = 0 and gives all deltas +0;
-//                      LT = +-0 keeps T = +0.
+// accumulate_pipelined the same with min/max and the fp64 bound software-pipelined ahead of the tangent chains
+//                      (round 1's kernel form): ~43 cycles per iteration, bound by the two fp64 <-> fp32
+//                      conversions (XU pipe) and the FADD -> FMNMX -> FMNMX chain of a tangent sum.
+// accumulate_fast      same bits from THREE PLAIN FADD CHAINS (round 2).  With LN > 0 the normal sum never
+//                      clamps, and a tangent is, for all 70 iterations, in one of two regimes that one compare
+//                      against LN decides:
+//                        free      |LT| <= (1 - 1e-4) c LN : the clamp never fires, T_k is the running sum of LT;
+//                        saturated |LT| >= (1 + 2e-3) c LN : the clamp fires every iteration, T_k = sign(LT) M_k,
+//                                                            so only M_69 and M_70 are needed (two fp64 bounds);
+//                      c = sqrt(2) * 0.1.  Proof sketch: k fp32 additions of a constant stay within a relative
+//                      k * 2^-24 (< 4.2e-6 for k <= 70) of k * L, and M_k within 2^-24 of c N_k, so the ratio
+//                      |T_k| / M_k stays within 1.3e-5 of |LT| / (c LN) while unclamped (free), and
+//                      M_(k-1) + |LT| >= M_k (1 + 4e-4) by induction when saturated; LN is required to lie in
+//                      [1e-30, 1e30] so that nothing under- or overflows.  Anything else (the 0.2 % band around
+//                      saturation, extreme magnitudes) runs the pipelined form.  Closed forms: LN <= 0 keeps
+//                      N = M = 0 and gives all deltas +0.
 // tests/test_solver_accum_host.py compiles this header for the host and compares the forms bit for bit
 // over random, borderline and non-finite increments.
-//
-// Measured (B200, 1 M-cube pile, 0 fallbacks in 1.03 M contacts): the fast form is NOT faster in the kernel --
-// apply 3859 vs 3499 cycles per contact.  The hand-pipelined form already hides the fp64 conversions; what
-// bounds both is the FADD -> FMNMX -> FMNMX chain of a tangent sum (the same in both) and issue slots, of
-// which the interval form needs 15 per iteration against 11.  It stays as the host-checked alternative.
 #pragma once
 #include "nans_math.cuh"
 
 namespace nans {
 
 #ifndef NANS_ACCUM_FAST
-#define NANS_ACCUM_FAST 0   // measured on the 1 M-cube pile: fast form 0.385 ms solver stage, pipelined form 0.372 ms (see below)
+#define NANS_ACCUM_FAST 1   // 0: the pipelined form for every contact (round 1)
 #endif
 
 struct AccumDeltas { float DLN, DLT1, DLT2; };
@@ -114,24 +111,9 @@ __device__ __forceinline__ AccumDeltas accumulate_pipelined(float lambdaN, float
     return r;
 }
 
-// one tangent sum as an interval: the true sum stays inside [tl, th]
-struct TanInterval {
-    float tl, th;
-    __device__ __forceinline__ void step(float lt, float lo, float hi)
-    {
-        tl = fminf(fmaxf(fadd(tl, lt), -hi), lo);
-        th = fmaxf(fminf(fadd(th, lt), hi), -lo);
-    }
-};
-
-// true: DLT is decided.  (old, now) = the intervals after iterations 69 and 70.
-__device__ __forceinline__ bool tangent_delta(float lt, const TanInterval &old, const TanInterval &now, float &DLT)
-{
-    DLT = fsub(now.tl, old.tl);
-    if (lt == 0.0f) { DLT = 0.0f; return true; }     // T stays +0 (NaN increments never get here)
-    // a point interval away from zero has one bit pattern; x - (+-0) and (+-0) - x do not depend on the zero's sign
-    return old.tl == old.th && now.tl == now.th && (old.tl != 0.0f || now.tl != 0.0f);
-}
+// c (1 - 1e-4) rounded down and c (1 + 2e-3) rounded up, c = sqrt(2) * (double)0.1f = 0.14142135834465...
+#define NANS_KFRIC_FREE 0.1414071f
+#define NANS_KFRIC_SAT 0.1417043f
 
 // Requires: no NaN among the increments.
 __device__ __forceinline__ AccumDeltas accumulate_fast(float lambdaN, float lambdaT1, float lambdaT2)
@@ -141,29 +123,32 @@ __device__ __forceinline__ AccumDeltas accumulate_fast(float lambdaN, float lamb
         r.DLN = r.DLT1 = r.DLT2 = 0.0f;
         return r;
     }
-    // lambdaN > 0: the sum never goes negative, the max(., 0) of the reference is the identity
-    float sumN = 0.f;
-    TanInterval t1 = {0.f, 0.f}, t2 = {0.f, 0.f};
-#pragma unroll 4
-    for (int it = 0; it < 68; ++it) {
-        sumN = fadd(sumN, lambdaN);
-        const float lo = fmul(NANS_KFRIC_LO, sumN), hi = fmul(NANS_KFRIC_HI, sumN);
-        t1.step(lambdaT1, lo, hi);
-        t2.step(lambdaT2, lo, hi);
-    }
-    const float n69 = fadd(sumN, lambdaN), n70 = fadd(n69, lambdaN);
-    const float m69 = friction_bound(n69), m70 = friction_bound(n70);
-    t1.step(lambdaT1, m69, m69); t2.step(lambdaT2, m69, m69);
-    const TanInterval o1 = t1, o2 = t2;
-    t1.step(lambdaT1, m70, m70); t2.step(lambdaT2, m70, m70);
-    r.DLN = fsub(n70, n69);
-    const bool ok1 = tangent_delta(lambdaT1, o1, t1, r.DLT1);
-    const bool ok2 = tangent_delta(lambdaT2, o2, t2, r.DLT2);
-    if (!(ok1 && ok2)) {
+    const float a1 = fabsf(lambdaT1), a2 = fabsf(lambdaT2);
+    const float lim_free = fmul(NANS_KFRIC_FREE, lambdaN), lim_sat = fmul(NANS_KFRIC_SAT, lambdaN);
+    const bool free1 = a1 <= lim_free, free2 = a2 <= lim_free;
+    const bool ok = lambdaN >= 1e-30f && lambdaN <= 1e30f && (free1 || a1 >= lim_sat) && (free2 || a2 >= lim_sat);
+    if (!ok) {
 #ifdef NANS_ACCUM_ON_FALLBACK
         NANS_ACCUM_ON_FALLBACK;
 #endif
-        return accumulate_literal(lambdaN, lambdaT1, lambdaT2);
+        return accumulate_pipelined(lambdaN, lambdaT1, lambdaT2);
+    }
+    // three independent chains of plain additions (a saturated tangent's chain is computed and ignored: no branch)
+    float n = 0.f, t1 = 0.f, t2 = 0.f;
+#pragma unroll 23
+    for (int it = 0; it < 69; ++it) {
+        n = fadd(n, lambdaN);
+        t1 = fadd(t1, lambdaT1);
+        t2 = fadd(t2, lambdaT2);
+    }
+    const float n70 = fadd(n, lambdaN);
+    r.DLN = fsub(n70, n);
+    r.DLT1 = fsub(fadd(t1, lambdaT1), t1);
+    r.DLT2 = fsub(fadd(t2, lambdaT2), t2);
+    if (!(free1 && free2)) {
+        const float m69 = friction_bound(n), m70 = friction_bound(n70);
+        if (!free1) r.DLT1 = lambdaT1 < 0.0f ? fsub(-m70, -m69) : fsub(m70, m69);
+        if (!free2) r.DLT2 = lambdaT2 < 0.0f ? fsub(-m70, -m69) : fsub(m70, m69);
     }
     return r;
 }

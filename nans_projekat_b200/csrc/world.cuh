@@ -30,12 +30,12 @@ struct Counters {
     int32_t max_epa_faces;
     int32_t frontier_n[3];   // solver: [0] sweep tickets issued, [1] number of runs
     int32_t pad[11];         // [0] narrowphase work counter, [1] solver abort flag (watchdog), [2] max AABB extent bits,
-                             // [3] largest Morton key, [4..6] histogram length of sort passes 1..3 (0 = skipped),
+                             // [3..6] unused,
                              // [7..9] smallest AABB centre per axis (order-encoded, complemented: 0 = none yet),
                              // [10] slab error bits (SLAB_ERR_*)
 };
 
-constexpr int kMaxKey = 3, kPassLen = 4, kMinCentre = 7;   // Counters::pad slots used by the broadphase
+constexpr int kMinCentre = 7;                              // Counters::pad slots used by the broadphase
 constexpr int kSlabErr = 10;                               // Counters::pad slot of the slab error bits
 enum { SLAB_ERR_HALO_CAP = 1,      // more halo bodies than the fixed-capacity message holds
        SLAB_ERR_NOT_ADJACENT = 2 };// an owned body reaches into the box of a rank other than the lower neighbour
@@ -64,13 +64,16 @@ struct DeviceWorld {
     float4 *st_aabb;   // [n_statics][2]
     // --- broadphase
     float4 *aabb_lo, *aabb_hi;          // [nb] by body row
-    uint32_t *key[2];                   // Morton cell keys (double buffer for the radix sort)
-    uint32_t *val[2];                   // body rows
-    uint32_t *radix_hist;               // [256 * radix_blocks]
-    uint4 *cell_tab;                    // hash table of cells: {key, first sorted position, one past last, -}
+    uint32_t *key[2];                   // Morton cell keys: [0] by body row, [1] in cell order
+    uint32_t *val[2];                   // counting sort: [0] the body's cell slot, [1] its rank inside the cell
+    uint32_t *cell_count;               // [table + 1] bodies per cell slot -> (scanned) first sorted position of the cell
+    uint32_t *pair_fill;                // [nb] pair-slot cursors of the counting pass (by sorted position)
+    uint4 *cell_tab;                    // open-addressed table of cells: {key, first sorted position, one past last, -}
     float4 *sbox;                       // [2*nb] Morton-ordered AABB records {lo.xyz,row}{hi.xyz,world}
     uint32_t *pair_tmp;                 // [nb * 24] partner slots filled by the counting pass
     uint32_t cell_mask;                 // table size - 1
+    int32_t cell_bits;                  // log2(table size)
+    int32_t n_seg;                      // pair segments in use: 2 (CC, CF) for a cube-only world, else 5
     uint32_t *pair_count;               // [5 * nb + 1] per (type, body) candidate counts -> offsets
     int32_t *pair_a, *pair_b;           // [max_pairs] body rows; static k encoded as -(k+1)
     float cell_size;                    // >= largest body AABB extent (fixed at upload)

@@ -162,13 +162,15 @@ def cube_pile_slabs(n_slabs=2, side_x=100, ny=100, nz=100, seed=7, spacing=1.02,
     SLAB-MAJOR: slab r (x in [r*side_x, (r+1)*side_x)) holds the contiguous global indices
     [r*m, (r+1)*m), m = side_x*ny*nz, ordered inside like :func:`cube_pile` (layer by layer).  Contiguous index
     ranges are therefore spatial x-slabs, which is what csrc/slab.cu's exact decomposition needs.  ``slab=r``
-    returns only that slab's bodies (each slab draws its jitter from its own stream, so a rank can build its share
-    without the rest); the floor slab spans the whole pile either way."""
+    returns only that slab's bodies.  Every slab carries the SAME jitter pattern (the stream of ``cube_pile(seed)``),
+    so a rank can build its share without the rest and every slab behaves like the single-GPU pile of that seed --
+    how long a pile survives the reference's unstable one-pass solver depends on the jitter, and a
+    slab that blows up early would make the halo exchange fail (loudly).  The floor spans the whole pile."""
     m = side_x * ny * nz
     which = range(n_slabs) if slab is None else [slab]
     s = Scene(m * len(which), 0, 1)
     for k, r in enumerate(which):
-        rng = np.random.default_rng([seed, r])
+        rng = np.random.default_rng(seed)
         s.pos[k * m:(k + 1) * m] = _lattice(m, (side_x, ny, nz), spacing, jitter, rng,
                                             (0.5 + r * side_x * spacing, 0.52, 0.5))
     s.mass[:] = 1.0

@@ -82,3 +82,20 @@ def test_special_values(accum):
     x = _logu(rng, 50_000); x[::7] = np.nan
     y = _logu(rng, 50_000); y[::11] = np.nan
     _compare(accum, x, y, _logu(rng, 50_000), "NaN increments take the literal loop")
+
+
+def test_regime_thresholds(accum):
+    """accumulate_fast decides free / saturated by one compare against LN: increments within a few ulps of both
+    thresholds (where the chains run closest to the clamp), across the magnitude guards 1e-30 / 1e30, and the
+    band in between (pipelined fallback) must all give the literal loop's bits."""
+    rng = np.random.default_rng(7)
+    n = 1_000_000
+    for lo, hi in ((-99, -95), (-40, 40), (95, 101)):       # around 1e-30, the bulk, around 1e30
+        ln = (2.0 ** rng.uniform(lo, hi, n)).astype(np.float32)
+        for c in (0.1414071, 0.1417043, 0.14142136, 0.1413, 0.1420):
+            lt = (np.float32(c) * ln).astype(np.float32)
+            lt = (lt.view(np.int32) + rng.integers(-4, 5, n).astype(np.int32)).view(np.float32)
+            lt = np.where(np.isfinite(lt), lt, np.float32(1.0)) * rng.choice([-1, 1], n).astype(np.float32)
+            _compare(accum, ln, lt, lt[::-1].copy(), f"threshold {c} 2^[{lo},{hi}]")
+    ln = np.abs(_logu(rng, n, -20, 20))
+    _compare(accum, ln, ln * np.float32(0.05), -ln * np.float32(3.0), "free + saturated", 1e-6)

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """profiles/ncu_traffic.json from an `ncu --set full ... --page raw --csv` dump of one step: per kernel the DRAM
 bytes of its largest launch (bench.py's roofline.traffic) and, for the FP32-bound narrowphase, the pipe
-utilisation figures north_star asks for.  usage: python tools/ncu_traffic.py raw.csv "source description" > json"""
+utilisation figures north_star asks for.  usage: python tools/ncu_traffic.py raw.csv "source description" workload_name > json"""
 import csv, json, sys
 
 rows = list(csv.reader(open(sys.argv[1])))
@@ -27,5 +27,6 @@ for r in rows[2:]:
         }
 keep = ("narrowphase_world_kernel", "solve_versioned_kernel", "pair_count_kernel")
 print(json.dumps({"source": sys.argv[2] if len(sys.argv) > 2 else sys.argv[1],
+                  "workload": sys.argv[3] if len(sys.argv) > 3 else None,   # bench.py only uses the capture for this workload
                   "dram_bytes_per_launch": dram,
                   "pipes": {k: pipes[k] for k in keep if k in pipes}}, indent=1))

@@ -25,6 +25,12 @@ for k in range(12):
 w.restore()
 for k in range(3):
     w.step_profiled(dt)
+w.set_solver("shuffled")          # throughput sweep order (solve_versioned_kernel<true, false>)
+for k in range(3):
+    w.step(dt)
+w.set_solver("exact")
+w.step(np.float32(1 / 50.))       # another dt: the captured graph is replayed, dt comes from device memory
+m = w.models()
 st = w.stats()
 c = w.contacts(); a, b = w.pairs(); d = w.download()
 q = scenes.narrowphase_pairs(2048, seed=3)
