@@ -160,20 +160,6 @@ __global__ void pack_vec3_kernel(const float4 *__restrict__ src, float *__restri
     const float4 v = src[i];
     dst[3 * i] = v.x; dst[3 * i + 1] = v.y; dst[3 * i + 2] = v.z;
 }
-// up to 7 fields in ONE pass, written straight into the caller's pinned (device-mapped) host buffers: no staging
-// slot, no per-field memcpy -- the stores travel over PCIe as the kernel produces them
-struct PackMany { const float4 *src[7]; float *dst[7]; int n_fields; };
-__global__ void __launch_bounds__(256) pack_vec3_many_kernel(PackMany p, int n)
-{
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-#pragma unroll 1
-    for (int k = 0; k < p.n_fields; ++k) {
-        const float4 v = p.src[k][i];
-        float *d = p.dst[k] + 3 * (size_t)i;
-        d[0] = v.x; d[1] = v.y; d[2] = v.z;
-    }
-}
 // which: 0 mass -> pos.w, vel.w = 1/m ; 1 moi -> ang.w, angvel.w = 1/moi ; 2 radius -> scale.w
 __global__ void unpack_scalar_kernel(const float *__restrict__ src, DeviceWorld w, int which)
 {
@@ -416,27 +402,9 @@ int nans_world_download(nans_world *h, nans_scene_view *sc)
     float *vdst[7] = {sc->pos, sc->vel, sc->force, sc->ang, sc->angvel, sc->torque, sc->scale};
     const float4 *vsrc[7] = {d.pos, d.vel, d.force, d.ang, d.angvel, d.torque, d.scale};
     if (w->io.init) { NANS_CUDA(cudaStreamSynchronize(w->io.up)); NANS_CUDA(cudaStreamSynchronize(w->io.down)); }
-    // zero-copy path: every requested [nb][3] field lives in pinned, device-mapped host memory
-    bool direct = nb > 0;
-    PackMany pm;
-    pm.n_fields = 0;
-    for (int k = 0; k < 7 && direct; ++k) {
-        if (!vdst[k]) continue;
-        cudaPointerAttributes at;
-        if (cudaPointerGetAttributes(&at, vdst[k]) != cudaSuccess || at.type != cudaMemoryTypeHost || !at.devicePointer) {
-            cudaGetLastError();
-            direct = false;
-            break;
-        }
-        pm.src[pm.n_fields] = vsrc[k];
-        pm.dst[pm.n_fields] = (float *)at.devicePointer;
-        ++pm.n_fields;
-    }
-    if (direct && pm.n_fields > 0) {
-        pack_vec3_many_kernel<<<grid, 256, 0, s>>>(pm, nb);
-        NANS_LAUNCH_CHECK();
-        for (int k = 0; k < 7; ++k) vdst[k] = nullptr;       // done
-    }
+    // (writing the packed rows straight into the caller's pinned, device-mapped buffers from one fused kernel -- no
+    // staging slot, no memcpy -- was measured in round 2: 12-byte-stride stores over PCIe, end-to-end throughput
+    // fell from 5.4e8 to 1.8e8 body-steps/s; the staged copy below stays)
     if (nb > 0) {
         for (int k = 0; k < 7; ++k) {
             if (!vdst[k]) continue;

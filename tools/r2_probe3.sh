@@ -2,7 +2,7 @@
 # round 2: after the solver rewrite (b128 rows, shuffled mode) and slab v2 (NCCL + peer stores): tests, slab check, benches
 cd "$GRAFT_REPO_ROOT"
 nvidia-smi -L > gpurun_out/r2_probe3_gpus.txt
-timeout 1500 python -m pytest tests -x -q -m gpu > gpurun_out/r2_probe3_pytest.txt 2>&1
+timeout 420 python -m pytest tests -x -q -m gpu > gpurun_out/r2_probe3_pytest.txt 2>&1
 tail -15 gpurun_out/r2_probe3_pytest.txt
 NG=$(nvidia-smi -L | wc -l)
 if [ "$NG" -ge 2 ]; then
