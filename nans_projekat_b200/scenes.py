@@ -165,7 +165,7 @@ def cube_pile_slabs(n_slabs=2, side_x=100, ny=100, nz=100, seed=7, spacing=1.02,
     returns only that slab's bodies.  Every slab carries the SAME jitter pattern (the stream of ``cube_pile(seed)``),
     so a rank can build its share without the rest and every slab behaves like the single-GPU pile of that seed --
     how long a pile survives the reference's unstable one-pass solver depends on the jitter, and a
-    slab that blows up early would make the halo exchange fail (loudly).  The floor spans the whole pile."""
+    slab that blows up early would make the halo exchange fail (loudly)."""
     m = side_x * ny * nz
     which = range(n_slabs) if slab is None else [slab]
     s = Scene(m * len(which), 0, 1)
@@ -176,9 +176,18 @@ def cube_pile_slabs(n_slabs=2, side_x=100, ny=100, nz=100, seed=7, spacing=1.02,
     s.mass[:] = 1.0
     s.moi[:] = F32(F32(1.0) / F32(12.0)) * F32(2.0)
     s.scale[:] = 1.0
-    ext_x, ext_z = n_slabs * side_x * spacing, nz * spacing
-    size = float(2 ** np.ceil(np.log2(max(ext_x, ext_z) + 16.0)))
-    s.set_static(0, (ext_x / 2 + 0.13, -0.5, ext_z / 2 + 0.07), (size, 1.0, size), size_for_moi=size)
+    # the floor: one static tile per slab, as wide as the slab (a single 1024-wide slab under an 8-slab pile puts
+    # the reference's GJK/EPA far outside the range it behaves in: cubes 400 units from the floor's centre start
+    # it almost parallel to the floor, and that pile blew apart by step 50).  Every rank holds all the tiles.
+    w_x, ext_z = side_x * spacing, nz * spacing
+    size_z = float(2 ** np.ceil(np.log2(ext_z + 16.0)))
+    s.n_statics = n_slabs
+    for f, shape in (("st_pos", 3), ("st_ang", 3), ("st_scale", 3)):
+        setattr(s, f, np.zeros((n_slabs, shape), F32))
+    s.st_mass, s.st_moi = np.ones(n_slabs, F32), np.ones(n_slabs, F32)
+    s.st_verts = np.zeros((n_slabs, 8, 3), F32)
+    for r in range(n_slabs):
+        s.set_static(r, ((r + 0.5) * w_x, -0.5, ext_z / 2 + 0.07), (w_x, 1.0, size_z), size_for_moi=size_z)
     return s
 
 
