@@ -374,11 +374,13 @@ def run_c3(n_pairs, device, n_check, reps=3):
     return res
 
 
-SLAB_SHAPE = dict(side_x=250, ny=16, nz=250, settle=40)   # 1M cubes per GPU; the window [40, 60) lies before the blow-up on every slab
+# 1M cubes per GPU; steps [25, 40): 0.6-1.0 contacts per body and before the blow-up on every one of 8 slabs (the
+# CPU oracle stepping the same 8M-cube world: all slabs calm at step 40, the outer ones gone by step 48)
+SLAB_SHAPE = dict(side_x=125, ny=16, nz=500, settle=25, window=15)
 
 
 def slab_record(args, rank, local, size, dist, reduce_max, barrier, warmup):
-    """Config C5: ONE world of size x 1M cubes in x-slabs (250 x 16 x 250 cubes per GPU), NCCL halo exchange +
+    """Config C5: ONE world of size x 1M cubes in x-slabs (125 x 16 x 500 cubes per GPU), NCCL halo exchange +
     cross-GPU dataflow solve over NVLink peer memory (csrc/slab.cu), exact reference order.  Weak scaling of one
     world: efficiency = ms/step of one GPU stepping ONE slab alone (same scene, same window, measured here on
     every rank, max taken) / ms/step of N GPUs stepping the N-slab world.  The flat shape is used because how
@@ -388,10 +390,9 @@ def slab_record(args, rank, local, size, dist, reduce_max, barrier, warmup):
     from nans_projekat_b200 import scenes
     from nans_projekat_b200.slab import SlabWorld
     from nans_projekat_b200.world import World
-    side_x, ny, nz, settle = (SLAB_SHAPE[k] for k in ("side_x", "ny", "nz", "settle"))
+    side_x, ny, nz, settle, window = (SLAB_SHAPE[k] for k in ("side_x", "ny", "nz", "settle", "window"))
     m = side_x * ny * nz
-    window = args.window
-    owned = scenes.cube_pile_slabs(n_slabs=size, side_x=side_x, ny=ny, nz=nz, seed=7, slab=rank)
+    owned = scenes.cube_pile_slabs(n_slabs=size, side_x=side_x, ny=ny, nz=nz, seed=7, slab=rank, centre=True)
     stream = torch.cuda.Stream()
 
     def measure(step, restore, sync):

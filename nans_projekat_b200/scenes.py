@@ -157,7 +157,8 @@ def cube_pile(n_side=100, seed=7, spacing=1.02, jitter=0.005, n=None, layers=Non
     return s
 
 
-def cube_pile_slabs(n_slabs=2, side_x=100, ny=100, nz=100, seed=7, spacing=1.02, jitter=0.005, slab=None) -> Scene:
+def cube_pile_slabs(n_slabs=2, side_x=100, ny=100, nz=100, seed=7, spacing=1.02, jitter=0.005, slab=None,
+                    centre=False) -> Scene:
     """Config C5 for several GPUs: ONE pile of ``n_slabs * side_x`` x ``ny`` x ``nz`` unit cubes, numbered
     SLAB-MAJOR: slab r (x in [r*side_x, (r+1)*side_x)) holds the contiguous global indices
     [r*m, (r+1)*m), m = side_x*ny*nz, ordered inside like :func:`cube_pile` (layer by layer).  Contiguous index
@@ -165,14 +166,18 @@ def cube_pile_slabs(n_slabs=2, side_x=100, ny=100, nz=100, seed=7, spacing=1.02,
     returns only that slab's bodies.  Every slab carries the SAME jitter pattern (the stream of ``cube_pile(seed)``),
     so a rank can build its share without the rest and every slab behaves like the single-GPU pile of that seed --
     how long a pile survives the reference's unstable one-pass solver depends on the jitter, and a
-    slab that blows up early would make the halo exchange fail (loudly)."""
+    slab that blows up early would make the halo exchange fail (loudly).  ``centre=True`` puts the middle of the
+    pile's footprint at x = z = 0, which halves the largest coordinate (fp32 resolution there is what seeds the
+    blow-up first)."""
     m = side_x * ny * nz
     which = range(n_slabs) if slab is None else [slab]
     s = Scene(m * len(which), 0, 1)
+    x0 = -0.5 * n_slabs * side_x * spacing if centre else 0.0
+    z0 = -0.5 * nz * spacing if centre else 0.0
     for k, r in enumerate(which):
         rng = np.random.default_rng(seed)
         s.pos[k * m:(k + 1) * m] = _lattice(m, (side_x, ny, nz), spacing, jitter, rng,
-                                            (0.5 + r * side_x * spacing, 0.52, 0.5))
+                                            (x0 + 0.5 + r * side_x * spacing, 0.52, z0 + 0.5))
     s.mass[:] = 1.0
     s.moi[:] = F32(F32(1.0) / F32(12.0)) * F32(2.0)
     s.scale[:] = 1.0
@@ -187,7 +192,7 @@ def cube_pile_slabs(n_slabs=2, side_x=100, ny=100, nz=100, seed=7, spacing=1.02,
     s.st_mass, s.st_moi = np.ones(n_slabs, F32), np.ones(n_slabs, F32)
     s.st_verts = np.zeros((n_slabs, 8, 3), F32)
     for r in range(n_slabs):
-        s.set_static(r, ((r + 0.5) * w_x, -0.5, ext_z / 2 + 0.07), (w_x, 1.0, size_z), size_for_moi=size_z)
+        s.set_static(r, (x0 + (r + 0.5) * w_x, -0.5, z0 + ext_z / 2 + 0.07), (w_x, 1.0, size_z), size_for_moi=size_z)
     return s
 
 

@@ -1,7 +1,7 @@
 #!/bin/bash
 # Build one libnans_b200.so per "name:flags" argument into gpurun_variants/ (offline; nvcc cross-compiles),
 # then restore the default build.  Files whose objects must be rebuilt: all (flags may touch any header).
-# usage: tools/build_variants.sh "base:-DNANS_NP_BOX_EPA=0" "v4:-DNANS_NP_V4=1" ...
+# usage: tools/build_variants.sh "base:" "blk6:-DNANS_NP_MINBLOCKS=6" ...
 cd "$(dirname "$0")/.."
 V=gpurun_variants; mkdir -p $V; rm -f $V/*.so
 C=nans_projekat_b200/csrc

@@ -1,5 +1,5 @@
 #!/bin/bash
-# A/B on the GPU box: bench every library in gpurun_variants/ (built offline, see tools/np_sweep.sh),
+# A/B on the GPU box: bench every library in gpurun_variants/ (built offline by tools/build_variants.sh),
 # then optionally run the GPU tests and one ncu --set full capture of a kernel with the default library.
 # usage: tools/gpu_ab.sh [--tests] [--ncu KERNEL_REGEX NAME] [--workload W]
 cd "$(dirname "$0")/.."
@@ -36,6 +36,6 @@ if [ $TESTS = 1 ]; then
 fi
 if [ -n "$NCU" ]; then
   timeout 600 ncu --set full --clock-control none --import-source on --profile-from-start off -k "regex:$NCU" -c 1 \
-      -f -o gpurun_out/$NAME python tools/profile_step.py 1000000 250 45 1 > gpurun_out/$NAME.log 2>&1
+      -f -o gpurun_out/$NAME python tools/profile_step.py 1000000 100 85 1 > gpurun_out/$NAME.log 2>&1
   ls -la gpurun_out/$NAME.ncu-rep
 fi
