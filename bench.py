@@ -374,9 +374,10 @@ def run_c3(n_pairs, device, n_check, reps=3):
     return res
 
 
-# 1M cubes per GPU; steps [25, 40): 0.6-1.0 contacts per body and before the blow-up on every one of 8 slabs (the
-# CPU oracle stepping the same 8M-cube world: all slabs calm at step 40, the outer ones gone by step 48)
-SLAB_SHAPE = dict(side_x=125, ny=16, nz=500, settle=25, window=15)
+# 1M cubes per GPU; steps [10, 25): 0.2-0.6 contacts per body (the pile compacting from the floor) and well before the
+# blow-up on every slab: the CPU oracle stepping the same 8M-cube world sees every slab calm at step 30 and the first
+# one gone by step 35 (WHEN a pile blows apart under the reference's solver is chaotic)
+SLAB_SHAPE = dict(side_x=125, ny=16, nz=500, settle=10, window=15)
 
 
 def slab_record(args, rank, local, size, dist, reduce_max, barrier, warmup):
@@ -430,13 +431,19 @@ def slab_record(args, rank, local, size, dist, reduce_max, barrier, warmup):
     sw.world.synchronize()
     sw.world.snapshot()
     ms = measure(lambda: sw.step(DT), sw.world.restore, sw.world.synchronize)
-    st = sw.status()            # raises if the exchange pattern was violated (the world would not be exact)
-    ws = sw.world.stats()
+    try:                        # the exchange pattern violated (an exploded pile): the world would not be exact
+        st, err = sw.status(), None
+    except Exception as ex:
+        st, err = {"ghosts": -1, "halo_message_bytes": 0}, str(ex)
+    ws = sw.world.stats(strict=False)
     info = [None] * size
     dist.all_gather_object(info, {"ghosts": st["ghosts"], "contacts": ws["n_contacts"], "pairs": ws["n_pairs"],
-                                  "solver_levels": ws["solver_levels"]})
+                                  "solver_levels": ws["solver_levels"], "error": err})
     sw.close()
     torch.cuda.empty_cache()
+    if any(i["error"] for i in info):
+        return {"workload": f"cube_pile_{size}M_one_world", "error": [i["error"] for i in info if i["error"]][0],
+                "note": "the timed numbers are withheld: a step whose exchange was refused is not a valid step"}
     return {"workload": f"cube_pile_{size}M_one_world ({size * side_x}x{ny}x{nz} cubes in {size} x-slabs, config C5)",
             "bodies": size * m, "n_gpus": size, "ms_per_step": ms, "body_steps_per_s": size * m / (ms * 1e-3),
             "scaling": "weak (one world grows with the GPU count: 1M cubes per GPU)",
