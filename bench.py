@@ -422,7 +422,7 @@ def slab_record(args, rank, local, size, dist, reduce_max, barrier, warmup):
     del alone
     torch.cuda.empty_cache()
 
-    halo_cap = 4 * ny * nz
+    halo_cap = 3 * ny * nz          # three face layers (one is in use while the pile stands)
     sw = SlabWorld(owned, rank, size, dist, local, gid_base=rank * m, halo_cap=halo_cap, capacity=m + halo_cap,
                    stream=stream.cuda_stream)
     sw.rebuild_vertices()

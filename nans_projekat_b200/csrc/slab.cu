@@ -122,6 +122,9 @@ struct SlabState {
     int32_t *h_status;         // pinned: {err, live, sent count}
     void *peer_base;           // the upper neighbour's arena, opened through CUDA IPC
     size_t halo_floats;        // floats per message
+    cudaGraphExec_t graph;     // the whole step (NCCL calls included), captured on the second call
+    int graph_state;           // 0 first call pending, 1 eager step done, 2 captured, -1 capture not possible
+    unsigned graph_launches;
 };
 
 struct IpcBlob {               // what nans_slab_ipc_handle hands out (128 bytes)
@@ -252,6 +255,7 @@ void slab_destroy(World *w)
 {
     SlabState *S = state(w);
     if (!S) return;
+    if (S->graph) cudaGraphExecDestroy(S->graph);
     if (S->peer_base) cudaIpcCloseMemHandle(S->peer_base);
     if (S->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(S->comm);
     if (S->blk) cudaFree(S->blk);
@@ -364,19 +368,15 @@ int nans_slab_connect(nans_world *h, const void *handles)
     return NANS_OK;
 }
 
-// One step of this rank's share of the world, exchanges included; asynchronous on the world's stream.
-int nans_slab_step(nans_world *h, float dt)
+// everything of one step except dt (which travels through device memory, so the captured graph does not depend on it)
+static int slab_step_body(World *w)
 {
-    World *w = reinterpret_cast<World *>(h);
-    if (!w || !w->slab) { snprintf(g_err, sizeof(g_err), "nans_slab_step: not a slab world"); return NANS_ERR_ARG; }
     SlabState *S = state(w);
     DeviceWorld &d = w->d;
     cudaStream_t s = w->stream;
-    NANS_CUDA(cudaSetDevice(w->device));
     int rc;
     slab_begin_kernel<<<1, 1, 0, s>>>(d, S->live);                      // live rows = owned rows
     NANS_LAUNCH_CHECK();
-    if ((rc = launch_set_dt(w, dt))) return rc;
     if ((rc = launch_integrate_forces(w))) return rc;
     if ((rc = launch_aabb_only(w))) return rc;                          // owned rows (live = n_owned)
     const int n = d.n_owned;
@@ -404,6 +404,55 @@ int nans_slab_step(nans_world *h, float dt)
     w->have_contacts = true;
     if ((rc = launch_solver(w))) return rc;
     return launch_integrate_velocities(w);
+}
+
+// One step of this rank's share of the world, exchanges included; asynchronous on the world's stream.  Like
+// nans_step, the step is ~45 launches (two of them NCCL) with frame-independent parameters: the first call runs
+// eagerly, the second is captured into ONE CUDA graph (NCCL supports capture; every rank captures the same
+// sequence), later calls replay it.  NANS_GRAPH=0 disables.
+int nans_slab_step(nans_world *h, float dt)
+{
+    World *w = reinterpret_cast<World *>(h);
+    if (!w || !w->slab) { snprintf(g_err, sizeof(g_err), "nans_slab_step: not a slab world"); return NANS_ERR_ARG; }
+    SlabState *S = state(w);
+    NANS_CUDA(cudaSetDevice(w->device));
+    int rc;
+    if ((rc = launch_set_dt(w, dt))) return rc;
+    static int enabled = -1;
+    if (enabled < 0) { const char *e = getenv("NANS_GRAPH"); enabled = (e && atoi(e) == 0) ? 0 : 1; }
+    if (!enabled || S->graph_state < 0) return slab_step_body(w);
+    if (S->graph_state == 2) {
+        NANS_CUDA(cudaGraphLaunch(S->graph, w->stream));
+        g_launches += S->graph_launches;
+        w->have_contacts = true;
+        return NANS_OK;
+    }
+    if (S->graph_state == 1) {
+        const unsigned long long before = g_launches;
+        cudaGraph_t graph = nullptr;
+        bool ok = cudaStreamBeginCapture(w->stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+        if (ok) {
+            rc = slab_step_body(w);
+            const cudaError_t ee = cudaStreamEndCapture(w->stream, &graph);
+            ok = !rc && ee == cudaSuccess && graph && cudaGraphInstantiate(&S->graph, graph, 0) == cudaSuccess;
+            if (graph) cudaGraphDestroy(graph);
+        }
+        S->graph_launches = (unsigned)(g_launches - before);
+        g_launches = before;
+        if (!ok) {
+            cudaGetLastError();
+            S->graph = nullptr;
+            S->graph_state = -1;                 // stay eager (every rank takes the same decision or NCCL would hang:
+            return slab_step_body(w);            // capture support is a property of the NCCL / driver pair, equal on all ranks)
+        }
+        S->graph_state = 2;
+        NANS_CUDA(cudaGraphLaunch(S->graph, w->stream));
+        g_launches += S->graph_launches;
+        w->have_contacts = true;
+        return NANS_OK;
+    }
+    S->graph_state = 1;
+    return slab_step_body(w);
 }
 
 // synchronises; err_bits: SLAB_ERR_* (sticky), live_rows: owned + ghosts of the last step

@@ -17,7 +17,7 @@ def test_slab_two_gpus_bit_exact():
         pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
            "--master-addr", "127.0.0.1", "--master-port", "29517",
-           os.path.join(ROOT, "tools", "slab_check.py"), "16", "12", "16", "30", "15", "5"]
+           os.path.join(ROOT, "tools", "slab_check.py"), "16", "12", "16", "20", "10", "5"]
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
     sys.stdout.write(out.stdout[-3000:])
     assert out.returncode == 0, out.stderr[-3000:]

