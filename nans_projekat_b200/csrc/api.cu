@@ -101,8 +101,6 @@ static Layout carve(const nans_world_desc &desc, char *base)
     d.pair_a = b.take<int32_t>(mp); d.pair_b = b.take<int32_t>(mp);
     d.pair_hit = b.take<int32_t>(mp + 1); d.pair_hit_scan = b.take<uint32_t>(mp + 1);
     d.pair_out = b.take<float4>(3 * mp);
-    d.np_pool_ctas = narrowphase_pool_ctas(d.max_pairs);
-    d.np_pool = b.take<char>(narrowphase_pool_bytes_per_cta() * (size_t)d.np_pool_ctas);
     d.c_a = b.take<int32_t>(mc); d.c_b = b.take<int32_t>(mc);
     d.c_pa = b.take<float4>(mc); d.c_pb = b.take<float4>(mc); d.c_n = b.take<float4>(mc);
     d.deg = b.take<uint32_t>(nb + 1); d.cursor = b.take<uint32_t>(nb);

@@ -57,152 +57,62 @@ __device__ __forceinline__ NpResult dispatch(bool a_sphere, bool b_sphere, NpSha
     return check_collision<true, true>(S, E, ovf, max_faces);
 }
 
-// ---- the world narrowphase: pairs regrouped between EPA iterations ------------------------------------------------
-// One thread per pair wastes most of the machine on this algorithm: on the settled 1 M-cube pile EPA runs 1-7
-// iterations per pair (mode 4-6) and a warp waits for its slowest lane: 13.5 of 32 lanes active per instruction
-// (profiles/r2_mid_ncu_full_summary.txt), 0.59 lane efficiency from the iteration counts alone.  Here a CTA takes
-// kNpThreads pairs at a time.  GJK runs one pair per thread (it is uniform: 5 evolutions for nearly every pair of a
-// pile).  EPA then runs ONE ITERATION PER ROUND: before every round the pairs still iterating are compacted
-// (ballot + prefix over the CTA) and handed to the first lanes, so every warp but the last is full, and -- because
-// all pairs started together -- every lane of a round is at the same iteration number and therefore holds a
-// polytope of the same size (4 + 2 it faces): the face / edge loops of a warp run the same trip counts.  A pair can
-// move to another lane because its state is not in registers or local memory: shapes and the five state words live
-// in shared memory by SLOT, the polytope in a global pool with local-memory interleaving (EpaPooledArena).
-// Results are bit-identical to the one-thread-per-pair loop: the same epa_begin / epa_iter run in the same order
-// for every pair (tests/test_np_host.py runs them through epa_resolve).
-struct NpSlotShared {
-    float pos[8][kNpThreads];          // posA.xyz, radA, posB.xyz, radB
-    float cur[kNpThreads];
-    uint32_t st[kNpThreads];           // nv | nf << 8 | ci << 16 | it << 24
-    uint8_t kind[kNpThreads];          // bit 0 a_sphere, bit 1 b_sphere, bit 2 still iterating
-    int list[kNpThreads];
-    int warp_cnt[kNpThreads / 32];
-    int base, total;
-};
-
-template <bool AS, bool BS>
-__device__ __noinline__ int np_gjk_begin(NpShapes &S, char *cta_pool, EpaState &st)
+// (Round 2 measured a CTA-level regrouping of the pairs between EPA iterations -- one iteration per round, the pairs
+// still iterating compacted onto the first lanes, polytopes in a slot-addressed global pool so that a pair can change
+// lanes -- to attack the 13.5 of 32 active lanes of this kernel.  Bit-exact, and slower: 0.77 vs 0.50 ms on the
+// 1 M-cube pile.  Lanes per instruction only rose to 15.6: the divergence is INSIDE an iteration (how many faces the
+// new point sees, how many horizon edges survive), not in the iteration counts, and the barriers cost 33 % of the
+// stall samples at 20 warps per SM.  profiles/r2_np_regroup_*.  The one-thread-per-pair kernel below stays.)
+__device__ __forceinline__ void np_world_pair(const DeviceWorld &w, int p, int ra, int rb, NpShapes &S, EpaArena &E,
+                                              int &ovf, int &max_faces, int &found)
 {
-    GjkVertex<AS, BS> s[4];
-    const int ev = gjk_run<AS, BS>(S, s);
-    if (ev == kFoundIntersection) {
-        EpaPooledArena E = epa_pool_view(cta_pool, S.slot);     // built here: ten pointers stay in registers
-        epa_begin<AS, BS>(s, E, st);
+    const bool a_sphere = ra >= w.n_cubes;
+    const bool b_sphere = rb >= w.n_cubes;   // statics are negative -> box
+    S.posA = V3(w.pos[ra]);
+    S.radA = 0.f;
+    if (a_sphere) S.radA = w.scale[ra].w; else load_box(0, w.verts + 6 * (size_t)ra);
+    S.radB = 0.f;
+    if (rb < 0) {
+        const int k = -rb - 1;
+        S.posB = V3(w.st_pos[k]);
+        load_box(1, w.st_verts + 6 * k);
+    } else {
+        S.posB = V3(w.pos[rb]);
+        if (b_sphere) S.radB = w.scale[rb].w; else load_box(1, w.verts + 6 * (size_t)rb);
     }
-    return ev;
-}
-template <bool AS, bool BS>
-__device__ __noinline__ int np_epa_round(const NpShapes &S, char *cta_pool, EpaState &st, vec3 &PA, vec3 &PB, vec3 &N,
-                                         int &ovf, int &max_faces)
-{
-    EpaPooledArena E = epa_pool_view(cta_pool, S.slot);
-    return epa_iter<AS, BS>(S, E, st, PA, PB, N, ovf, max_faces);
+    const NpResult r = dispatch(a_sphere, b_sphere, S, E, ovf, max_faces);
+    found += (r.gjk == kFoundIntersection);
+    w.pair_hit[p] = r.hit;
+    if (r.hit) {
+        float4 *o = w.pair_out + 3 * (size_t)p;
+#if NANS_NP_STREAM
+        __stcs(o, make_float4(r.PA.x, r.PA.y, r.PA.z, 0.f));
+        __stcs(o + 1, make_float4(r.PB.x, r.PB.y, r.PB.z, 0.f));
+        __stcs(o + 2, make_float4(r.N.x, r.N.y, r.N.z, 0.f));
+#else
+        o[0] = make_float4(r.PA.x, r.PA.y, r.PA.z, 0.f);
+        o[1] = make_float4(r.PB.x, r.PB.y, r.PB.z, 0.f);
+        o[2] = make_float4(r.N.x, r.N.y, r.N.z, 0.f);
+#endif
+    }
 }
 
-__global__ void __launch_bounds__(kNpThreads, NANS_NP_MINBLOCKS) narrowphase_world_kernel(DeviceWorld w, int *work_counter, char *pool)
+__global__ void __launch_bounds__(kNpThreads, NANS_NP_MINBLOCKS) narrowphase_world_kernel(DeviceWorld w, int *work_counter)
 {
-    __shared__ NpSlotShared sh;
-    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    EpaArena E;
+    const int lane = threadIdx.x & 31;
     const int n_pairs = w.counters->n_pairs;
-    char *cta_pool = pool + (size_t)blockIdx.x * kEpaPoolBytesPerCta;
     int ovf = 0, max_faces = 0, found = 0;
+    NpShapes S;
+    S.slot = threadIdx.x;
+    constexpr int kPerTicket = 32;
     while (true) {
-        __syncthreads();                                   // the previous batch is done with the shared slots
-        if (tid == 0) sh.base = atomicAdd(work_counter, kNpThreads);
-        __syncthreads();
-        const int base = sh.base;
+        int base = 0;
+        if (lane == 0) base = atomicAdd(work_counter, kPerTicket);
+        base = __shfl_sync(0xffffffffu, base, 0);
         if (base >= n_pairs) break;
-        // ---- GJK, one pair per thread; an intersecting pair starts its polytope in slot tid
-        const int p = base + tid;
-        uint32_t kind = 0;
-        if (p < n_pairs) {
-            const int ra = w.pair_a[p], rb = w.pair_b[p];
-            const bool a_sphere = ra >= w.n_cubes;
-            const bool b_sphere = rb >= w.n_cubes;   // statics are negative -> box
-            NpShapes S;
-            S.slot = tid;
-            S.posA = V3(w.pos[ra]);
-            S.radA = 0.f;
-            if (a_sphere) S.radA = w.scale[ra].w; else load_box(0, w.verts + 6 * (size_t)ra);
-            S.radB = 0.f;
-            if (rb < 0) {
-                const int k = -rb - 1;
-                S.posB = V3(w.st_pos[k]);
-                load_box(1, w.st_verts + 6 * k);
-            } else {
-                S.posB = V3(w.pos[rb]);
-                if (b_sphere) S.radB = w.scale[rb].w; else load_box(1, w.verts + 6 * (size_t)rb);
-            }
-            EpaState st;
-            int ev;
-            if (!a_sphere && !b_sphere) ev = np_gjk_begin<false, false>(S, cta_pool, st);
-            else if (!a_sphere && b_sphere) ev = np_gjk_begin<false, true>(S, cta_pool, st);
-            else if (a_sphere && !b_sphere) ev = np_gjk_begin<true, false>(S, cta_pool, st);
-            else ev = np_gjk_begin<true, true>(S, cta_pool, st);
-            kind = (a_sphere ? 1u : 0u) | (b_sphere ? 2u : 0u);
-            if (ev == kFoundIntersection) {
-                ++found;
-                kind |= 4u;
-                sh.pos[0][tid] = S.posA.x; sh.pos[1][tid] = S.posA.y; sh.pos[2][tid] = S.posA.z; sh.pos[3][tid] = S.radA;
-                sh.pos[4][tid] = S.posB.x; sh.pos[5][tid] = S.posB.y; sh.pos[6][tid] = S.posB.z; sh.pos[7][tid] = S.radB;
-                sh.cur[tid] = st.cur;
-                sh.st[tid] = (uint32_t)st.nv | ((uint32_t)st.nf << 8) | ((uint32_t)st.ci << 16) | ((uint32_t)st.it << 24);
-            } else {
-                w.pair_hit[p] = 0;
-            }
-        }
-        sh.kind[tid] = (uint8_t)kind;
-        // ---- EPA, one iteration per round over the compacted list of pairs still iterating
-        while (true) {
-            __syncthreads();
-            const bool alive = (sh.kind[tid] & 4u) != 0;
-            const unsigned m = __ballot_sync(0xffffffffu, alive);
-            if (lane == 0) sh.warp_cnt[wid] = __popc(m);
-            __syncthreads();
-            int off = 0, total = 0;
-#pragma unroll
-            for (int q = 0; q < kNpThreads / 32; ++q) {
-                const int c = sh.warp_cnt[q];
-                if (q < wid) off += c;
-                total += c;
-            }
-            if (total == 0) break;
-            if (alive) sh.list[off + __popc(m & ((1u << lane) - 1u))] = tid;
-            __syncthreads();
-            if (tid < total) {
-                const int slot = sh.list[tid];
-                const uint32_t kd = sh.kind[slot];
-                NpShapes S;
-                S.slot = slot;
-                S.posA = V3(sh.pos[0][slot], sh.pos[1][slot], sh.pos[2][slot]); S.radA = sh.pos[3][slot];
-                S.posB = V3(sh.pos[4][slot], sh.pos[5][slot], sh.pos[6][slot]); S.radB = sh.pos[7][slot];
-                S.dir0 = V3(0.f, 0.f, 0.f);                 // GJK only
-                const uint32_t pk = sh.st[slot];
-                EpaState st;
-                st.nv = pk & 255; st.nf = (pk >> 8) & 255; st.ci = (pk >> 16) & 255; st.it = pk >> 24; st.cur = sh.cur[slot];
-                vec3 PA, PB, N;
-                int r;
-                const bool as = kd & 1u, bs = kd & 2u;
-                if (!as && !bs) r = np_epa_round<false, false>(S, cta_pool, st, PA, PB, N, ovf, max_faces);
-                else if (!as && bs) r = np_epa_round<false, true>(S, cta_pool, st, PA, PB, N, ovf, max_faces);
-                else if (as && !bs) r = np_epa_round<true, false>(S, cta_pool, st, PA, PB, N, ovf, max_faces);
-                else r = np_epa_round<true, true>(S, cta_pool, st, PA, PB, N, ovf, max_faces);
-                if (r == kEpaContinue) {
-                    sh.cur[slot] = st.cur;
-                    sh.st[slot] = (uint32_t)st.nv | ((uint32_t)st.nf << 8) | ((uint32_t)st.ci << 16) | ((uint32_t)st.it << 24);
-                } else {
-                    const int q = base + slot;
-                    w.pair_hit[q] = r;
-                    if (r) {
-                        float4 *o = w.pair_out + 3 * (size_t)q;
-                        __stcs(o, make_float4(PA.x, PA.y, PA.z, 0.f));
-                        __stcs(o + 1, make_float4(PB.x, PB.y, PB.z, 0.f));
-                        __stcs(o + 2, make_float4(N.x, N.y, N.z, 0.f));
-                    }
-                    sh.kind[slot] = (uint8_t)(kd & 3u);
-                }
-            }
-        }
+        const int p = base + lane;
+        if (p < n_pairs) np_world_pair(w, p, w.pair_a[p], w.pair_b[p], S, E, ovf, max_faces, found);
     }
     // per-warp stats
     found = __reduce_add_sync(0xffffffffu, found);
@@ -470,15 +380,6 @@ static int np_grid(int blocks_needed)
     return blocks_needed < cap ? (blocks_needed < 1 ? 1 : blocks_needed) : cap;
 }
 
-// CTAs the world kernel may run (= polytope pools to carve) and the bytes of one pool
-int narrowphase_pool_ctas(int max_pairs)
-{
-    const int need = div_up(max_pairs, kNpThreads);
-    const int cap = kNumSMs * NANS_NP_MINBLOCKS;
-    return need < cap ? (need < 1 ? 1 : need) : cap;
-}
-size_t narrowphase_pool_bytes_per_cta() { return kEpaPoolBytesPerCta; }
-
 int launch_narrowphase(World *w)
 {
     DeviceWorld &d = w->d;
@@ -486,9 +387,8 @@ int launch_narrowphase(World *w)
     // the work counter lives in the Counters pad (zeroed with the block at the start of detect)
     int *work = &d.counters->pad[0];
     // pair count is device-resident: size the grid for the capacity, CTAs beyond the work exit at once
-    int grid = np_grid(div_up(d.max_pairs, kNpThreads));
-    if (grid > d.np_pool_ctas) grid = d.np_pool_ctas;      // one polytope pool per CTA (carved with the world)
-    narrowphase_world_kernel<<<grid, kNpThreads, 0, w->stream>>>(d, work, d.np_pool);
+    const int grid = np_grid(div_up(d.max_pairs, kNpThreads));
+    narrowphase_world_kernel<<<grid, kNpThreads, 0, w->stream>>>(d, work);
     NANS_LAUNCH_CHECK();
     return NANS_OK;
 }

@@ -37,9 +37,7 @@ constexpr int kNoVertex = 8;
 // so every access compiles to LDS/STS (a pointer carried through the call chain degrades to generic loads).
 __shared__ float g_np_verts[48 * kNpThreads];
 
-// One pair's view of the two shapes.  `slot` is the pair's column in the shared vertex block: the thread's own
-// index where a thread keeps its pair from start to finish, any column of the CTA where pairs are regrouped between
-// EPA iterations (narrowphase_world_kernel).
+// One pair's view of the two shapes.  `slot` is the pair's column in the shared vertex block (the thread's index).
 struct NpShapes {
     vec3 posA, posB;     // body centres (GJK start direction; sphere support)
     vec3 dir0;           // normalize(posB - posA): EvolveSimplex recomputes it every call (:575); hoisted
@@ -216,46 +214,6 @@ struct EpaGenericArena {
 };
 using EpaArena = EpaGenericArena;
 constexpr int kCidNaN = 254;
-
-// The same arena for a POOL of pairs that are regrouped between EPA iterations: pair `slot` of a CTA's kNpThreads
-// pairs owns element i of an array at base[i * kNpThreads + slot], i.e. the interleaving the hardware gives
-// per-thread local memory (the lanes of a warp that work on consecutive slots touch consecutive words), but
-// addressable by ANY thread of the CTA, so a pair can move to another lane.
-template <typename T> struct Strided {
-    T *p;
-    __device__ __forceinline__ T &operator[](int i) const { return p[(size_t)i * kNpThreads]; }
-};
-struct EpaPooledArena {
-    Strided<vec3> P, SA, SB;
-    Strided<uint8_t> ia, ib, cid;
-    Strided<float4> fnd;
-    Strided<uint32_t> fidx, vis, edge;
-};
-// bytes of one CTA's pool and the view of one slot inside it
-constexpr size_t kEpaPoolBytesPerSlot = sizeof(vec3) * 3 * kEpaMaxVerts + 3 * kEpaMaxVerts + 4 /* pad to 4 */ +
-                                        sizeof(float4) * kEpaMaxFaces + 4 * (2 * kEpaMaxFaces + kEpaMaxEdges);
-constexpr size_t kEpaPoolBytesPerCta = ((kEpaPoolBytesPerSlot * kNpThreads + 255) / 256) * 256 + 256 * 8;
-__device__ __forceinline__ EpaPooledArena epa_pool_view(char *cta_base, int slot)
-{
-    EpaPooledArena E;
-    char *q = cta_base;
-    auto take = [&](size_t elem_bytes, size_t count) -> char * {
-        char *r = q;
-        q += ((elem_bytes * count * kNpThreads + 255) / 256) * 256;
-        return r;
-    };
-    E.fnd.p = (float4 *)take(16, kEpaMaxFaces) + slot;
-    E.P.p = (vec3 *)take(12, kEpaMaxVerts) + slot;
-    E.SA.p = (vec3 *)take(12, kEpaMaxVerts) + slot;
-    E.SB.p = (vec3 *)take(12, kEpaMaxVerts) + slot;
-    E.fidx.p = (uint32_t *)take(4, kEpaMaxFaces) + slot;
-    E.vis.p = (uint32_t *)take(4, kEpaMaxFaces) + slot;
-    E.edge.p = (uint32_t *)take(4, kEpaMaxEdges) + slot;
-    E.ia.p = (uint8_t *)take(1, kEpaMaxVerts) + slot;
-    E.ib.p = (uint8_t *)take(1, kEpaMaxVerts) + slot;
-    E.cid.p = (uint8_t *)take(1, kEpaMaxVerts) + slot;
-    return E;
-}
 
 // The reference's edge cancels an opposite-winding edge BY VALUE of P (code/nans.h:251-254).  Float
 // equality is an equivalence on non-NaN vectors (+0 == -0 included), so every vertex gets the lowest

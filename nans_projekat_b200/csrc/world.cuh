@@ -81,8 +81,6 @@ struct DeviceWorld {
     int32_t *pair_hit;                  // [max_pairs] 0/1
     uint32_t *pair_hit_scan;            // [max_pairs + 1]
     float4 *pair_out;                   // [max_pairs][3]: PointA, PointB, N
-    char *np_pool;                      // EPA polytope pools of the world narrowphase, one per CTA (narrowphase.cu)
-    int32_t np_pool_ctas;
     // --- contacts (reference order)
     int32_t *c_a, *c_b;                 // body rows / -(k+1)
     float4 *c_pa, *c_pb, *c_n;          // [max_contacts]
@@ -161,8 +159,6 @@ int launch_rebuild_statics(World *w);
 int launch_models(World *w, float4 *d_out);
 int launch_broadphase(World *w);
 int launch_narrowphase(World *w);
-int narrowphase_pool_ctas(int max_pairs);
-size_t narrowphase_pool_bytes_per_cta();
 int launch_contacts(World *w);
 int launch_solver(World *w);
 int solver_accum_fallbacks(World *w, int32_t *out);
