@@ -45,7 +45,7 @@ __device__ __forceinline__ void load_box(int side, const float4 *__restrict__ v6
 #endif
         v[4 * q] = t.x; v[4 * q + 1] = t.y; v[4 * q + 2] = t.z; v[4 * q + 3] = t.w;
     }
-    NpShapes::store_box(side, v, threadIdx.x);
+    NpShapes::store_box(side, v);
 }
 
 __device__ __forceinline__ NpResult dispatch(bool a_sphere, bool b_sphere, NpShapes &S, EpaArena &E,
@@ -62,7 +62,8 @@ __device__ __forceinline__ NpResult dispatch(bool a_sphere, bool b_sphere, NpSha
 // lanes -- to attack the 13.5 of 32 active lanes of this kernel.  Bit-exact, and slower: 0.77 vs 0.50 ms on the
 // 1 M-cube pile.  Lanes per instruction only rose to 15.6: the divergence is INSIDE an iteration (how many faces the
 // new point sees, how many horizon edges survive), not in the iteration counts, and the barriers cost 33 % of the
-// stall samples at 20 warps per SM.  profiles/r2_np_regroup_*.  The one-thread-per-pair kernel below stays.)
+// stall samples at 20 warps per SM.  The begin / iterate split of EPA it needed also cost the explicit-pairs EPA
+// kernel 12 % (config C3: 23.8 -> 26.6 ms).  profiles/r2_np_regroup_*.  The one-thread-per-pair kernel below stays.)
 __device__ __forceinline__ void np_world_pair(const DeviceWorld &w, int p, int ra, int rb, NpShapes &S, EpaArena &E,
                                               int &ovf, int &max_faces, int &found)
 {
@@ -104,7 +105,6 @@ __global__ void __launch_bounds__(kNpThreads, NANS_NP_MINBLOCKS) narrowphase_wor
     const int n_pairs = w.counters->n_pairs;
     int ovf = 0, max_faces = 0, found = 0;
     NpShapes S;
-    S.slot = threadIdx.x;
     constexpr int kPerTicket = 32;
     while (true) {
         int base = 0;
@@ -278,7 +278,6 @@ template <typename Src>
 __global__ void __launch_bounds__(kNpThreads, NANS_GJK_MINBLOCKS) gjk_continue_kernel(Src src, SplitScratch sc)
 {
     NpShapes S;
-    S.slot = threadIdx.x;
     gjk_continue_list<false, false>(src, sc, S);
     gjk_continue_list<false, true>(src, sc, S);
     gjk_continue_list<true, false>(src, sc, S);
@@ -292,7 +291,6 @@ __global__ void __launch_bounds__(kNpThreads, NANS_GJK_MINBLOCKS) gjk_split_kern
     const int n_pairs = src.n_pairs();
     int found = 0;
     NpShapes S;
-    S.slot = threadIdx.x;
     while (true) {
         int base = 0;
         if (lane == 0) base = atomicAdd(work_counter, 32);
@@ -355,7 +353,6 @@ __global__ void __launch_bounds__(kNpThreads, NANS_EPA_MINBLOCKS) epa_refill_ker
 {
     EpaArena E;
     NpShapes S;
-    S.slot = threadIdx.x;
     int ovf = 0, max_faces = 0;
     epa_chunk_list<false, false>(src, sc, S, E, ovf, max_faces);
     epa_chunk_list<false, true>(src, sc, S, E, ovf, max_faces);

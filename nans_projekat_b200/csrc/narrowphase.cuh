@@ -37,24 +37,23 @@ constexpr int kNoVertex = 8;
 // so every access compiles to LDS/STS (a pointer carried through the call chain degrades to generic loads).
 __shared__ float g_np_verts[48 * kNpThreads];
 
-// One pair's view of the two shapes.  `slot` is the pair's column in the shared vertex block (the thread's index).
+// Per-thread view of the two shapes.
 struct NpShapes {
     vec3 posA, posB;     // body centres (GJK start direction; sphere support)
     vec3 dir0;           // normalize(posB - posA): EvolveSimplex recomputes it every call (:575); hoisted
     float radA, radB;    // spheres
-    int slot;
     // box vertex k of a side; k = kNoVertex (every support compare failed) is vec3(0)
     __device__ __forceinline__ vec3 vertex(int side, int k) const
     {
         if (k >= 8) return V3(0.f, 0.f, 0.f);
-        const float *p = g_np_verts + (24 * side + 3 * k) * kNpThreads + slot;
+        const float *p = g_np_verts + (24 * side + 3 * k) * kNpThreads + threadIdx.x;
         return V3(p[0], p[kNpThreads], p[2 * kNpThreads]);
     }
     // stage one box: v24 = its 8 packed vec3 (reference vertex order)
-    __device__ __forceinline__ static void store_box(int side, const float (&v24)[24], int slot_)
+    __device__ __forceinline__ static void store_box(int side, const float (&v24)[24])
     {
 #pragma unroll
-        for (int q = 0; q < 24; ++q) g_np_verts[(24 * side + q) * kNpThreads + slot_] = v24[q];
+        for (int q = 0; q < 24; ++q) g_np_verts[(24 * side + q) * kNpThreads + threadIdx.x] = v24[q];
     }
 };
 
@@ -66,7 +65,7 @@ __device__ __forceinline__ vec3 box_support(const NpShapes &S, int side, vec3 d,
     float dist[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-        const float *p = g_np_verts + 24 * side * kNpThreads + S.slot;
+        const float *p = g_np_verts + 24 * side * kNpThreads + threadIdx.x;
         const vec3 c = V3(p[(3 * k) * kNpThreads], p[(3 * k + 1) * kNpThreads], p[(3 * k + 2) * kNpThreads]);
         dist[k] = dot(c, d);
     }
@@ -218,8 +217,8 @@ constexpr int kCidNaN = 254;
 // The reference's edge cancels an opposite-winding edge BY VALUE of P (code/nans.h:251-254).  Float
 // equality is an equivalence on non-NaN vectors (+0 == -0 included), so every vertex gets the lowest
 // index of its class once, when it is stored, and the edge compares become one integer compare.
-template <bool AS, bool BS, class Arena>
-__device__ __forceinline__ void epa_store_vertex(Arena &E, int i, const GjkVertex<AS, BS> &v)
+template <bool AS, bool BS>
+__device__ __forceinline__ void epa_store_vertex(EpaGenericArena &E, int i, const GjkVertex<AS, BS> &v)
 {
     E.P[i] = v.P;
     if constexpr (AS) E.SA[i] = v.a.v; else E.ia[i] = (uint8_t)v.a.idx;
@@ -233,11 +232,11 @@ __device__ __forceinline__ void epa_store_vertex(Arena &E, int i, const GjkVerte
     }
     E.cid[i] = (uint8_t)c;
 }
-template <bool AS, class Arena> __device__ __forceinline__ vec3 epa_sup_a(const Arena &E, const NpShapes &S, int i)
+template <bool AS> __device__ __forceinline__ vec3 epa_sup_a(const EpaGenericArena &E, const NpShapes &S, int i)
 {
     if constexpr (AS) return E.SA[i]; else return S.vertex(0, E.ia[i]);
 }
-template <bool BS, class Arena> __device__ __forceinline__ vec3 epa_sup_b(const Arena &E, const NpShapes &S, int i)
+template <bool BS> __device__ __forceinline__ vec3 epa_sup_b(const EpaGenericArena &E, const NpShapes &S, int i)
 {
     if constexpr (BS) return E.SB[i]; else return S.vertex(1, E.ib[i]);
 }
@@ -250,8 +249,7 @@ __device__ __forceinline__ void epa_track_min(float d, int slot, float &cur, int
     if (slot == 0 || dist < cur) { cur = dist; ci = slot; }
 }
 
-template <class Arena>
-__device__ __forceinline__ void epa_push_face(Arena &E, int &nf, int a, int b, int c, vec3 pa, float &cur, int &ci)
+__device__ __forceinline__ void epa_push_face(EpaGenericArena &E, int &nf, int a, int b, int c, vec3 pa, float &cur, int &ci)
 {
     // PushTriangle, code/nans.cpp:293-322 (flip folded into the sign of d); pa == E.P[a]
     const vec3 n = normalize(cross(E.P[b] - pa, E.P[c] - pa));
@@ -269,8 +267,7 @@ __device__ __forceinline__ vec3 face_normal_flipped(const float4 &nd)
 
 // PushEdge, code/nans.cpp:233-266: an opposite-winding edge already in the list is erased (order of
 // the rest kept), otherwise the edge is appended
-template <class Arena>
-__device__ __forceinline__ void epa_push_edge(Arena &E, int &ne, int a, int b, int &ovf)
+__device__ __forceinline__ void epa_push_edge(EpaGenericArena &E, int &ne, int a, int b, int &ovf)
 {
     const uint32_t ca = E.cid[a], cb = E.cid[b];
     // a NaN vertex equals nothing, itself included: its id on the probing side never matches a stored one
@@ -286,123 +283,100 @@ __device__ __forceinline__ void epa_push_edge(Arena &E, int &ne, int a, int b, i
     E.edge[ne++] = (uint32_t)a | ((uint32_t)b << 8) | (ca << 16) | (cb << 24);
 }
 
-// The polytope between two iterations of ResolveCollision (everything else in the arena is scratch of one iteration).
-struct EpaState { int nv, nf, ci, it; float cur; };
-enum { kEpaContinue = 2 };   // epa_iter: 0 = no collision, 1 = collision (outputs filled), 2 = call again
-
-// the start of ResolveCollision (:791-802): the simplex becomes the first four vertices and faces
-template <bool AS, bool BS, class Arena>
-__device__ __forceinline__ void epa_begin(const GjkVertex<AS, BS> (&s)[4], Arena &E, EpaState &st)
+// ResolveCollision, code/nans.cpp:788-904.  Returns the bool32 result; fills PointA/PointB/N.
+template <bool AS, bool BS>
+__device__ __forceinline__ int epa_resolve(const NpShapes &S, const GjkVertex<AS, BS> (&s)[4], EpaGenericArena &E,
+                                           vec3 &outPA, vec3 &outPB, vec3 &outN, int &ovf, int &max_faces)
 {
+    // the simplex becomes the first four vertices and faces (:791-802)
 #pragma unroll
     for (int k = 0; k < 4; ++k) epa_store_vertex<AS, BS>(E, k, s[k]);
-    int nf = 0, ci = 0;
+    int nv = 4, nf = 0, ne = 0, ci = 0, it = 0;
     float cur = 0.f;
     epa_push_face(E, nf, 0, 1, 2, s[0].P, cur, ci);  // ABC
     epa_push_face(E, nf, 0, 2, 3, s[0].P, cur, ci);  // ACD
     epa_push_face(E, nf, 0, 3, 1, s[0].P, cur, ci);  // ADB
     epa_push_face(E, nf, 1, 3, 2, s[1].P, cur, ci);  // BDC
-    st.nv = 4; st.nf = nf; st.ci = ci; st.it = 0; st.cur = cur;
-}
-
-// ONE iteration of ResolveCollision's loop (code/nans.cpp:805-903): `while (it++ <= 64) { ... }`
-template <bool AS, bool BS, class Arena>
-__device__ __forceinline__ int epa_iter(const NpShapes &S, Arena &E, EpaState &st,
-                                        vec3 &outPA, vec3 &outPB, vec3 &outN, int &ovf, int &max_faces)
-{
-    if (!(st.it++ <= 64)) return 0;            // MAX_EPA_ITERATIONS, code/nans.h:56
-    int nv = st.nv, nf = st.nf, ne = 0, ci = st.ci;
-    float cur = st.cur;
-    max_faces = max(max_faces, nf);
-    const float4 cnd = E.fnd[ci];
-    const vec3 N = face_normal_flipped(cnd);
-    const GjkVertex<AS, BS> ns = calc_support<AS, BS>(S, N);
-    if (fsub(dot(N, ns.P), cur) < 0.001f) {   // MAX_EPA_ERROR, code/nans.h:55
-        const uint32_t f = E.fidx[ci];
-        const int a = f & 255, b = (f >> 8) & 255, c = (f >> 16) & 255;
-        // Barycentric, code/nans.cpp:772-785
-        const vec3 Pp = N * cur;
-        const vec3 A0 = E.P[a];
-        const vec3 v0 = E.P[b] - A0, v1 = E.P[c] - A0, v2 = Pp - A0;
-        const float d00 = dot(v0, v0), d01 = dot(v0, v1), d11 = dot(v1, v1);
-        const float d20 = dot(v2, v0), d21 = dot(v2, v1);
-        const float denom = fsub(fmul(d00, d11), fmul(d01, d01));
-        const float bv = fdiv(fsub(fmul(d11, d20), fmul(d01, d21)), denom);
-        const float bw = fdiv(fsub(fmul(d00, d21), fmul(d01, d20)), denom);
-        const float bu = fsub(fsub(1.0f, bv), bw);
-        if (fabsf(bu) > 1.0f || fabsf(bv) > 1.0f || fabsf(bw) > 1.0f) return 0;
-        if (!isfinite(bu) || !isfinite(bv) || !isfinite(bw)) return 0;   // IsValid, :4-17
-        outPA = ((bu * epa_sup_a<AS>(E, S, a)) + (bv * epa_sup_a<AS>(E, S, b))) + (bw * epa_sup_a<AS>(E, S, c));
-        outN = -1.0f * N;
-        outPB = ((bu * epa_sup_b<BS>(E, S, a)) + (bv * epa_sup_b<BS>(E, S, b))) + (bw * epa_sup_b<BS>(E, S, c));
-        return 1;
-    }
-    if (nv >= kEpaMaxVerts) { ovf |= OVF_EPA_FACES; return 0; }
-    epa_store_vertex<AS, BS>(E, nv, ns);
-    // dissolve every face the new point can see (:869-891); survivors keep their order.  The
-    // dissolved faces are only LISTED here; their edges are pushed in a second loop, so the warp
-    // stays converged over the face scan.
-    const int nf_old = nf;
-    int keep = 0, nvis = 0;
-    float4 nd_next = E.fnd[0];
-    uint32_t f_next = E.fidx[0];
-    for (int i = 0; i < nf; ++i) {
-        const float4 nd = nd_next;
-        const uint32_t f = f_next;
-        if (i + 1 < nf) { nd_next = E.fnd[i + 1]; f_next = E.fidx[i + 1]; }
-        const vec3 tmp = ns.P - E.P[f & 255];
-        if (dot(face_normal_flipped(nd), tmp) > 0.0f) {
-            E.vis[nvis++] = f;
-        } else {
-            if (keep != i) { E.fnd[keep] = nd; E.fidx[keep] = f; }
-            epa_track_min(nd.w, keep, cur, ci);
-            ++keep;
+    while (it++ <= 64) {            // MAX_EPA_ITERATIONS, code/nans.h:56
+        max_faces = max(max_faces, nf);
+        const float4 cnd = E.fnd[ci];
+        const vec3 N = face_normal_flipped(cnd);
+        const GjkVertex<AS, BS> ns = calc_support<AS, BS>(S, N);
+        if (fsub(dot(N, ns.P), cur) < 0.001f) {   // MAX_EPA_ERROR, code/nans.h:55
+            const uint32_t f = E.fidx[ci];
+            const int a = f & 255, b = (f >> 8) & 255, c = (f >> 16) & 255;
+            // Barycentric, code/nans.cpp:772-785
+            const vec3 Pp = N * cur;
+            const vec3 A0 = E.P[a];
+            const vec3 v0 = E.P[b] - A0, v1 = E.P[c] - A0, v2 = Pp - A0;
+            const float d00 = dot(v0, v0), d01 = dot(v0, v1), d11 = dot(v1, v1);
+            const float d20 = dot(v2, v0), d21 = dot(v2, v1);
+            const float denom = fsub(fmul(d00, d11), fmul(d01, d01));
+            const float bv = fdiv(fsub(fmul(d11, d20), fmul(d01, d21)), denom);
+            const float bw = fdiv(fsub(fmul(d00, d21), fmul(d01, d20)), denom);
+            const float bu = fsub(fsub(1.0f, bv), bw);
+            if (fabsf(bu) > 1.0f || fabsf(bv) > 1.0f || fabsf(bw) > 1.0f) return 0;
+            if (!isfinite(bu) || !isfinite(bv) || !isfinite(bw)) return 0;   // IsValid, :4-17
+            outPA = ((bu * epa_sup_a<AS>(E, S, a)) + (bv * epa_sup_a<AS>(E, S, b))) + (bw * epa_sup_a<AS>(E, S, c));
+            outN = -1.0f * N;
+            outPB = ((bu * epa_sup_b<BS>(E, S, a)) + (bv * epa_sup_b<BS>(E, S, b))) + (bw * epa_sup_b<BS>(E, S, c));
+            return 1;
         }
-    }
-    nf = keep;
-    for (int j = 0; j < nvis; ++j) {
-        uint32_t f = E.vis[j];
+        if (nv >= kEpaMaxVerts) { ovf |= OVF_EPA_FACES; return 0; }
+        epa_store_vertex<AS, BS>(E, nv, ns);
+        // dissolve every face the new point can see (:869-891); survivors keep their order.  The
+        // dissolved faces are only LISTED here; their edges are pushed in a second loop, so the warp
+        // stays converged over the face scan.
+        const int nf_old = nf;
+        int keep = 0, nvis = 0;
+        float4 nd_next = E.fnd[0];
+        uint32_t f_next = E.fidx[0];
+        for (int i = 0; i < nf; ++i) {
+            const float4 nd = nd_next;
+            const uint32_t f = f_next;
+            if (i + 1 < nf) { nd_next = E.fnd[i + 1]; f_next = E.fidx[i + 1]; }
+            const vec3 tmp = ns.P - E.P[f & 255];
+            if (dot(face_normal_flipped(nd), tmp) > 0.0f) {
+                E.vis[nvis++] = f;
+            } else {
+                if (keep != i) { E.fnd[keep] = nd; E.fidx[keep] = f; }
+                epa_track_min(nd.w, keep, cur, ci);
+                ++keep;
+            }
+        }
+        nf = keep;
+        for (int j = 0; j < nvis; ++j) {
+            uint32_t f = E.vis[j];
 #pragma unroll 1
-        for (int k = 0; k < 3; ++k) {           // AB, BC, CA
-            epa_push_edge(E, ne, f & 255, (f >> 8) & 255, ovf);
-            f = (f >> 8) | ((f & 255) << 16);
+            for (int k = 0; k < 3; ++k) {           // AB, BC, CA
+                epa_push_edge(E, ne, f & 255, (f >> 8) & 255, ovf);
+                f = (f >> 8) | ((f & 255) << 16);
+            }
+        }
+        // one new face per horizon edge, in edge-list order (:894-901)
+        if (nf + ne > kEpaMaxFaces) { ovf |= OVF_EPA_FACES; return 0; }
+        for (int i = 0; i < ne; ++i) {
+            const uint32_t ed = E.edge[i];
+            epa_push_face(E, nf, nv, ed & 255, (ed >> 8) & 255, ns.P, cur, ci);
+        }
+        ne = 0;
+        ++nv;
+        // The EMPTIED polytope.  When the new point sees every face and every horizon edge cancels (the origin
+        // lies on a face plane of a flat start tetrahedron: seen once per ~10^6 pairs of a settling pile), the
+        // reference's std::vector<triangle> is empty, and its next iteration still reads Triangle[0] (:807-811,
+        // 824-866).  erase() shifted the list down one element at a time, so that storage slot holds the LAST
+        // face of the dissolved list; the reference goes on with it as the closest face (direction, distance,
+        // barycentrics) in every remaining iteration.  The prebuilt nans.so behaves exactly so (tests/golden/
+        // epa_emptied.npz); kept here: slot 0 := that face, ci = 0, cur = its |d|, nf stays 0.
+        if (nf == 0 && nf_old > 0) {
+            const float4 last = E.fnd[nf_old - 1];
+            E.fnd[0] = last;
+            E.fidx[0] = E.fidx[nf_old - 1];
+            cur = fabsf(last.w);
+            ci = 0;
         }
     }
-    // one new face per horizon edge, in edge-list order (:894-901)
-    if (nf + ne > kEpaMaxFaces) { ovf |= OVF_EPA_FACES; return 0; }
-    for (int i = 0; i < ne; ++i) {
-        const uint32_t ed = E.edge[i];
-        epa_push_face(E, nf, nv, ed & 255, (ed >> 8) & 255, ns.P, cur, ci);
-    }
-    ++nv;
-    // The EMPTIED polytope.  When the new point sees every face and every horizon edge cancels (the origin
-    // lies on a face plane of a flat start tetrahedron: seen once per ~10^6 pairs of a settling pile), the
-    // reference's std::vector<triangle> is empty, and its next iteration still reads Triangle[0] (:807-811,
-    // 824-866).  erase() shifted the list down one element at a time, so that storage slot holds the LAST
-    // face of the dissolved list; the reference goes on with it as the closest face (direction, distance,
-    // barycentrics) in every remaining iteration.  The prebuilt nans.so behaves exactly so (tests/golden/
-    // epa_emptied.npz); kept here: slot 0 := that face, ci = 0, cur = its |d|, nf stays 0.
-    if (nf == 0 && nf_old > 0) {
-        const float4 last = E.fnd[nf_old - 1];
-        E.fnd[0] = last;
-        E.fidx[0] = E.fidx[nf_old - 1];
-        cur = fabsf(last.w);
-        ci = 0;
-    }
-    st.nv = nv; st.nf = nf; st.ci = ci; st.cur = cur;
-    return kEpaContinue;
-}
-
-// ResolveCollision, code/nans.cpp:788-904.  Returns the bool32 result; fills PointA/PointB/N.
-template <bool AS, bool BS, class Arena>
-__device__ __forceinline__ int epa_resolve(const NpShapes &S, const GjkVertex<AS, BS> (&s)[4], Arena &E,
-                                           vec3 &outPA, vec3 &outPB, vec3 &outN, int &ovf, int &max_faces)
-{
-    EpaState st;
-    epa_begin<AS, BS>(s, E, st);
-    int r;
-    do r = epa_iter<AS, BS>(S, E, st, outPA, outPB, outN, ovf, max_faces); while (r == kEpaContinue);
-    return r;
+    return 0;
 }
 
 struct NpResult { int hit, gjk; vec3 PA, PB, N; };

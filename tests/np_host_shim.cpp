@@ -41,7 +41,7 @@ static void load_box_host(int side, const float *v24)
 {
     float v[24];
     for (int q = 0; q < 24; ++q) v[q] = v24[q];
-    NpShapes::store_box(side, v, 0);
+    NpShapes::store_box(side, v);
 }
 
 template <bool AS, bool BS>
@@ -62,7 +62,6 @@ extern "C" int np_host_check_collision_batch(int n, const int32_t *type, const f
         const int t = type[p];
         const bool as = (t == NANS_SS || t == NANS_SF), bs = (t == NANS_CS || t == NANS_SS);
         NpShapes S;
-        S.slot = 0;
         S.posA = V3(pos_a[3 * p], pos_a[3 * p + 1], pos_a[3 * p + 2]); S.radA = rad_a[p];
         S.posB = V3(pos_b[3 * p], pos_b[3 * p + 1], pos_b[3 * p + 2]); S.radB = rad_b[p];
         if (!as) load_box_host(0, verts_a + 24 * (size_t)p);
