@@ -18,7 +18,7 @@ for so in gpurun_variants/*.so; do
   [ -f "$so" ] || continue
   cp "$so" nans_projekat_b200/libnans_b200.so
   n=$(basename "$so" .so)
-  timeout 300 python bench.py --no-cpu-baseline --no-e2e --steps 40 $EXTRA > gpurun_out/ab_$n.json 2> gpurun_out/ab_$n.err
+  timeout 300 python bench.py --no-cpu-baseline --no-e2e --no-subrecords --steps 40 $EXTRA > gpurun_out/ab_$n.json 2> gpurun_out/ab_$n.err
   python - "$n" <<'PY'
 import json, sys
 n = sys.argv[1]
