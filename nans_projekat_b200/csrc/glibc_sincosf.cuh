@@ -7,8 +7,8 @@
 // kernel of sysdeps/ieee754/flt-32/s_sinf.c / s_cosf.c (glibc >= 2.28, same through 2.39), in the
 // FMA contraction pattern of the x86-64 `__sinf_fma` / `__cosf_fma` ifunc variants every
 // FMA-capable host selects.  The constants are the published __sincosf_table / __inv_pio4.
-// tests/test_sincos_emulation.py proves this file equal to the running libm, bit for bit,
-// over the full float range (it compiles this header for the host).
+// tests/test_host_cpu.py::test_sincos_emulation_matches_libm (tests/sincos_check.cpp compiles this header for
+// the host) proves it equal to the running libm, bit for bit, over the full float range.
 #pragma once
 #include <stdint.h>
 #include <string.h>

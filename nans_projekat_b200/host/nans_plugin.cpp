@@ -187,6 +187,10 @@ void Init(memory *Memory, plugin_state *S)
     const char *dev = getenv("NANS_DEVICE");
     d.device = dev ? atoi(dev) : 0;
     CK(nans_world_create(&d, &S->world));
+    // sweep order of SolveConstraints: the reference's (default) or the faster shuffled one (NOT the reference's
+    // results; include/nans_b200.h).  Hot reload is the reference's config mechanism; an env var is ours.
+    const char *sv = getenv("NANS_SOLVER");
+    if (sv && !strcmp(sv, "shuffled")) CK(nans_world_set_solver(S->world, NANS_SOLVER_SHUFFLED));
 
     nans_scene_view v;
     memset(&v, 0, sizeof(v));
