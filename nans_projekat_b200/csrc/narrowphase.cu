@@ -27,6 +27,10 @@
 #define NANS_EPA_MINBLOCKS 5   // EPA refill kernel of the split path
 #endif
 
+#ifndef NANS_EPAW_MINBLOCKS
+#define NANS_EPAW_MINBLOCKS 5   // EPA kernel of the two-kernel world narrowphase
+#endif
+
 #ifndef NANS_NP_STREAM
 #define NANS_NP_STREAM 1
 #endif
@@ -118,6 +122,202 @@ __global__ void __launch_bounds__(kNpThreads, NANS_NP_MINBLOCKS) narrowphase_wor
     found = __reduce_add_sync(0xffffffffu, found);
     ovf = __reduce_or_sync(0xffffffffu, ovf);
     max_faces = __reduce_max_sync(0xffffffffu, max_faces);
+    if (lane == 0) {
+        if (found) atomicAdd(&w.counters->n_gjk_found, found);
+        if (ovf) atomicOr(&w.counters->overflow, ovf);
+        atomicMax(&w.counters->max_epa_faces, max_faces);
+    }
+}
+
+// ---- the world narrowphase in two kernels ---------------------------------------------------------------------------
+// In the one-kernel form the lanes whose pair misses idle through the EPA of their 32-pair chunk (24 % of the lanes on
+// the 100^3 pile).  Here a first kernel runs GJK alone over every candidate (box pairs; a pair with a sphere still runs
+// GJK + EPA in place) and appends the intersecting box pairs to ONE list -- entry = {pair, the final simplex as eight
+// 4-bit box-vertex indices}: P = SupA - SupB is re-formed from the same operands, so nothing else has to be saved --
+// and a second kernel runs EPA over whole 32-entry chunks of that list.  Results are written per pair, so the list's
+// (atomic) order is not observable.  The list lives in the solver's schedule buffers, which are idle until the
+// contact list exists (inc: 8 B x 2 x max_contacts).
+constexpr int kNpListCount = 4, kNpListTicket = 5, kNpDeferCount = 6;    // Counters::pad slots (zeroed with the block per detect)
+#ifndef NANS_NP_GJK_CAP_WORLD
+#define NANS_NP_GJK_CAP_WORLD 6
+#endif
+constexpr int kNpGjkCap = NANS_NP_GJK_CAP_WORLD;   // evolutions in the GJK kernel (a pile's pairs take 5; 1000 = no cap)
+
+__device__ __forceinline__ void np_load_world_shapes(const DeviceWorld &w, int ra, int rb, bool a_sphere, bool b_sphere, NpShapes &S)
+{
+    S.posA = V3(w.pos[ra]);
+    S.radA = 0.f;
+    if (a_sphere) S.radA = w.scale[ra].w; else load_box(0, w.verts + 6 * (size_t)ra);
+    S.radB = 0.f;
+    if (rb < 0) {
+        const int k = -rb - 1;
+        S.posB = V3(w.st_pos[k]);
+        load_box(1, w.st_verts + 6 * k);
+    } else {
+        S.posB = V3(w.pos[rb]);
+        if (b_sphere) S.radB = w.scale[rb].w; else load_box(1, w.verts + 6 * (size_t)rb);
+    }
+}
+
+__device__ __forceinline__ void np_store_hit(const DeviceWorld &w, int p, const NpResult &r)
+{
+    w.pair_hit[p] = r.hit;
+    if (r.hit) {
+        float4 *o = w.pair_out + 3 * (size_t)p;
+        __stcs(o, make_float4(r.PA.x, r.PA.y, r.PA.z, 0.f));
+        __stcs(o + 1, make_float4(r.PB.x, r.PB.y, r.PB.z, 0.f));
+        __stcs(o + 2, make_float4(r.N.x, r.N.y, r.N.z, 0.f));
+    }
+}
+
+template <bool HAS_SPHERES>
+__global__ void __launch_bounds__(kNpThreads, HAS_SPHERES ? NANS_NP_MINBLOCKS : NANS_GJK_MINBLOCKS) narrowphase_world_gjk_kernel(DeviceWorld w, int *work_counter)
+{
+    const int lane = threadIdx.x & 31;
+    const int n_pairs = w.counters->n_pairs;
+    uint2 *list = reinterpret_cast<uint2 *>(w.inc);
+    const int list_cap = w.max_contacts;
+    int ovf = 0, max_faces = 0, found = 0;
+    NpShapes S;
+    while (true) {
+        int base = 0;
+        if (lane == 0) base = atomicAdd(work_counter, 32);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (base >= n_pairs) break;
+        const int p = base + lane;
+        bool want = false, defer = false;
+        uint32_t rec = 0;
+        int state = 0;
+        if (p < n_pairs) {
+            const int ra = w.pair_a[p], rb = w.pair_b[p];
+            const bool a_sphere = ra >= w.n_cubes, b_sphere = rb >= w.n_cubes;
+            np_load_world_shapes(w, ra, rb, a_sphere, b_sphere, S);
+            if (HAS_SPHERES && (a_sphere || b_sphere)) {
+                if constexpr (HAS_SPHERES) {
+                    EpaArena E;
+                    const NpResult r = dispatch(a_sphere, b_sphere, S, E, ovf, max_faces);
+                    found += (r.gjk == kFoundIntersection);
+                    np_store_hit(w, p, r);
+                }
+            } else {
+                GjkVertex<false, false> s[4];
+                int n = 0, iter = 0;
+                const int ev = gjk_resume<false, false>(S, s, n, iter, kNpGjkCap);
+                want = ev == kFoundIntersection;
+                defer = ev == kStillEvolving && iter <= 64;
+                if (want || defer) {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        if (k < n) rec |= ((uint32_t)s[k].a.idx | ((uint32_t)s[k].b.idx << 4)) << (8 * k);
+                    state = n | (iter << 8);
+                } else {
+                    w.pair_hit[p] = 0;
+                }
+            }
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, want);
+        if (m) {
+            int at = 0;
+            if (lane == 0) at = atomicAdd(&w.counters->pad[kNpListCount], __popc(m));
+            at = __shfl_sync(0xffffffffu, at, 0) + __popc(m & ((1u << lane) - 1u));
+            if (want) {
+                if (at < list_cap) list[at] = make_uint2((uint32_t)p, rec);
+                else { ovf |= OVF_CONTACTS; w.pair_hit[p] = 0; }
+            }
+            found += want;
+        }
+        // the few pairs still evolving after kNpGjkCap evolutions (misses that cycle up to the reference's limit of 65:
+        // 0.5-2 % of a pile's candidates, but a chunk waits for its slowest lane) are finished by the EPA kernel
+        const unsigned md = __ballot_sync(0xffffffffu, defer);
+        if (md) {
+            int at = 0;
+            if (lane == 0) at = atomicAdd(&w.counters->pad[kNpDeferCount], __popc(md));
+            at = __shfl_sync(0xffffffffu, at, 0) + __popc(md & ((1u << lane) - 1u));
+            if (defer) {
+                if (at < list_cap) { w.succ_a[at] = p; w.succ_b[at] = (int32_t)rec; w.run_flag[at] = state; }
+                else { ovf |= OVF_CONTACTS; w.pair_hit[p] = 0; }
+            }
+        }
+    }
+    found = __reduce_add_sync(0xffffffffu, found);
+    ovf = __reduce_or_sync(0xffffffffu, ovf);
+    max_faces = __reduce_max_sync(0xffffffffu, max_faces);
+    if (lane == 0) {
+        if (found) atomicAdd(&w.counters->n_gjk_found, found);
+        if (ovf) atomicOr(&w.counters->overflow, ovf);
+        if (max_faces) atomicMax(&w.counters->max_epa_faces, max_faces);
+    }
+}
+
+__global__ void __launch_bounds__(kNpThreads, NANS_EPAW_MINBLOCKS) narrowphase_world_epa_kernel(DeviceWorld w)
+{
+    EpaArena E;
+    NpShapes S;
+    const int lane = threadIdx.x & 31;
+    const uint2 *list = reinterpret_cast<const uint2 *>(w.inc);
+    const int count = min(w.counters->pad[kNpListCount], w.max_contacts);
+    int ovf = 0, max_faces = 0, found = 0;
+    // tickets [0, nd32): the deferred GJK pairs, 32 per ticket, taken FIRST (each runs up to ~60 more evolutions: started
+    // early they end inside the kernel instead of forming its tail); tickets from nd32 on: the EPA list
+    const int nd = min(w.counters->pad[kNpDeferCount], w.max_contacts);
+    const int nd32 = (nd + 31) & ~31;
+    while (true) {
+        int base = 0;
+        if (lane == 0) base = atomicAdd(&w.counters->pad[kNpListTicket], 32);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (base >= nd32 + count) break;
+        if (base < nd32) {
+            const int k = base + lane;
+            if (k < nd) {
+                const int p = w.succ_a[k];
+                const uint32_t rec = (uint32_t)w.succ_b[k];
+                int n = w.run_flag[k] & 255, iter = w.run_flag[k] >> 8;
+                const int ra = w.pair_a[p], rb = w.pair_b[p];
+                np_load_world_shapes(w, ra, rb, false, false, S);
+                GjkVertex<false, false> s[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    s[j].a.idx = (int)((rec >> (8 * j)) & 15u);
+                    s[j].b.idx = (int)((rec >> (8 * j + 4)) & 15u);
+                    s[j].P = S.vertex(0, s[j].a.idx) - S.vertex(1, s[j].b.idx);
+                }
+                const int ev = gjk_resume<false, false>(S, s, n, iter, 1000);
+                NpResult r;
+                r.gjk = ev;
+                r.hit = 0;
+                r.PA = r.PB = r.N = V3(0.f, 0.f, 0.f);
+                if (ev == kFoundIntersection) {
+                    ++found;
+                    r.hit = epa_resolve<false, false>(S, s, E, r.PA, r.PB, r.N, ovf, max_faces);
+                }
+                np_store_hit(w, p, r);
+            }
+            continue;
+        }
+        const int k = base - nd32 + lane;
+        if (k < count) {
+            const uint2 e = list[k];
+            const int p = (int)e.x;
+            const int ra = w.pair_a[p], rb = w.pair_b[p];
+            load_box(0, w.verts + 6 * (size_t)ra);
+            if (rb < 0) load_box(1, w.st_verts + 6 * (-rb - 1)); else load_box(1, w.verts + 6 * (size_t)rb);
+            GjkVertex<false, false> s[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                s[j].a.idx = (int)((e.y >> (8 * j)) & 15u);
+                s[j].b.idx = (int)((e.y >> (8 * j + 4)) & 15u);
+                s[j].P = S.vertex(0, s[j].a.idx) - S.vertex(1, s[j].b.idx);   // CalculateSupport's P = SupA - SupB
+            }
+            NpResult r;
+            r.gjk = kFoundIntersection;
+            r.PA = r.PB = r.N = V3(0.f, 0.f, 0.f);
+            r.hit = epa_resolve<false, false>(S, s, E, r.PA, r.PB, r.N, ovf, max_faces);
+            np_store_hit(w, p, r);
+        }
+    }
+    ovf = __reduce_or_sync(0xffffffffu, ovf);
+    max_faces = __reduce_max_sync(0xffffffffu, max_faces);
+    found = __reduce_add_sync(0xffffffffu, found);
     if (lane == 0) {
         if (found) atomicAdd(&w.counters->n_gjk_found, found);
         if (ovf) atomicOr(&w.counters->overflow, ovf);
@@ -384,8 +584,37 @@ int launch_narrowphase(World *w)
     // the work counter lives in the Counters pad (zeroed with the block at the start of detect)
     int *work = &d.counters->pad[0];
     // pair count is device-resident: size the grid for the capacity, CTAs beyond the work exit at once
-    const int grid = np_grid(div_up(d.max_pairs, kNpThreads));
-    narrowphase_world_kernel<<<grid, kNpThreads, 0, w->stream>>>(d, work);
+    const int need = div_up(d.max_pairs, kNpThreads);
+    // two kernels (GJK, then EPA over the list of intersecting pairs) for a cube-only world, one kernel for a world
+    // with spheres (measured: 4096 x 64-body worlds with 16 spheres each, 0.257 ms in one kernel, 0.280 in two);
+    // NANS_NP_SPLIT=0/1 forces either form (A/B runs)
+    static int split_env = -2;
+    if (split_env == -2) { const char *e = getenv("NANS_NP_SPLIT"); split_env = e ? atoi(e) : -1; }
+    const bool split = split_env < 0 ? d.n_spheres == 0 : split_env != 0;
+    if (!split) {
+        narrowphase_world_kernel<<<np_grid(need), kNpThreads, 0, w->stream>>>(d, work);
+        NANS_LAUNCH_CHECK();
+        return NANS_OK;
+    }
+    static int gjk_per_sm[2] = {0, 0}, epa_per_sm = 0;
+    if (!epa_per_sm) {
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&gjk_per_sm[0], narrowphase_world_gjk_kernel<false>, kNpThreads, 0);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&gjk_per_sm[1], narrowphase_world_gjk_kernel<true>, kNpThreads, 0);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&epa_per_sm, narrowphase_world_epa_kernel, kNpThreads, 0);
+        if (gjk_per_sm[0] < 1) gjk_per_sm[0] = 1;
+        if (gjk_per_sm[1] < 1) gjk_per_sm[1] = 1;
+        if (epa_per_sm < 1) epa_per_sm = 1;
+        const char *e = getenv("NANS_EPAW_CTAS");       // experiment: fewer resident CTAs = more L1 per polytope arena
+        if (e && atoi(e) > 0 && atoi(e) < epa_per_sm) epa_per_sm = atoi(e);
+    }
+    const int sph = d.n_spheres > 0;
+    const int g1 = need < kNumSMs * gjk_per_sm[sph] ? need : kNumSMs * gjk_per_sm[sph];
+    if (sph) narrowphase_world_gjk_kernel<true><<<g1, kNpThreads, 0, w->stream>>>(d, work);
+    else narrowphase_world_gjk_kernel<false><<<g1, kNpThreads, 0, w->stream>>>(d, work);
+    NANS_LAUNCH_CHECK();
+    const int need2 = div_up(d.max_contacts, kNpThreads);
+    const int g2 = need2 < kNumSMs * epa_per_sm ? need2 : kNumSMs * epa_per_sm;
+    narrowphase_world_epa_kernel<<<g2, kNpThreads, 0, w->stream>>>(d);
     NANS_LAUNCH_CHECK();
     return NANS_OK;
 }

@@ -201,8 +201,51 @@ __device__ __forceinline__ int evolve_simplex(const NpShapes &S, GjkVertex<AS, B
 // the unflipped unit normal n with d = dot(n, A.P), and the packed vertex indices a | b<<8 | c<<16.
 // (Carrying A.P in the record as well saved a dependent load but grew the arena: 640 threads/SM x
 // the touched part already exceeds L1, and the smaller record measured 6 % faster.)
+// The polytope's first kEpaShP vertices live in SHARED memory, transposed like the shapes ([3 * k + r][thread]: any
+// per-lane index is bank-conflict free): every P access feeds arithmetic at once (the face scan's `ns.P - P[a]`
+// with a per-lane index, the class scan of a new vertex, a new face's edges), and in the local-memory arena those
+// loads were 45 % of the EPA kernel's stall samples (profiles/r3_np_split_ncu_summary.txt).  Later vertices (only
+// long EPA runs have them) stay in the arena.
+#ifndef NANS_EPA_SHP
+#define NANS_EPA_SHP 0
+#endif
+constexpr int kEpaShP = NANS_EPA_SHP;
+#ifndef NANS_EPA_EDGE4
+#define NANS_EPA_EDGE4 0
+#endif
+#ifndef NANS_EPA_CLS_NOBREAK
+#define NANS_EPA_CLS_NOBREAK 0
+#endif
+#ifndef NANS_EPA_FACE_PIPE2
+#define NANS_EPA_FACE_PIPE2 0
+#endif
+#if NANS_EPA_SHP > 0
+__shared__ float g_np_P[3 * kEpaShP * kNpThreads];
+#endif
+
 struct EpaGenericArena {
-    vec3 P[kEpaMaxVerts];
+    vec3 Pl[kEpaMaxVerts - kEpaShP];
+    __device__ __forceinline__ vec3 getP(int i) const
+    {
+#if NANS_EPA_SHP > 0
+        if (i < kEpaShP) {
+            const float *p = g_np_P + 3 * i * kNpThreads + threadIdx.x;
+            return V3(p[0], p[kNpThreads], p[2 * kNpThreads]);
+        }
+#endif
+        return Pl[i - kEpaShP];
+    }
+    __device__ __forceinline__ void setP(int i, vec3 v)
+    {
+#if NANS_EPA_SHP > 0
+        if (i < kEpaShP) {
+            float *p = g_np_P + 3 * i * kNpThreads + threadIdx.x;
+            p[0] = v.x; p[kNpThreads] = v.y; p[2 * kNpThreads] = v.z;
+            return;
+        }
+#endif
+        Pl[i - kEpaShP] = v;
+    }
     vec3 SA[kEpaMaxVerts], SB[kEpaMaxVerts];    // sphere sides only
     uint8_t ia[kEpaMaxVerts], ib[kEpaMaxVerts]; // box sides only
     uint8_t cid[kEpaMaxVerts];                  // lowest vertex index with an equal P (kCidNaN: equal to nothing)
@@ -220,15 +263,21 @@ constexpr int kCidNaN = 254;
 template <bool AS, bool BS>
 __device__ __forceinline__ void epa_store_vertex(EpaGenericArena &E, int i, const GjkVertex<AS, BS> &v)
 {
-    E.P[i] = v.P;
+    E.setP(i, v.P);
     if constexpr (AS) E.SA[i] = v.a.v; else E.ia[i] = (uint8_t)v.a.idx;
     if constexpr (BS) E.SB[i] = v.b.v; else E.ib[i] = (uint8_t)v.b.idx;
     int c = i;
     if (!equal(v.P, v.P)) {
         c = kCidNaN;
     } else {
+#if NANS_EPA_CLS_NOBREAK
+        // lowest equal index without an early exit: the loads do not wait for each other's compare
+        for (int j = i - 1; j >= 0; --j)
+            if (equal(E.getP(j), v.P)) c = j;
+#else
         for (int j = 0; j < i; ++j)
-            if (equal(E.P[j], v.P)) { c = j; break; }
+            if (equal(E.getP(j), v.P)) { c = j; break; }
+#endif
     }
     E.cid[i] = (uint8_t)c;
 }
@@ -252,7 +301,7 @@ __device__ __forceinline__ void epa_track_min(float d, int slot, float &cur, int
 __device__ __forceinline__ void epa_push_face(EpaGenericArena &E, int &nf, int a, int b, int c, vec3 pa, float &cur, int &ci)
 {
     // PushTriangle, code/nans.cpp:293-322 (flip folded into the sign of d); pa == E.P[a]
-    const vec3 n = normalize(cross(E.P[b] - pa, E.P[c] - pa));
+    const vec3 n = normalize(cross(E.getP(b) - pa, E.getP(c) - pa));
     const float d = dot(pa, n);
     E.fnd[nf] = make_float4(n.x, n.y, n.z, d);
     E.fidx[nf] = (uint32_t)a | ((uint32_t)b << 8) | ((uint32_t)c << 16);
@@ -273,7 +322,21 @@ __device__ __forceinline__ void epa_push_edge(EpaGenericArena &E, int &ne, int a
     // a NaN vertex equals nothing, itself included: its id on the probing side never matches a stored one
     const uint32_t want = (cb == kCidNaN ? 255u : cb) | ((ca == kCidNaN ? 255u : ca) << 8);
     int i = 0;
+#if NANS_EPA_EDGE4
+    // four entries per round trip (the one-at-a-time walk is a chain of dependent local loads); entries past ne are
+    // read (inside the array) and ignored
+    int at = -1;
+    for (int b = 0; b < ne && at < 0; b += 4) {
+        const uint32_t e0 = E.edge[b], e1 = E.edge[b + 1], e2 = E.edge[b + 2], e3 = E.edge[b + 3];
+        if ((e0 >> 16) == want) at = b;
+        else if (b + 1 < ne && (e1 >> 16) == want) at = b + 1;
+        else if (b + 2 < ne && (e2 >> 16) == want) at = b + 2;
+        else if (b + 3 < ne && (e3 >> 16) == want) at = b + 3;
+    }
+    i = at < 0 ? ne : at;
+#else
     while (i < ne && (E.edge[i] >> 16) != want) ++i;
+#endif
     if (i < ne) {
         for (int k = i; k < ne - 1; ++k) E.edge[k] = E.edge[k + 1];
         --ne;
@@ -307,8 +370,8 @@ __device__ __forceinline__ int epa_resolve(const NpShapes &S, const GjkVertex<AS
             const int a = f & 255, b = (f >> 8) & 255, c = (f >> 16) & 255;
             // Barycentric, code/nans.cpp:772-785
             const vec3 Pp = N * cur;
-            const vec3 A0 = E.P[a];
-            const vec3 v0 = E.P[b] - A0, v1 = E.P[c] - A0, v2 = Pp - A0;
+            const vec3 A0 = E.getP(a);
+            const vec3 v0 = E.getP(b) - A0, v1 = E.getP(c) - A0, v2 = Pp - A0;
             const float d00 = dot(v0, v0), d01 = dot(v0, v1), d11 = dot(v1, v1);
             const float d20 = dot(v2, v0), d21 = dot(v2, v1);
             const float denom = fsub(fmul(d00, d11), fmul(d01, d01));
@@ -329,13 +392,32 @@ __device__ __forceinline__ int epa_resolve(const NpShapes &S, const GjkVertex<AS
         // stays converged over the face scan.
         const int nf_old = nf;
         int keep = 0, nvis = 0;
+#if NANS_EPA_FACE_PIPE2
+        // two faces in flight: face i's record AND its vertex A (a dependent, per-lane-indexed load) are fetched one
+        // iteration ahead, face i + 2's record two ahead
+        float4 nd_next = E.fnd[0];
+        uint32_t f_next = E.fidx[0];
+        vec3 pa_next = E.getP(f_next & 255);
+        float4 nd_nn = nd_next;
+        uint32_t f_nn = f_next;
+        if (nf > 1) { nd_nn = E.fnd[1]; f_nn = E.fidx[1]; }
+        for (int i = 0; i < nf; ++i) {
+            const float4 nd = nd_next;
+            const uint32_t f = f_next;
+            const vec3 pa_cur = pa_next;
+            nd_next = nd_nn; f_next = f_nn;
+            if (i + 1 < nf) pa_next = E.getP(f_next & 255);
+            if (i + 2 < nf) { nd_nn = E.fnd[i + 2]; f_nn = E.fidx[i + 2]; }
+            const vec3 tmp = ns.P - pa_cur;
+#else
         float4 nd_next = E.fnd[0];
         uint32_t f_next = E.fidx[0];
         for (int i = 0; i < nf; ++i) {
             const float4 nd = nd_next;
             const uint32_t f = f_next;
             if (i + 1 < nf) { nd_next = E.fnd[i + 1]; f_next = E.fidx[i + 1]; }
-            const vec3 tmp = ns.P - E.P[f & 255];
+            const vec3 tmp = ns.P - E.getP(f & 255);
+#endif
             if (dot(face_normal_flipped(nd), tmp) > 0.0f) {
                 E.vis[nvis++] = f;
             } else {
