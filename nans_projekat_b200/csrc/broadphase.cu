@@ -348,6 +348,9 @@ constexpr int kPairSlots = 24;
 #ifndef NANS_PC_PIPELINE
 #define NANS_PC_PIPELINE 1
 #endif
+// (Round 2 also measured SEVERAL threads per body, each walking every 2nd / 4th / 7th neighbour cell: broadphase stage
+// 0.283 -> 0.298 / 0.330 / 0.358 ms on the 1 M-cube pile.  The kernel is bound by issued instructions and L2 requests,
+// not by the length of one body's probe chain; one thread per body stays.)
 #ifndef NANS_PC_MINBLOCKS
 #define NANS_PC_MINBLOCKS 10   // 47 registers with two candidate records in flight (sweep, broadphase stage: w2/b10 0.415, w2/b9 0.413, w2/b12 0.445 (spills), w3/b10 0.448, w3/b8 0.437, w4/b8 0.437, w4/b6 0.434, w1/b12 0.452 ms)
 #endif
