@@ -213,6 +213,11 @@ int nans_check_collision_device_status(int32_t *overflow_bits);
 /* debug aid: per-contact start time (ns) and dependency level of the last solve (NANS_SOLVER_TRACE=1) */
 int nans_debug_solver_trace(nans_world *w, uint64_t *times, int32_t *levels, int32_t cap);
 
+/* debug aid: the library's exclusive prefix sum over n uint32 (csrc/scan.cu; every offset table of the step comes out of
+ * it), host buffers in and out, on the current device: out[i] = in[0] + ... + in[i-1].  Lets the tests drive
+ * it at any length. */
+int nans_debug_scan(const uint32_t *in, uint32_t *out, int32_t n);
+
 /* kernel-launch counter (all launches issued by this library in this process) */
 uint64_t nans_kernel_launches(void);
 

@@ -39,7 +39,7 @@ EXPORTS = ("nans_world_create", "nans_world_destroy", "nans_world_arena_bytes", 
            "nans_world_set_body", "nans_world_upload_async", "nans_world_download_async", "nans_world_wait", "nans_world_snapshot", "nans_world_restore", "nans_integrate_forces", "nans_detect_collisions",
            "nans_solve_constraints", "nans_integrate_velocities", "nans_rebuild_vertices", "nans_step", "nans_step_profiled",
            "nans_synchronize", "nans_get_stats", "nans_get_contacts", "nans_get_pairs", "nans_set_contacts",
-           "nans_check_collision_batch", "nans_check_collision_device", "nans_check_collision_device_status", "nans_kernel_launches", "nans_debug_solver_trace", "nans_world_set_solver", "nans_world_models",
+           "nans_check_collision_batch", "nans_check_collision_device", "nans_check_collision_device_status", "nans_kernel_launches", "nans_debug_solver_trace", "nans_debug_scan", "nans_world_set_solver", "nans_world_models",
            "nans_slab_unique_id", "nans_slab_init", "nans_slab_ipc_handle", "nans_slab_connect", "nans_slab_step",
            "nans_slab_status", "nans_slab_row_gids")
 
@@ -99,6 +99,7 @@ def lib():
     L.nans_slab_status.argtypes = [C.c_void_p, i32p, i32p, C.POINTER(C.c_int64)]
     L.nans_slab_row_gids.argtypes = [C.c_void_p, i32p, C.c_int32, i32p]
     L.nans_debug_solver_trace.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32]
+    L.nans_debug_scan.argtypes = [C.c_void_p, C.c_void_p, C.c_int32]
     _lib = L
     return L
 

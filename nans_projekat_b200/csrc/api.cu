@@ -212,6 +212,31 @@ int nans_device_count(void)
 
 uint64_t nans_kernel_launches(void) { return g_launches; }
 
+int nans_debug_scan(const uint32_t *in, uint32_t *out, int32_t n)
+{
+    if (n < 0 || (n > 0 && (!in || !out))) return fail(NANS_ERR_ARG, "nans_debug_scan: bad arguments");
+    if (n == 0) return NANS_OK;
+    uint32_t *d = nullptr, *scratch = nullptr;
+    const size_t sb = sizeof(uint32_t) * (size_t)scan_scratch_elems(n);
+    NANS_CUDA(cudaMalloc(&d, sizeof(uint32_t) * (size_t)n));
+    if (cudaMalloc(&scratch, sb) != cudaSuccess) { cudaFree(d); return fail(NANS_ERR_CUDA, "nans_debug_scan: out of device memory"); }
+    int rc = NANS_OK;
+    auto body = [&]() -> int {
+        NANS_CUDA(cudaMemset(scratch, 0, sb));
+        NANS_CUDA(cudaMemcpy(d, in, sizeof(uint32_t) * (size_t)n, cudaMemcpyHostToDevice));
+        for (int rep = 0; rep < 2; ++rep) {        // twice: the second run sees the re-armed scratch (epoch + 1) and, in place, the first one's sums
+            if (rep == 1) NANS_CUDA(cudaMemcpy(d, in, sizeof(uint32_t) * (size_t)n, cudaMemcpyHostToDevice));
+            const int r = exclusive_scan_u32(d, d, n, scratch, 0);
+            if (r) return r;
+        }
+        NANS_CUDA(cudaMemcpy(out, d, sizeof(uint32_t) * (size_t)n, cudaMemcpyDeviceToHost));
+        return NANS_OK;
+    };
+    rc = body();
+    cudaFree(d); cudaFree(scratch);
+    return rc;
+}
+
 uint64_t nans_world_arena_bytes(const nans_world_desc *desc)
 {
     if (!desc) return 0;

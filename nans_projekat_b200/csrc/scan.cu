@@ -109,6 +109,9 @@ __global__ void __launch_bounds__(kScanThreads) scan_apply_kernel(const uint32_t
 // predecessors 32 descriptors at a time.  The epoch lives in device memory and is advanced by the
 // last block to finish, so stale descriptors never need clearing and the launch replays unchanged
 // inside a CUDA graph.  scratch: [0] ticket, [1] epoch, [2] finished blocks, [4..] descriptors.
+// (Round 2 measured a FLAT look-back for scans of up to 1024 tiles -- every block sums the aggregates of all its
+// predecessors in one sweep instead of walking back 32 at a time: 0.943 vs 0.940 ms per step, no difference; the
+// ~11 us of a 2 M-element scan is not the look-back chain.  Removed.)
 constexpr int kLbThreads = 256;
 constexpr int kLbItems = 16;
 constexpr int kLbTile = kLbThreads * kLbItems;   // 4096

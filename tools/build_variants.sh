@@ -7,10 +7,10 @@ V=gpurun_variants; mkdir -p $V; rm -f $V/*.so
 C=nans_projekat_b200/csrc
 for spec in "$@"; do
   name="${spec%%:*}"; flags="${spec#*:}"
-  rm -f $C/narrowphase.o $C/solver.o $C/broadphase.o
+  rm -f $C/*.o
   make -C $C EXTRA="$flags" >/dev/null 2>&1 || { echo "build failed: $spec"; continue; }
   regs=$(grep -A3 "Compiling entry function '_ZN4nans24narrowphase_world" $C/narrowphase.ptxas.log | grep -o "Used [0-9]* registers.*smem" | head -1)
   echo "$name [$flags]: $regs"
   cp nans_projekat_b200/libnans_b200.so $V/$name.so
 done
-rm -f $C/narrowphase.o $C/solver.o $C/broadphase.o; make -C $C >/dev/null 2>&1
+rm -f $C/*.o; make -C $C >/dev/null 2>&1
