@@ -520,44 +520,75 @@ __global__ void __launch_bounds__(kNpThreads, NANS_GJK_MINBLOCKS) gjk_split_kern
 // 27.2 ms, against 29.6-35.4 ms for a resumable per-iteration form with lane-level refill (lanes at different iteration
 // numbers carry polytopes of very different sizes and in lock step every lane pays for the largest) and 40.9 ms for
 // GJK + EPA in one kernel.  Resident CTAs per SM 2..5 make no difference.
+//
+// Round 2: in PASSES with growing iteration budgets.  A chunk runs as long as its slowest lane, and EPA lengths of
+// random pairs are long-tailed (cube-cube: median 6, p99 12, max 23; cube-sphere: median 9, p99 24, max 64 iterations;
+// each iteration costs more than the one before it, the polytope grows): 0.37 (CC) / 0.25 (CS) of the lane-time of a
+// chunk is useful.  A pass gives every pair of its list `budget` iterations; a pair that needs more is appended to
+// the next pass's list and RUN AGAIN from its saved simplex there, among pairs that are all long.  Redoing the first
+// iterations of the long pairs costs less than the short pairs' idle lanes (oracle iteration counts, cost model
+// k (5 + k): two budgets bring the lane-time to 0.69 (CC) / 0.57 (CS) of the single pass).  Results are per pair and
+// the same code runs each time, so nothing observable changes.
+struct EpaPass {
+    const int32_t *list;     // pairs of this pass
+    const int32_t *count;    // their number (device)
+    int32_t *ticket;         // chunk tickets
+    int32_t *next_list;      // pairs that ran out of budget (null in the last pass)
+    int32_t *next_count;
+    int budget[4];           // iterations per class (65 = no limit)
+};
+
 template <bool AS, bool BS, typename Src>
-__device__ __noinline__ void epa_chunk_list(const Src &src, const SplitScratch &sc, NpShapes &S, EpaArena &E,
-                                            int &ovf, int &max_faces)
+__device__ __noinline__ void epa_chunk_list(const Src &src, const SplitScratch &sc, const EpaPass (&pass)[4], NpShapes &S,
+                                            EpaArena &E, int &ovf, int &max_faces)
 {
     constexpr int cls = 2 * (int)AS + (int)BS;
     const int lane = threadIdx.x & 31;
-    const int32_t *list = sc.list[cls];
-    const int count = sc.head[cls];
+    const EpaPass &ps = pass[cls];
+    const int32_t *list = ps.list;
+    const int count = *ps.count;
+    const int budget = ps.budget[cls];
     while (true) {
         int base = 0;
-        if (lane == 0) base = atomicAdd(sc.head + 4 + cls, 32);
+        if (lane == 0) base = atomicAdd(ps.ticket, 32);
         base = __shfl_sync(0xffffffffu, base, 0);
         if (base >= count) break;
         const int k = base + lane;
+        bool again = false;
+        int p = 0;
         if (k < count) {
-            const int p = list[k];
+            p = list[k];
             src.load(p, AS, BS, S);
             GjkVertex<AS, BS> s[4];
             int n_, iter_;
             load_simplex<AS, BS>(S, sc.rec, p, s, n_, iter_);
             vec3 PA, PB, N;
-            int hit;
-            hit = epa_resolve<AS, BS>(S, s, E, PA, PB, N, ovf, max_faces);
-            if (hit) src.store_hit(p, PA, PB, N);
+            const int hit = epa_resolve<AS, BS>(S, s, E, PA, PB, N, ovf, max_faces, budget);
+            if (hit == 1) src.store_hit(p, PA, PB, N);
+            again = hit == kEpaOutOfBudget && budget < 65;
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, again);
+        if (m && ps.next_list) {
+            int at = 0;
+            if (lane == 0) at = atomicAdd(ps.next_count, __popc(m));
+            at = __shfl_sync(0xffffffffu, at, 0) + __popc(m & ((1u << lane) - 1u));
+            if (again) ps.next_list[at] = p;
         }
     }
 }
 
 template <typename Src>
-__global__ void __launch_bounds__(kNpThreads, NANS_EPA_MINBLOCKS) epa_refill_kernel(Src src, SplitScratch sc, Counters *counters)
+__global__ void __launch_bounds__(kNpThreads, NANS_EPA_MINBLOCKS) epa_refill_kernel(Src src, SplitScratch sc, Counters *counters,
+                                                                                     EpaPass p0, EpaPass p1, EpaPass p2, EpaPass p3)
 {
     EpaArena E;
     NpShapes S;
     int ovf = 0, max_faces = 0;
-    epa_chunk_list<false, false>(src, sc, S, E, ovf, max_faces);
-    epa_chunk_list<false, true>(src, sc, S, E, ovf, max_faces);
-    epa_chunk_list<true, false>(src, sc, S, E, ovf, max_faces);
-    epa_chunk_list<true, true>(src, sc, S, E, ovf, max_faces);
+    const EpaPass pass[4] = {p0, p1, p2, p3};
+    epa_chunk_list<false, false>(src, sc, pass, S, E, ovf, max_faces);
+    epa_chunk_list<false, true>(src, sc, pass, S, E, ovf, max_faces);
+    epa_chunk_list<true, false>(src, sc, pass, S, E, ovf, max_faces);
+    epa_chunk_list<true, true>(src, sc, pass, S, E, ovf, max_faces);
     ovf = __reduce_or_sync(0xffffffffu, ovf);
     max_faces = __reduce_max_sync(0xffffffffu, max_faces);
     if ((threadIdx.x & 31) == 0 && counters) {
@@ -680,8 +711,37 @@ int launch_narrowphase_batch(int n, const int32_t *type, const float4 *posrad_a,
             NANS_LAUNCH_CHECK();
         }
         const int g2 = need < kNumSMs * epa_per_sm ? need : kNumSMs * epa_per_sm;
-        epa_refill_kernel<BatchSrc><<<g2, kNpThreads, 0, s>>>(src, sc, counters);
-        NANS_LAUNCH_CHECK();
+        // EPA in up to three passes: list -> (pairs out of budget) glist -> list.  The GJK lists (glist) are idle once
+        // gjk_continue_kernel has run; the original list is idle once pass 0 has.  head: [16 + cls] / [20 + cls] count and
+        // tickets of pass 1, [24 + cls] / [28 + cls] of pass 2.
+        static int budgets[2][4] = {{-1}};
+        if (budgets[0][0] < 0) {
+            // per class {CC, CS, SC, SS}; NANS_EPA_BUDGETS="cc0,cs0,cc1,cs1" overrides (65 = no limit; A/B runs)
+            int b[4] = {7, 10, 12, 18};      // C3, 16 Mi pairs: 23.98 ms in one pass, 21.85 with these (6,8,10,14: 23.1; 8,12,-,-: 22.2)
+            const char *e = getenv("NANS_EPA_BUDGETS");
+            if (e) sscanf(e, "%d,%d,%d,%d", &b[0], &b[1], &b[2], &b[3]);
+            for (int k = 0; k < 4; ++k) if (b[k] < 1 || b[k] > 65) b[k] = 65;
+            budgets[0][0] = b[0]; budgets[0][1] = budgets[0][2] = b[1]; budgets[0][3] = 65;
+            budgets[1][0] = b[2]; budgets[1][1] = budgets[1][2] = b[3]; budgets[1][3] = 65;
+        }
+        for (int pass = 0; pass < 3; ++pass) {
+            EpaPass ps[4];
+            bool any_budget = false;
+            for (int c = 0; c < 4; ++c) {
+                EpaPass &q = ps[c];
+                const bool odd = pass & 1;
+                q.list = odd ? sc.glist[c] : sc.list[c];
+                q.count = pass == 0 ? sc.head + c : sc.head + 16 + 8 * (pass - 1) + c;
+                q.ticket = pass == 0 ? sc.head + 4 + c : sc.head + 20 + 8 * (pass - 1) + c;
+                q.next_list = pass == 2 ? nullptr : (odd ? sc.list[c] : sc.glist[c]);
+                q.next_count = pass == 2 ? nullptr : sc.head + 16 + 8 * pass + c;
+                for (int k = 0; k < 4; ++k) q.budget[k] = pass == 2 ? 65 : budgets[pass][k];
+                if (q.budget[c] < 65) any_budget = true;
+            }
+            epa_refill_kernel<BatchSrc><<<g2, kNpThreads, 0, s>>>(src, sc, counters, ps[0], ps[1], ps[2], ps[3]);
+            NANS_LAUNCH_CHECK();
+            if (!any_budget) break;          // this pass ran to the reference's own limit: nothing was deferred
+        }
     }
     return NANS_OK;
 }

@@ -26,6 +26,7 @@
 namespace nans {
 
 enum { kNoIntersection = 0, kFoundIntersection = 1, kStillEvolving = 2 };  // evolve_result, code/nans.h:89-94
+constexpr int kEpaOutOfBudget = 2;   // epa_resolve with an iteration budget: not finished (never returned for 65)
 
 #ifndef NANS_NP_THREADS
 #define NANS_NP_THREADS 128
@@ -349,7 +350,8 @@ __device__ __forceinline__ void epa_push_edge(EpaGenericArena &E, int &ne, int a
 // ResolveCollision, code/nans.cpp:788-904.  Returns the bool32 result; fills PointA/PointB/N.
 template <bool AS, bool BS>
 __device__ __forceinline__ int epa_resolve(const NpShapes &S, const GjkVertex<AS, BS> (&s)[4], EpaGenericArena &E,
-                                           vec3 &outPA, vec3 &outPB, vec3 &outN, int &ovf, int &max_faces)
+                                           vec3 &outPA, vec3 &outPB, vec3 &outN, int &ovf, int &max_faces,
+                                           int max_iters = 65)
 {
     // the simplex becomes the first four vertices and faces (:791-802)
 #pragma unroll
@@ -361,6 +363,9 @@ __device__ __forceinline__ int epa_resolve(const NpShapes &S, const GjkVertex<AS
     epa_push_face(E, nf, 0, 3, 1, s[0].P, cur, ci);  // ADB
     epa_push_face(E, nf, 1, 3, 2, s[1].P, cur, ci);  // BDC
     while (it++ <= 64) {            // MAX_EPA_ITERATIONS, code/nans.h:56
+        // a BUDGETED run (max_iters < 65: the multi-pass batch path) gives up before iteration max_iters + 1; the
+        // caller runs the pair again, from its simplex, with a larger budget
+        if (it > max_iters) return kEpaOutOfBudget;
         max_faces = max(max_faces, nf);
         const float4 cnd = E.fnd[ci];
         const vec3 N = face_normal_flipped(cnd);
