@@ -2,11 +2,10 @@
 argument also check that many hit flags against the reference binary.  usage: python tools/c3_time.py [pairs] [check]"""
 import json, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-import bench
 
-if __name__ != "__main__":      # the checker's worker processes re-import this file (spawn)
-    raise SystemExit(0)
-n = int(sys.argv[1]) if len(sys.argv) > 1 else 16777216
-chk = int(sys.argv[2]) if len(sys.argv) > 2 else 0
-r = bench.run_c3(n, 0, chk, reps=3)
-print(json.dumps({k: r[k] for k in ("pairs", "ms", "pairs_per_s", "hit_rate", "flags_bit_exact", "mismatches") if k in r}))
+if __name__ == "__main__":          # the checker's worker processes re-import this file (spawn)
+    import bench
+    n = int(sys.argv[1]) if len(sys.argv) > 1 else 16777216
+    chk = int(sys.argv[2]) if len(sys.argv) > 2 else 0
+    r = bench.run_c3(n, 0, chk, reps=3)
+    print(json.dumps({k: r[k] for k in ("pairs", "ms", "pairs_per_s", "hit_rate", "flags_bit_exact", "mismatches") if k in r}))
