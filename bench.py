@@ -648,11 +648,17 @@ def main():
         # only when the capture was taken on THIS workload (else null: a capture of another scene says nothing here)
         tj = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
         if tj.get("workload") == workload_name:
-            kname = {"narrowphase": "narrowphase_world_kernel", "solver": "solve_versioned_kernel",
-                     "integrate_forces": "integrate_forces_kernel", "integrate_velocities": "integrate_velocities_kernel",
-                     "broadphase": "pair_count_kernel"}[dom]
-            traffic, traffic_src = tj["dram_bytes_per_launch"].get(kname), tj["source"] + " : " + kname
-            pipes = tj.get("pipes", {}).get(kname)
+            # the narrowphase stage of a cube-only world is two kernels (GJK, then EPA over the intersecting pairs):
+            # traffic = both, pipes = the EPA kernel's (80 % of the stage)
+            knames = {"narrowphase": ["narrowphase_world_epa_kernel", "narrowphase_world_gjk_kernel"],
+                      "solver": ["solve_versioned_kernel"], "integrate_forces": ["integrate_forces_kernel"],
+                      "integrate_velocities": ["integrate_velocities_kernel"], "broadphase": ["pair_count_kernel"]}[dom]
+            if dom == "narrowphase" and knames[0] not in tj["dram_bytes_per_launch"]:
+                knames = ["narrowphase_world_kernel"]          # a world with spheres: one kernel
+            got = [tj["dram_bytes_per_launch"].get(k) for k in knames]
+            traffic = sum(got) if all(g is not None for g in got) else None
+            traffic_src = tj["source"] + " : " + " + ".join(knames)
+            pipes = tj.get("pipes", {}).get(knames[0])
     except Exception:
         pass
     limiter = {"narrowphase": "FP32 issue slots / divergence / local-memory latency of GJK+EPA (not HBM): see pipes_ncu",

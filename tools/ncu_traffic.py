@@ -25,7 +25,8 @@ for r in rows[2:]:
             "l1_hit_pct": f(r, "l1tex__t_sector_hit_rate.pct"),
             "duration_us": f(r, "gpu__time_duration.sum") * {"us": 1.0, "ms": 1e3, "ns": 1e-3}.get(unit["gpu__time_duration.sum"], 1.0),
         }
-keep = ("narrowphase_world_kernel", "solve_versioned_kernel", "pair_count_kernel")
+keep = ("narrowphase_world_kernel", "narrowphase_world_epa_kernel", "narrowphase_world_gjk_kernel", "solve_versioned_kernel",
+        "pair_count_kernel")
 print(json.dumps({"source": sys.argv[2] if len(sys.argv) > 2 else sys.argv[1],
                   "workload": sys.argv[3] if len(sys.argv) > 3 else None,   # bench.py only uses the capture for this workload
                   "dram_bytes_per_launch": dram,

@@ -35,5 +35,15 @@ st = w.stats()
 c = w.contacts(); a, b = w.pairs(); d = w.download()
 q = scenes.narrowphase_pairs(2048, seed=3)
 r = check_collision(q["type"], q["pos_a"], q["verts_a"], q["rad_a"], q["pos_b"], q["verts_b"], q["rad_b"])
+# a cube-only world: the two-kernel narrowphase (GJK kernel, deferred stragglers + EPA kernel) instead of the one-kernel form
+s2 = scenes.cube_drop(n=400, dims=(8, 7, 8), spacing=1.02, jitter=0.08)
+w2 = World(s2)
+w2.rebuild_vertices()
+for k in range(14):
+    w2.step(dt)
+st2 = w2.stats()
+c2 = w2.contacts()
+w2.close()
+print("cube-only world ok:", st2, "contacts", len(c2))
 print("sanitize run ok:", st, "contacts", len(c), "pairs", len(a), "hits", int(r["hit"].sum()))
 w.close()
