@@ -61,12 +61,6 @@ __device__ __forceinline__ NpResult dispatch(bool a_sphere, bool b_sphere, NpSha
     return check_collision<true, true>(S, E, ovf, max_faces);
 }
 
-constexpr int kNpListCount = 4, kNpListTicket = 5, kNpDeferCount = 6;    // Counters::pad slots (zeroed with the block per detect)
-#ifndef NANS_NP_GJK_CAP_WORLD
-#define NANS_NP_GJK_CAP_WORLD 6
-#endif
-constexpr int kNpGjkCap = NANS_NP_GJK_CAP_WORLD;   // evolutions in the GJK kernel (a pile's pairs take 5; 1000 = no cap)
-
 // (Round 2 measured a CTA-level regrouping of the pairs between EPA iterations -- one iteration per round, the pairs
 // still iterating compacted onto the first lanes, polytopes in a slot-addressed global pool so that a pair can change
 // lanes -- to attack the 13.5 of 32 active lanes of this kernel.  Bit-exact, and slower: 0.77 vs 0.50 ms on the
@@ -74,43 +68,6 @@ constexpr int kNpGjkCap = NANS_NP_GJK_CAP_WORLD;   // evolutions in the GJK kern
 // new point sees, how many horizon edges survive), not in the iteration counts, and the barriers cost 33 % of the
 // stall samples at 20 warps per SM.  The begin / iterate split of EPA it needed also cost the explicit-pairs EPA
 // kernel 12 % (config C3: 23.8 -> 26.6 ms).  profiles/r2_np_regroup_*.  The one-thread-per-pair kernel below stays.)
-// A box pair of the one-kernel form: GJK capped like the two-kernel form's; a pair still evolving (a miss cycling up to
-// the reference's 65 evolutions, while the other 31 lanes of the chunk wait) goes to the deferred list that
-// narrowphase_world_epa_kernel finishes.
-__device__ __noinline__ NpResult box_pair_capped(const DeviceWorld &w, int p, NpShapes &S, EpaArena &E, int &ovf, int &max_faces,
-                                                 bool &deferred)
-{
-    NpResult r;
-    GjkVertex<false, false> s[4];
-    int n = 0, iter = 0;
-    r.gjk = gjk_resume<false, false>(S, s, n, iter, kNpGjkCap);
-    r.hit = 0;
-    r.PA = r.PB = r.N = V3(0.f, 0.f, 0.f);
-    const bool defer = r.gjk == kStillEvolving && iter <= 64;
-    const unsigned act = __activemask();
-    const unsigned md = __ballot_sync(act, defer);
-    if (md) {
-        const int lane = threadIdx.x & 31, leader = __ffs(md) - 1;
-        int at = 0;
-        if (lane == leader) at = atomicAdd(&w.counters->pad[kNpDeferCount], __popc(md));
-        at = __shfl_sync(act, at, leader) + __popc(md & ((1u << lane) - 1u));
-        if (defer) {
-            if (at < w.max_contacts) {
-                uint32_t rec = 0;
-#pragma unroll
-                for (int k = 0; k < 4; ++k)
-                    if (k < n) rec |= ((uint32_t)s[k].a.idx | ((uint32_t)s[k].b.idx << 4)) << (8 * k);
-                w.succ_a[at] = p; w.succ_b[at] = (int32_t)rec; w.run_flag[at] = n | (iter << 8);
-                deferred = true;
-                return r;
-            }
-            ovf |= OVF_CONTACTS;
-        }
-    }
-    if (r.gjk == kFoundIntersection) r.hit = epa_resolve<false, false>(S, s, E, r.PA, r.PB, r.N, ovf, max_faces);
-    return r;
-}
-
 __device__ __forceinline__ void np_world_pair(const DeviceWorld &w, int p, int ra, int rb, NpShapes &S, EpaArena &E,
                                               int &ovf, int &max_faces, int &found)
 {
@@ -128,14 +85,7 @@ __device__ __forceinline__ void np_world_pair(const DeviceWorld &w, int p, int r
         S.posB = V3(w.pos[rb]);
         if (b_sphere) S.radB = w.scale[rb].w; else load_box(1, w.verts + 6 * (size_t)rb);
     }
-    NpResult r;
-    if (!a_sphere && !b_sphere) {
-        bool deferred = false;
-        r = box_pair_capped(w, p, S, E, ovf, max_faces, deferred);
-        if (deferred) return;                 // its flag and contact come from the EPA kernel
-    } else {
-        r = dispatch(a_sphere, b_sphere, S, E, ovf, max_faces);
-    }
+    const NpResult r = dispatch(a_sphere, b_sphere, S, E, ovf, max_faces);
     found += (r.gjk == kFoundIntersection);
     w.pair_hit[p] = r.hit;
     if (r.hit) {
@@ -187,6 +137,11 @@ __global__ void __launch_bounds__(kNpThreads, NANS_NP_MINBLOCKS) narrowphase_wor
 // and a second kernel runs EPA over whole 32-entry chunks of that list.  Results are written per pair, so the list's
 // (atomic) order is not observable.  The list lives in the solver's schedule buffers, which are idle until the
 // contact list exists (inc: 8 B x 2 x max_contacts).
+constexpr int kNpListCount = 4, kNpListTicket = 5, kNpDeferCount = 6;    // Counters::pad slots (zeroed with the block per detect)
+#ifndef NANS_NP_GJK_CAP_WORLD
+#define NANS_NP_GJK_CAP_WORLD 6
+#endif
+constexpr int kNpGjkCap = NANS_NP_GJK_CAP_WORLD;   // evolutions in the GJK kernel (a pile's pairs take 5; 1000 = no cap)
 
 __device__ __forceinline__ void np_load_world_shapes(const DeviceWorld &w, int ra, int rb, bool a_sphere, bool b_sphere, NpShapes &S)
 {
@@ -662,11 +617,17 @@ int launch_narrowphase(World *w)
     // pair count is device-resident: size the grid for the capacity, CTAs beyond the work exit at once
     const int need = div_up(d.max_pairs, kNpThreads);
     // two kernels (GJK, then EPA over the list of intersecting pairs) for a cube-only world, one kernel for a world
-    // with spheres (measured: 4096 x 64-body worlds with 16 spheres each, 0.257 ms in one kernel, 0.280 in two);
+    // with spheres (measured: 4096 x 64-body worlds with 16 spheres each, 0.257 ms in one kernel, 0.280 in two; capping
+    // the one-kernel form's box-pair GJK and deferring the stragglers the same way: 0.318, its register budget breaks);
     // NANS_NP_SPLIT=0/1 forces either form (A/B runs)
     static int split_env = -2;
     if (split_env == -2) { const char *e = getenv("NANS_NP_SPLIT"); split_env = e ? atoi(e) : -1; }
     const bool split = split_env < 0 ? d.n_spheres == 0 : split_env != 0;
+    if (!split) {
+        narrowphase_world_kernel<<<np_grid(need), kNpThreads, 0, w->stream>>>(d, work);
+        NANS_LAUNCH_CHECK();
+        return NANS_OK;
+    }
     static int gjk_per_sm[2] = {0, 0}, epa_per_sm = 0;
     if (!epa_per_sm) {
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&gjk_per_sm[0], narrowphase_world_gjk_kernel<false>, kNpThreads, 0);
@@ -678,22 +639,13 @@ int launch_narrowphase(World *w)
         const char *e = getenv("NANS_EPAW_CTAS");       // experiment: fewer resident CTAs = more L1 per polytope arena
         if (e && atoi(e) > 0 && atoi(e) < epa_per_sm) epa_per_sm = atoi(e);
     }
-    const int need2 = div_up(d.max_contacts, kNpThreads);
-    int g2 = need2 < kNumSMs * epa_per_sm ? need2 : kNumSMs * epa_per_sm;
-    if (!split) {
-        // one kernel, then the EPA kernel for the few box pairs whose GJK ran past the cap (its list is empty here)
-        narrowphase_world_kernel<<<np_grid(need), kNpThreads, 0, w->stream>>>(d, work);
-        NANS_LAUNCH_CHECK();
-        if (g2 > kNumSMs) g2 = kNumSMs;
-        narrowphase_world_epa_kernel<<<g2, kNpThreads, 0, w->stream>>>(d);
-        NANS_LAUNCH_CHECK();
-        return NANS_OK;
-    }
     const int sph = d.n_spheres > 0;
     const int g1 = need < kNumSMs * gjk_per_sm[sph] ? need : kNumSMs * gjk_per_sm[sph];
     if (sph) narrowphase_world_gjk_kernel<true><<<g1, kNpThreads, 0, w->stream>>>(d, work);
     else narrowphase_world_gjk_kernel<false><<<g1, kNpThreads, 0, w->stream>>>(d, work);
     NANS_LAUNCH_CHECK();
+    const int need2 = div_up(d.max_contacts, kNpThreads);
+    const int g2 = need2 < kNumSMs * epa_per_sm ? need2 : kNumSMs * epa_per_sm;
     narrowphase_world_epa_kernel<<<g2, kNpThreads, 0, w->stream>>>(d);
     NANS_LAUNCH_CHECK();
     return NANS_OK;
