@@ -198,58 +198,32 @@ __device__ __forceinline__ int evolve_simplex(const NpShapes &S, GjkVertex<AS, B
 }
 
 // ---- EPA --------------------------------------------------------------------------------------
-// Per-thread arena (local memory; only the touched part costs traffic).  A face record is 20 bytes:
-// the unflipped unit normal n with d = dot(n, A.P), and the packed vertex indices a | b<<8 | c<<16.
-// (Carrying A.P in the record as well saved a dependent load but grew the arena: 640 threads/SM x
-// the touched part already exceeds L1, and the smaller record measured 6 % faster.)
-// The polytope's first kEpaShP vertices live in SHARED memory, transposed like the shapes ([3 * k + r][thread]: any
-// per-lane index is bank-conflict free): every P access feeds arithmetic at once (the face scan's `ns.P - P[a]`
-// with a per-lane index, the class scan of a new vertex, a new face's edges), and in the local-memory arena those
-// loads were 45 % of the EPA kernel's stall samples (profiles/r3_np_split_ncu_summary.txt).  Later vertices (only
-// long EPA runs have them) stay in the arena.
-#ifndef NANS_EPA_SHP
-#define NANS_EPA_SHP 0
+// Per-thread arena in local memory; only the touched part costs traffic, and that part is what bounds the kernel:
+// the arenas of the resident threads (640 per SM) do not fit the L1 next to the staged shapes, fewer resident
+// threads run slower, so every byte the arena does not hold is a byte that cannot miss.  Hence:
+//   NANS_EPA_FACE16   a face record is 16 bytes {unflipped unit normal n, packed indices a | b<<8 | c<<16}; the plane
+//                     offset d = dot(P[a], n) is re-formed where it is used (P[a] is needed there anyway).  Off: 20
+//                     bytes {n, d} + indices.  (Carrying P[a] in the record as well was measured in round 1: slower.)
+//   NANS_EPA_PSHAPES  box pairs: a vertex is ONE 16-bit word (ia, ib, class); P is re-formed from the shapes in
+//                     shared memory (epa_P).  Off: 15 bytes per vertex {P, ia, ib, class}.
+// Measured (1 M-cube pile 100^3 / flat 250x250x16 / config C3): narrowphase stage 0.367 -> 0.355 -> 0.347 ms,
+// 0.723 -> 0.681 -> 0.661 ms, 21.85 -> 21.05 -> 19.45 ms.  Also measured, no gain, removed: the first 8-12 vertices in
+// shared memory (the larger carve-out halves the L1), a 4-wide edge search, a class scan without early exit, the
+// face scan's vertex fetched one face ahead (profiles/README.md).
+#ifndef NANS_EPA_PSHAPES
+#define NANS_EPA_PSHAPES 1
 #endif
-constexpr int kEpaShP = NANS_EPA_SHP;
-#ifndef NANS_EPA_EDGE4
-#define NANS_EPA_EDGE4 0
+#ifndef NANS_EPA_FACE16
+#define NANS_EPA_FACE16 1
 #endif
-#ifndef NANS_EPA_CLS_NOBREAK
-#define NANS_EPA_CLS_NOBREAK 0
-#endif
-#ifndef NANS_EPA_FACE_PIPE2
-#define NANS_EPA_FACE_PIPE2 0
-#endif
-#if NANS_EPA_SHP > 0
-__shared__ float g_np_P[3 * kEpaShP * kNpThreads];
-#endif
-
 struct EpaGenericArena {
-    vec3 Pl[kEpaMaxVerts - kEpaShP];
-    __device__ __forceinline__ vec3 getP(int i) const
-    {
-#if NANS_EPA_SHP > 0
-        if (i < kEpaShP) {
-            const float *p = g_np_P + 3 * i * kNpThreads + threadIdx.x;
-            return V3(p[0], p[kNpThreads], p[2 * kNpThreads]);
-        }
-#endif
-        return Pl[i - kEpaShP];
-    }
-    __device__ __forceinline__ void setP(int i, vec3 v)
-    {
-#if NANS_EPA_SHP > 0
-        if (i < kEpaShP) {
-            float *p = g_np_P + 3 * i * kNpThreads + threadIdx.x;
-            p[0] = v.x; p[kNpThreads] = v.y; p[2 * kNpThreads] = v.z;
-            return;
-        }
-#endif
-        Pl[i - kEpaShP] = v;
-    }
+    vec3 P[kEpaMaxVerts];                       // stored vertices (pairs with a sphere; box pairs re-form them, epa_P)
+    __device__ __forceinline__ vec3 getP(int i) const { return P[i]; }
+    __device__ __forceinline__ void setP(int i, vec3 v) { P[i] = v; }
     vec3 SA[kEpaMaxVerts], SB[kEpaMaxVerts];    // sphere sides only
     uint8_t ia[kEpaMaxVerts], ib[kEpaMaxVerts]; // box sides only
     uint8_t cid[kEpaMaxVerts];                  // lowest vertex index with an equal P (kCidNaN: equal to nothing)
+    uint16_t vw[kEpaMaxVerts];                  // NANS_EPA_PSHAPES, box pairs: ia | ib << 4 | cid << 8 (replaces P, ia, ib, cid)
     float4 fnd[kEpaMaxFaces];
     uint32_t fidx[kEpaMaxFaces];
     uint32_t vis[kEpaMaxFaces];                 // packed indices of the faces dissolved this iteration
@@ -261,34 +235,61 @@ constexpr int kCidNaN = 254;
 // The reference's edge cancels an opposite-winding edge BY VALUE of P (code/nans.h:251-254).  Float
 // equality is an equivalence on non-NaN vectors (+0 == -0 included), so every vertex gets the lowest
 // index of its class once, when it is stored, and the edge compares become one integer compare.
+// Vertex i of the polytope.  For a BOX pair the point is a pure function of two vertex indices, P = A[ia] - B[ib]
+// (CalculateSupport, :464-519: the same subtraction of the same operands), and the shapes sit in shared memory: with
+// NANS_EPA_PSHAPES the arena keeps ONE 16-bit word per vertex (ia, ib, class) instead of 15 bytes, and every use
+// re-forms P from six shared-memory loads.  The polytope arenas of the resident threads do not fit the L1 (DESIGN.md
+// 4): what the arena does not hold it cannot miss on.
+template <bool AS, bool BS> constexpr bool kPFromShapes = NANS_EPA_PSHAPES && !AS && !BS;
+
 template <bool AS, bool BS>
-__device__ __forceinline__ void epa_store_vertex(EpaGenericArena &E, int i, const GjkVertex<AS, BS> &v)
+__device__ __forceinline__ vec3 epa_P(const EpaGenericArena &E, const NpShapes &S, int i)
 {
-    E.setP(i, v.P);
-    if constexpr (AS) E.SA[i] = v.a.v; else E.ia[i] = (uint8_t)v.a.idx;
-    if constexpr (BS) E.SB[i] = v.b.v; else E.ib[i] = (uint8_t)v.b.idx;
+    if constexpr (kPFromShapes<AS, BS>) {
+        const uint32_t w = E.vw[i];
+        return S.vertex(0, w & 15u) - S.vertex(1, (w >> 4) & 15u);
+    } else {
+        return E.getP(i);
+    }
+}
+template <bool AS, bool BS>
+__device__ __forceinline__ uint32_t epa_cid(const EpaGenericArena &E, int i)
+{
+    if constexpr (kPFromShapes<AS, BS>) return (uint32_t)E.vw[i] >> 8; else return E.cid[i];
+}
+
+// The reference's edge cancels an opposite-winding edge BY VALUE of P (code/nans.h:251-254).  Float
+// equality is an equivalence on non-NaN vectors (+0 == -0 included), so every vertex gets the lowest
+// index of its class once, when it is stored, and the edge compares become one integer compare.
+template <bool AS, bool BS>
+__device__ __forceinline__ void epa_store_vertex(EpaGenericArena &E, const NpShapes &S, int i, const GjkVertex<AS, BS> &v)
+{
+    if constexpr (!kPFromShapes<AS, BS>) {
+        E.setP(i, v.P);
+        if constexpr (AS) E.SA[i] = v.a.v; else E.ia[i] = (uint8_t)v.a.idx;
+        if constexpr (BS) E.SB[i] = v.b.v; else E.ib[i] = (uint8_t)v.b.idx;
+    }
     int c = i;
     if (!equal(v.P, v.P)) {
         c = kCidNaN;
     } else {
-#if NANS_EPA_CLS_NOBREAK
-        // lowest equal index without an early exit: the loads do not wait for each other's compare
-        for (int j = i - 1; j >= 0; --j)
-            if (equal(E.getP(j), v.P)) c = j;
-#else
         for (int j = 0; j < i; ++j)
-            if (equal(E.getP(j), v.P)) { c = j; break; }
-#endif
+            if (equal(epa_P<AS, BS>(E, S, j), v.P)) { c = j; break; }
     }
-    E.cid[i] = (uint8_t)c;
+    if constexpr (kPFromShapes<AS, BS>) E.vw[i] = (uint16_t)((uint32_t)v.a.idx | ((uint32_t)v.b.idx << 4) | ((uint32_t)c << 8));
+    else E.cid[i] = (uint8_t)c;
 }
-template <bool AS> __device__ __forceinline__ vec3 epa_sup_a(const EpaGenericArena &E, const NpShapes &S, int i)
+template <bool AS, bool BS> __device__ __forceinline__ vec3 epa_sup_a(const EpaGenericArena &E, const NpShapes &S, int i)
 {
-    if constexpr (AS) return E.SA[i]; else return S.vertex(0, E.ia[i]);
+    if constexpr (AS) return E.SA[i];
+    else if constexpr (kPFromShapes<AS, BS>) return S.vertex(0, E.vw[i] & 15u);
+    else return S.vertex(0, E.ia[i]);
 }
-template <bool BS> __device__ __forceinline__ vec3 epa_sup_b(const EpaGenericArena &E, const NpShapes &S, int i)
+template <bool AS, bool BS> __device__ __forceinline__ vec3 epa_sup_b(const EpaGenericArena &E, const NpShapes &S, int i)
 {
-    if constexpr (BS) return E.SB[i]; else return S.vertex(1, E.ib[i]);
+    if constexpr (BS) return E.SB[i];
+    else if constexpr (kPFromShapes<AS, BS>) return S.vertex(1, (E.vw[i] >> 4) & 15u);
+    else return S.vertex(1, E.ib[i]);
 }
 
 // closest face = FIRST strict minimum of |d| in face order (:807-822).  The reference rescans every
@@ -299,15 +300,36 @@ __device__ __forceinline__ void epa_track_min(float d, int slot, float &cur, int
     if (slot == 0 || dist < cur) { cur = dist; ci = slot; }
 }
 
-__device__ __forceinline__ void epa_push_face(EpaGenericArena &E, int &nf, int a, int b, int c, vec3 pa, float &cur, int &ci)
+template <bool AS, bool BS>
+__device__ __forceinline__ void epa_push_face(EpaGenericArena &E, const NpShapes &S, int &nf, int a, int b, int c, vec3 pa, float &cur, int &ci)
 {
-    // PushTriangle, code/nans.cpp:293-322 (flip folded into the sign of d); pa == E.P[a]
-    const vec3 n = normalize(cross(E.getP(b) - pa, E.getP(c) - pa));
+    // PushTriangle, code/nans.cpp:293-322 (flip folded into the sign of d); pa == P[a]
+    const vec3 n = normalize(cross(epa_P<AS, BS>(E, S, b) - pa, epa_P<AS, BS>(E, S, c) - pa));
     const float d = dot(pa, n);
+    const uint32_t f = (uint32_t)a | ((uint32_t)b << 8) | ((uint32_t)c << 16);
+#if NANS_EPA_FACE16
+    E.fnd[nf] = make_float4(n.x, n.y, n.z, __uint_as_float(f));
+#else
     E.fnd[nf] = make_float4(n.x, n.y, n.z, d);
-    E.fidx[nf] = (uint32_t)a | ((uint32_t)b << 8) | ((uint32_t)c << 16);
+    E.fidx[nf] = f;
+#endif
     epa_track_min(d, nf, cur, ci);
     ++nf;
+}
+// a face's packed vertex indices and plane offset d = dot(P[a], n).  NANS_EPA_FACE16: the record holds {n, indices}
+// and d is re-formed (the same dot product of the same operands PushTriangle's flip test forms, :316-320)
+__device__ __forceinline__ uint32_t face_idx(const EpaGenericArena &E, int i, const float4 &nd)
+{
+#if NANS_EPA_FACE16
+    return __float_as_uint(nd.w);
+#else
+    return E.fidx[i];
+#endif
+}
+__device__ __forceinline__ vec3 face_normal_flipped_d(const float4 &nd, float d)
+{
+    const vec3 n = V3(nd);
+    return d < 0.0f ? n * -1.0f : n;
 }
 __device__ __forceinline__ vec3 face_normal_flipped(const float4 &nd)
 {
@@ -317,27 +339,14 @@ __device__ __forceinline__ vec3 face_normal_flipped(const float4 &nd)
 
 // PushEdge, code/nans.cpp:233-266: an opposite-winding edge already in the list is erased (order of
 // the rest kept), otherwise the edge is appended
+template <bool AS, bool BS>
 __device__ __forceinline__ void epa_push_edge(EpaGenericArena &E, int &ne, int a, int b, int &ovf)
 {
-    const uint32_t ca = E.cid[a], cb = E.cid[b];
+    const uint32_t ca = epa_cid<AS, BS>(E, a), cb = epa_cid<AS, BS>(E, b);
     // a NaN vertex equals nothing, itself included: its id on the probing side never matches a stored one
     const uint32_t want = (cb == kCidNaN ? 255u : cb) | ((ca == kCidNaN ? 255u : ca) << 8);
     int i = 0;
-#if NANS_EPA_EDGE4
-    // four entries per round trip (the one-at-a-time walk is a chain of dependent local loads); entries past ne are
-    // read (inside the array) and ignored
-    int at = -1;
-    for (int b = 0; b < ne && at < 0; b += 4) {
-        const uint32_t e0 = E.edge[b], e1 = E.edge[b + 1], e2 = E.edge[b + 2], e3 = E.edge[b + 3];
-        if ((e0 >> 16) == want) at = b;
-        else if (b + 1 < ne && (e1 >> 16) == want) at = b + 1;
-        else if (b + 2 < ne && (e2 >> 16) == want) at = b + 2;
-        else if (b + 3 < ne && (e3 >> 16) == want) at = b + 3;
-    }
-    i = at < 0 ? ne : at;
-#else
     while (i < ne && (E.edge[i] >> 16) != want) ++i;
-#endif
     if (i < ne) {
         for (int k = i; k < ne - 1; ++k) E.edge[k] = E.edge[k + 1];
         --ne;
@@ -355,28 +364,32 @@ __device__ __forceinline__ int epa_resolve(const NpShapes &S, const GjkVertex<AS
 {
     // the simplex becomes the first four vertices and faces (:791-802)
 #pragma unroll
-    for (int k = 0; k < 4; ++k) epa_store_vertex<AS, BS>(E, k, s[k]);
+    for (int k = 0; k < 4; ++k) epa_store_vertex<AS, BS>(E, S, k, s[k]);
     int nv = 4, nf = 0, ne = 0, ci = 0, it = 0;
     float cur = 0.f;
-    epa_push_face(E, nf, 0, 1, 2, s[0].P, cur, ci);  // ABC
-    epa_push_face(E, nf, 0, 2, 3, s[0].P, cur, ci);  // ACD
-    epa_push_face(E, nf, 0, 3, 1, s[0].P, cur, ci);  // ADB
-    epa_push_face(E, nf, 1, 3, 2, s[1].P, cur, ci);  // BDC
+    epa_push_face<AS, BS>(E, S, nf, 0, 1, 2, s[0].P, cur, ci);  // ABC
+    epa_push_face<AS, BS>(E, S, nf, 0, 2, 3, s[0].P, cur, ci);  // ACD
+    epa_push_face<AS, BS>(E, S, nf, 0, 3, 1, s[0].P, cur, ci);  // ADB
+    epa_push_face<AS, BS>(E, S, nf, 1, 3, 2, s[1].P, cur, ci);  // BDC
     while (it++ <= 64) {            // MAX_EPA_ITERATIONS, code/nans.h:56
         // a BUDGETED run (max_iters < 65: the multi-pass batch path) gives up before iteration max_iters + 1; the
         // caller runs the pair again, from its simplex, with a larger budget
         if (it > max_iters) return kEpaOutOfBudget;
         max_faces = max(max_faces, nf);
         const float4 cnd = E.fnd[ci];
+#if NANS_EPA_FACE16
+        const vec3 N = face_normal_flipped_d(cnd, dot(epa_P<AS, BS>(E, S, __float_as_uint(cnd.w) & 255), V3(cnd)));
+#else
         const vec3 N = face_normal_flipped(cnd);
+#endif
         const GjkVertex<AS, BS> ns = calc_support<AS, BS>(S, N);
         if (fsub(dot(N, ns.P), cur) < 0.001f) {   // MAX_EPA_ERROR, code/nans.h:55
-            const uint32_t f = E.fidx[ci];
+            const uint32_t f = face_idx(E, ci, cnd);
             const int a = f & 255, b = (f >> 8) & 255, c = (f >> 16) & 255;
             // Barycentric, code/nans.cpp:772-785
             const vec3 Pp = N * cur;
-            const vec3 A0 = E.getP(a);
-            const vec3 v0 = E.getP(b) - A0, v1 = E.getP(c) - A0, v2 = Pp - A0;
+            const vec3 A0 = epa_P<AS, BS>(E, S, a);
+            const vec3 v0 = epa_P<AS, BS>(E, S, b) - A0, v1 = epa_P<AS, BS>(E, S, c) - A0, v2 = Pp - A0;
             const float d00 = dot(v0, v0), d01 = dot(v0, v1), d11 = dot(v1, v1);
             const float d20 = dot(v2, v0), d21 = dot(v2, v1);
             const float denom = fsub(fmul(d00, d11), fmul(d01, d01));
@@ -385,35 +398,35 @@ __device__ __forceinline__ int epa_resolve(const NpShapes &S, const GjkVertex<AS
             const float bu = fsub(fsub(1.0f, bv), bw);
             if (fabsf(bu) > 1.0f || fabsf(bv) > 1.0f || fabsf(bw) > 1.0f) return 0;
             if (!isfinite(bu) || !isfinite(bv) || !isfinite(bw)) return 0;   // IsValid, :4-17
-            outPA = ((bu * epa_sup_a<AS>(E, S, a)) + (bv * epa_sup_a<AS>(E, S, b))) + (bw * epa_sup_a<AS>(E, S, c));
+            outPA = ((bu * epa_sup_a<AS, BS>(E, S, a)) + (bv * epa_sup_a<AS, BS>(E, S, b))) + (bw * epa_sup_a<AS, BS>(E, S, c));
             outN = -1.0f * N;
-            outPB = ((bu * epa_sup_b<BS>(E, S, a)) + (bv * epa_sup_b<BS>(E, S, b))) + (bw * epa_sup_b<BS>(E, S, c));
+            outPB = ((bu * epa_sup_b<AS, BS>(E, S, a)) + (bv * epa_sup_b<AS, BS>(E, S, b))) + (bw * epa_sup_b<AS, BS>(E, S, c));
             return 1;
         }
         if (nv >= kEpaMaxVerts) { ovf |= OVF_EPA_FACES; return 0; }
-        epa_store_vertex<AS, BS>(E, nv, ns);
+        epa_store_vertex<AS, BS>(E, S, nv, ns);
         // dissolve every face the new point can see (:869-891); survivors keep their order.  The
         // dissolved faces are only LISTED here; their edges are pushed in a second loop, so the warp
         // stays converged over the face scan.
         const int nf_old = nf;
         int keep = 0, nvis = 0;
-#if NANS_EPA_FACE_PIPE2
-        // two faces in flight: face i's record AND its vertex A (a dependent, per-lane-indexed load) are fetched one
-        // iteration ahead, face i + 2's record two ahead
+#if NANS_EPA_FACE16
         float4 nd_next = E.fnd[0];
-        uint32_t f_next = E.fidx[0];
-        vec3 pa_next = E.getP(f_next & 255);
-        float4 nd_nn = nd_next;
-        uint32_t f_nn = f_next;
-        if (nf > 1) { nd_nn = E.fnd[1]; f_nn = E.fidx[1]; }
         for (int i = 0; i < nf; ++i) {
             const float4 nd = nd_next;
-            const uint32_t f = f_next;
-            const vec3 pa_cur = pa_next;
-            nd_next = nd_nn; f_next = f_nn;
-            if (i + 1 < nf) pa_next = E.getP(f_next & 255);
-            if (i + 2 < nf) { nd_nn = E.fnd[i + 2]; f_nn = E.fidx[i + 2]; }
-            const vec3 tmp = ns.P - pa_cur;
+            const uint32_t f = __float_as_uint(nd.w);
+            if (i + 1 < nf) nd_next = E.fnd[i + 1];
+            const vec3 pa = epa_P<AS, BS>(E, S, f & 255);
+            const float d = dot(pa, V3(nd));
+            const vec3 tmp = ns.P - pa;
+            if (dot(face_normal_flipped_d(nd, d), tmp) > 0.0f) {
+                E.vis[nvis++] = f;
+            } else {
+                if (keep != i) E.fnd[keep] = nd;
+                epa_track_min(d, keep, cur, ci);
+                ++keep;
+            }
+        }
 #else
         float4 nd_next = E.fnd[0];
         uint32_t f_next = E.fidx[0];
@@ -421,8 +434,7 @@ __device__ __forceinline__ int epa_resolve(const NpShapes &S, const GjkVertex<AS
             const float4 nd = nd_next;
             const uint32_t f = f_next;
             if (i + 1 < nf) { nd_next = E.fnd[i + 1]; f_next = E.fidx[i + 1]; }
-            const vec3 tmp = ns.P - E.getP(f & 255);
-#endif
+            const vec3 tmp = ns.P - epa_P<AS, BS>(E, S, f & 255);
             if (dot(face_normal_flipped(nd), tmp) > 0.0f) {
                 E.vis[nvis++] = f;
             } else {
@@ -431,12 +443,13 @@ __device__ __forceinline__ int epa_resolve(const NpShapes &S, const GjkVertex<AS
                 ++keep;
             }
         }
+#endif
         nf = keep;
         for (int j = 0; j < nvis; ++j) {
             uint32_t f = E.vis[j];
 #pragma unroll 1
             for (int k = 0; k < 3; ++k) {           // AB, BC, CA
-                epa_push_edge(E, ne, f & 255, (f >> 8) & 255, ovf);
+                epa_push_edge<AS, BS>(E, ne, f & 255, (f >> 8) & 255, ovf);
                 f = (f >> 8) | ((f & 255) << 16);
             }
         }
@@ -444,7 +457,7 @@ __device__ __forceinline__ int epa_resolve(const NpShapes &S, const GjkVertex<AS
         if (nf + ne > kEpaMaxFaces) { ovf |= OVF_EPA_FACES; return 0; }
         for (int i = 0; i < ne; ++i) {
             const uint32_t ed = E.edge[i];
-            epa_push_face(E, nf, nv, ed & 255, (ed >> 8) & 255, ns.P, cur, ci);
+            epa_push_face<AS, BS>(E, S, nf, nv, ed & 255, (ed >> 8) & 255, ns.P, cur, ci);
         }
         ne = 0;
         ++nv;
@@ -458,8 +471,12 @@ __device__ __forceinline__ int epa_resolve(const NpShapes &S, const GjkVertex<AS
         if (nf == 0 && nf_old > 0) {
             const float4 last = E.fnd[nf_old - 1];
             E.fnd[0] = last;
+#if NANS_EPA_FACE16
+            cur = fabsf(dot(epa_P<AS, BS>(E, S, __float_as_uint(last.w) & 255), V3(last)));
+#else
             E.fidx[0] = E.fidx[nf_old - 1];
             cur = fabsf(last.w);
+#endif
             ci = 0;
         }
     }
