@@ -30,7 +30,8 @@ struct Counters {
     int32_t max_epa_faces;
     int32_t frontier_n[3];   // solver: [0] sweep tickets issued, [1] number of runs
     int32_t pad[11];         // [0] narrowphase work counter, [1] solver abort flag (watchdog), [2] max AABB extent bits,
-                             // [3] largest Morton key of the step, [4..6] unused,
+                             // [3] largest Morton key of the step, [4] narrowphase hit-list length, [5] its chunk tickets,
+                             // [6] deferred-GJK list length (narrowphase.cu),
                              // [7..9] smallest AABB centre per axis (order-encoded, complemented: 0 = none yet),
                              // [10] slab error bits (SLAB_ERR_*)
 };
