@@ -223,7 +223,7 @@ struct EpaGenericArena {
     vec3 SA[kEpaMaxVerts], SB[kEpaMaxVerts];    // sphere sides only
     uint8_t ia[kEpaMaxVerts], ib[kEpaMaxVerts]; // box sides only
     uint8_t cid[kEpaMaxVerts];                  // lowest vertex index with an equal P (kCidNaN: equal to nothing)
-    uint16_t vw[kEpaMaxVerts];                  // NANS_EPA_PSHAPES, box pairs: ia | ib << 4 | cid << 8 (replaces P, ia, ib, cid)
+    uint32_t vw[kEpaMaxVerts];                  // NANS_EPA_PSHAPES, box pairs: ia | ib << 4 | cid << 8 | hash16(P) << 16 (replaces P, ia, ib, cid)
     float4 fnd[kEpaMaxFaces];
     uint32_t fidx[kEpaMaxFaces];
     uint32_t vis[kEpaMaxFaces];                 // packed indices of the faces dissolved this iteration
@@ -255,7 +255,15 @@ __device__ __forceinline__ vec3 epa_P(const EpaGenericArena &E, const NpShapes &
 template <bool AS, bool BS>
 __device__ __forceinline__ uint32_t epa_cid(const EpaGenericArena &E, int i)
 {
-    if constexpr (kPFromShapes<AS, BS>) return (uint32_t)E.vw[i] >> 8; else return E.cid[i];
+    if constexpr (kPFromShapes<AS, BS>) return (E.vw[i] >> 8) & 255u; else return E.cid[i];
+}
+
+__device__ __forceinline__ uint32_t epa_hash16(vec3 p)
+{
+    uint32_t h = __float_as_uint(fadd(p.x, 0.0f)) ^ (__float_as_uint(fadd(p.y, 0.0f)) * 0x9E3779B1u) ^
+                 (__float_as_uint(fadd(p.z, 0.0f)) * 0x85EBCA6Bu);
+    h ^= h >> 16;
+    return h & 0xffffu;
 }
 
 // The reference's edge cancels an opposite-winding edge BY VALUE of P (code/nans.h:251-254).  Float
@@ -270,14 +278,26 @@ __device__ __forceinline__ void epa_store_vertex(EpaGenericArena &E, const NpSha
         if constexpr (BS) E.SB[i] = v.b.v; else E.ib[i] = (uint8_t)v.b.idx;
     }
     int c = i;
-    if (!equal(v.P, v.P)) {
-        c = kCidNaN;
+    if constexpr (kPFromShapes<AS, BS>) {
+        // equal vectors have equal hashes (x + 0 maps -0 to +0, the one pair of different bit patterns that compare
+        // equal), so a stored 16-bit hash rules an earlier vertex out without re-forming its P
+        const uint32_t h = epa_hash16(v.P);
+        if (!equal(v.P, v.P)) {
+            c = kCidNaN;
+        } else {
+            for (int j = 0; j < i; ++j)
+                if ((E.vw[j] >> 16) == h && equal(epa_P<AS, BS>(E, S, j), v.P)) { c = j; break; }
+        }
+        E.vw[i] = (uint32_t)v.a.idx | ((uint32_t)v.b.idx << 4) | ((uint32_t)c << 8) | (h << 16);
     } else {
-        for (int j = 0; j < i; ++j)
-            if (equal(epa_P<AS, BS>(E, S, j), v.P)) { c = j; break; }
+        if (!equal(v.P, v.P)) {
+            c = kCidNaN;
+        } else {
+            for (int j = 0; j < i; ++j)
+                if (equal(E.getP(j), v.P)) { c = j; break; }
+        }
+        E.cid[i] = (uint8_t)c;
     }
-    if constexpr (kPFromShapes<AS, BS>) E.vw[i] = (uint16_t)((uint32_t)v.a.idx | ((uint32_t)v.b.idx << 4) | ((uint32_t)c << 8));
-    else E.cid[i] = (uint8_t)c;
 }
 template <bool AS, bool BS> __device__ __forceinline__ vec3 epa_sup_a(const EpaGenericArena &E, const NpShapes &S, int i)
 {
@@ -339,10 +359,8 @@ __device__ __forceinline__ vec3 face_normal_flipped(const float4 &nd)
 
 // PushEdge, code/nans.cpp:233-266: an opposite-winding edge already in the list is erased (order of
 // the rest kept), otherwise the edge is appended
-template <bool AS, bool BS>
-__device__ __forceinline__ void epa_push_edge(EpaGenericArena &E, int &ne, int a, int b, int &ovf)
+__device__ __forceinline__ void epa_push_edge(EpaGenericArena &E, int &ne, int a, int b, uint32_t ca, uint32_t cb, int &ovf)
 {
-    const uint32_t ca = epa_cid<AS, BS>(E, a), cb = epa_cid<AS, BS>(E, b);
     // a NaN vertex equals nothing, itself included: its id on the probing side never matches a stored one
     const uint32_t want = (cb == kCidNaN ? 255u : cb) | ((ca == kCidNaN ? 255u : ca) << 8);
     int i = 0;
@@ -447,10 +465,14 @@ __device__ __forceinline__ int epa_resolve(const NpShapes &S, const GjkVertex<AS
         nf = keep;
         for (int j = 0; j < nvis; ++j) {
             uint32_t f = E.vis[j];
+            // the three vertices' classes, fetched once per face (every vertex is on two of its edges)
+            uint32_t cl = epa_cid<AS, BS>(E, f & 255) | (epa_cid<AS, BS>(E, (f >> 8) & 255) << 8) |
+                          (epa_cid<AS, BS>(E, (f >> 16) & 255) << 16);
 #pragma unroll 1
             for (int k = 0; k < 3; ++k) {           // AB, BC, CA
-                epa_push_edge<AS, BS>(E, ne, f & 255, (f >> 8) & 255, ovf);
+                epa_push_edge(E, ne, f & 255, (f >> 8) & 255, cl & 255, (cl >> 8) & 255, ovf);
                 f = (f >> 8) | ((f & 255) << 16);
+                cl = (cl >> 8) | ((cl & 255) << 16);
             }
         }
         // one new face per horizon edge, in edge-list order (:894-901)
