@@ -27,8 +27,10 @@ __device__ __forceinline__ vec3 rk4(float dt, vec3 y0, vec3 sum, float m, float 
 {
     auto F = [&](vec3 y) { return kLinear ? movement_fn(y, sum, m, inv_m) : rotation_fn(y, sum, inv_m); };
     const vec3 k1 = dt * F(y0);
-    const vec3 k2 = dt * F(y0 + (k1 / 2.0f));
-    const vec3 k3 = dt * F(y0 + (k2 / 2.0f));
+    // k / 2.0f as k * 0.5f: halving is exact (or rounds the same real number the same way in the subnormal range), so the
+    // product has the quotient's bits without the six IEEE divisions per body
+    const vec3 k2 = dt * F(y0 + (k1 * 0.5f));
+    const vec3 k3 = dt * F(y0 + (k2 * 0.5f));
     const vec3 k4 = dt * F(y0 + k3);
     return y0 + 0.16666667f * (((k1 + 2.0f * k2) + 2.0f * k3) + k4);
 }

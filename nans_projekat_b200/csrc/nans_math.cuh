@@ -18,6 +18,9 @@ __device__ __forceinline__ float fsub(float a, float b) { return __fsub_rn(a, b)
 __device__ __forceinline__ float fmul(float a, float b) { return __fmul_rn(a, b); }
 __device__ __forceinline__ float fdiv(float a, float b) { return __fdiv_rn(a, b); }
 __device__ __forceinline__ float fsqrt(float a) { return __fsqrt_rn(a); }
+// 1.0f / a: the correctly rounded reciprocal IS the correctly rounded quotient (same real number, same rounding), at
+// about half the instructions of the general division
+__device__ __forceinline__ float frcp(float a) { return __frcp_rn(a); }
 
 __device__ __forceinline__ vec3 V3(float x, float y, float z) { vec3 r; r.x = x; r.y = y; r.z = z; return r; }
 __device__ __forceinline__ vec3 V3(float4 v) { return V3(v.x, v.y, v.z); }
@@ -41,7 +44,7 @@ __device__ __forceinline__ vec3 cross(vec3 x, vec3 y)
 }
 __device__ __forceinline__ float length(vec3 a) { return fsqrt(dot(a, a)); }
 // glm::normalize: v * inversesqrt(dot(v,v)), inversesqrt(x) = 1.0f / sqrt(x)  (normalize(0) = NaN)
-__device__ __forceinline__ vec3 normalize(vec3 a) { return a * fdiv(1.0f, fsqrt(dot(a, a))); }
+__device__ __forceinline__ vec3 normalize(vec3 a) { return a * frcp(fsqrt(dot(a, a))); }
 __device__ __forceinline__ bool equal(vec3 a, vec3 b) { return a.x == b.x && a.y == b.y && a.z == b.z; }
 
 }  // namespace nans

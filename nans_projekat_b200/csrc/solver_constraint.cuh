@@ -50,14 +50,14 @@ __device__ __forceinline__ void constraint_prepare(const DeviceWorld &w, int c, 
     const vec3 RN1 = cross(R1, N), RN2 = cross(R2, N);
     float JMJn = fadd(invM1, invM2);
     JMJn = fadd(JMJn, fsub(fmul(invI1, dot(RN1, RN1)), fmul(invI2, dot(-RN2, -RN2))));
-    JMJn = fdiv(1.0f, JMJn);
+    JMJn = frcp(JMJn);
     const vec3 R1T1 = cross(R1, T1), R2T1 = cross(R2, T1), R1T2 = cross(R1, T2), R2T2 = cross(R2, T2);
     float JMJt1 = fadd(invM1, invM2);
     JMJt1 = fadd(JMJt1, fsub(fmul(invI1, dot(R1T1, R1T1)), fmul(invI2, dot(-R2T1, -R2T1))));
-    JMJt1 = fdiv(1.0f, JMJt1);
+    JMJt1 = frcp(JMJt1);
     float JMJt2 = fadd(invM1, invM2);
     JMJt2 = fadd(JMJt2, fsub(fmul(invI1, dot(R1T2, R1T2)), fmul(invI2, dot(-R2T2, -R2T2))));
-    JMJt2 = fdiv(1.0f, JMJt2);
+    JMJt2 = frcp(JMJt2);
     const float Bd = fmul(fdiv(-0.3f, dt), depth);                  // (-Beta / dt) * Depth (:1156)
     q[0] = make_float4(N.x, N.y, N.z, JMJn);
     q[1] = make_float4(T1.x, T1.y, T1.z, JMJt1);

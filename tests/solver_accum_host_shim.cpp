@@ -12,6 +12,7 @@ static inline float __fsub_rn(float a, float b) { return a - b; }
 static inline float __fmul_rn(float a, float b) { return a * b; }
 static inline float __fdiv_rn(float a, float b) { return a / b; }
 static inline float __fsqrt_rn(float a) { return sqrtf(a); }
+static inline float __frcp_rn(float a) { return 1.0f / a; }
 static inline double __dmul_rn(double a, double b) { return a * b; }
 static inline float __double2float_rn(double a) { return (float)a; }
 static inline float cuda_fmaxf(float a, float b)

@@ -13,6 +13,7 @@ static inline float __fsub_rn(float a, float b) { return a - b; }
 static inline float __fmul_rn(float a, float b) { return a * b; }
 static inline float __fdiv_rn(float a, float b) { return a / b; }
 static inline float __fsqrt_rn(float a) { return sqrtf(a); }
+static inline float __frcp_rn(float a) { return 1.0f / a; }
 static inline double __dmul_rn(double a, double b) { return a * b; }
 static inline float __double2float_rn(double a) { return (float)a; }
 static inline int __float_as_int(float f) { int i; memcpy(&i, &f, 4); return i; }
