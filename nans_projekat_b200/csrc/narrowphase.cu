@@ -1,16 +1,19 @@
 // narrowphase.cu — kernels around narrowphase.cuh.
 //
-//   narrowphase_world_kernel   GJK+EPA over the world's candidate pairs (the step).  One pair per thread; warps
-//                              fetch 32-pair chunks from a global counter (a GJK miss is one support call, an EPA
-//                              hit is dozens), grid = SM count x resident CTAs.  Nearly every candidate of a pile
-//                              intersects (94 %), so GJK and EPA stay in one kernel.
+//   narrowphase_world_gjk_kernel, narrowphase_world_epa_kernel
+//                              the world's candidate pairs of a cube-only world (the step): GJK alone (capped at 6
+//                              evolutions) with the intersecting pairs appended to a list, then EPA over whole
+//                              chunks of that list, the few GJK stragglers finished first.  One pair per thread;
+//                              warps fetch 32-entry chunks from a global counter, grid = SM count x resident CTAs.
+//   narrowphase_world_kernel   the same in ONE kernel (GJK + EPA per pair): worlds with spheres, where nearly every
+//                              candidate intersects and the simplex does not reduce to eight vertex indices.
 //   gjk_split_kernel, gjk_continue_kernel, epa_refill_kernel
 //                              the same over stand-alone shape pairs (nans_check_collision_batch/_device, config
 //                              C3), where half the pairs miss and GJK / EPA lengths are long-tailed: GJK capped,
 //                              stragglers and intersecting pairs compacted into lists, EPA over the lists.
 //
-// FP32-pipe / divergence bound, not HBM bound: 216 B in + 48 B out per pair against ~1-5 kflop of unfused fp32
-// (SURVEY.md §8d).
+// Not HBM bound: 216 B in + 48 B out per pair against ~1-5 kflop of unfused fp32.  GJK is bound by
+// issue slots, EPA by the L1 capacity left for the per-thread polytope arenas (narrowphase.cuh).
 #include <stdlib.h>
 
 #include "narrowphase.cuh"

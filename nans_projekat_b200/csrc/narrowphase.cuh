@@ -7,13 +7,14 @@
 //     support is remembered as a 1-byte vertex index instead of a copied vec3;
 //   * the GJK simplex (std::vector<vertex>, <= 4 entries while GJK runs) lives in registers;
 //     erase()/swap are predicated register moves;
-//   * the EPA polytope is index-based and lives in a per-thread arena: vertices P plus support
-//     indices (or the sphere support point), faces as three byte indices plus a CACHED unflipped
-//     unit normal n and signed plane offset d = dot(n, A.P).  The reference recomputes
-//     normalize(cross(AB,AC)) for every face twice per iteration (closest-face scan :813-821 and
-//     visibility test :873-881); both are pure functions of the face's vertices, so they are
-//     computed once at face creation: |d| is the scan distance, the flipped normal is
-//     (d < 0 ? -n : n) = PushTriangle's stored N (:316-320);
+//   * the EPA polytope is index-based and lives in a per-thread arena kept as small as it can be (the
+//     arenas of the resident threads compete for the L1): a box-pair vertex is its two support
+//     indices (P = A[ia] - B[ib] is re-formed from shared memory), a face is three byte indices plus
+//     a CACHED unflipped unit normal n; the signed plane offset d = dot(n, A.P) is re-formed next to
+//     the visibility test.  The reference recomputes normalize(cross(AB,AC)) for every face twice
+//     per iteration (closest-face scan :813-821 and visibility test :873-881); it is a pure function
+//     of the face's vertices, so it is computed once at face creation: |d| is the scan distance,
+//     the flipped normal is (d < 0 ? -n : n) = PushTriangle's stored N (:316-320);
 //   * std::vector<edge>/<triangle> erase/push_back order is preserved exactly (the closest-face
 //     tie-break is "first minimum", so face order is observable);
 //   * the horizon's by-value edge cancellation compares precomputed vertex equivalence classes, the
