@@ -202,63 +202,49 @@ __device__ __forceinline__ int evolve_simplex(const NpShapes &S, GjkVertex<AS, B
 // Per-thread arena in local memory; only the touched part costs traffic, and that part is what bounds the kernel:
 // the arenas of the resident threads (640 per SM) do not fit the L1 next to the staged shapes, fewer resident
 // threads run slower, so every byte the arena does not hold is a byte that cannot miss.  Hence:
-//   NANS_EPA_FACE16   a face record is 16 bytes {unflipped unit normal n, packed indices a | b<<8 | c<<16}; the plane
-//                     offset d = dot(P[a], n) is re-formed where it is used (P[a] is needed there anyway).  Off: 20
-//                     bytes {n, d} + indices.  (Carrying P[a] in the record as well was measured in round 1: slower.)
-//   NANS_EPA_PSHAPES  box pairs: a vertex is ONE 16-bit word (ia, ib, class); P is re-formed from the shapes in
-//                     shared memory (epa_P).  Off: 15 bytes per vertex {P, ia, ib, class}.
-// Measured (1 M-cube pile 100^3 / flat 250x250x16 / config C3): narrowphase stage 0.367 -> 0.355 -> 0.347 ms,
-// 0.723 -> 0.681 -> 0.661 ms, 21.85 -> 21.05 -> 19.45 ms.  Also measured, no gain, removed: the first 8-12 vertices in
-// shared memory (the larger carve-out halves the L1), a 4-wide edge search, a class scan without early exit, the
-// face scan's vertex fetched one face ahead (profiles/README.md).
-#ifndef NANS_EPA_PSHAPES
-#define NANS_EPA_PSHAPES 1
-#endif
-#ifndef NANS_EPA_FACE16
-#define NANS_EPA_FACE16 1
-#endif
+//   * a vertex is ONE 32-bit word: its two box-support indices, its equivalence class and a 16-bit hash of P (a
+//     sphere side adds its support point, 12 bytes).  P itself is never stored: P = SupA - SupB (CalculateSupport,
+//     :464-519) is re-formed from the same operands wherever it is used -- for a box pair six conflict-free
+//     shared-memory loads and three subtractions (round 1 stored 15 bytes per vertex);
+//   * a face record is 16 bytes {unflipped unit normal n, packed indices a | b<<8 | c<<16}; the plane offset
+//     d = dot(P[a], n) is re-formed next to the visibility test, which needs P[a] anyway (round 1: 20 bytes;
+//     carrying P[a] in the record as well was measured then: slower).
+// Measured, step by step (1 M-cube pile 100^3 / flat 250x250x16 / config C3): narrowphase stage 0.367 -> 0.355 ->
+// 0.347 ms, 0.723 -> 0.681 -> 0.661 ms, 21.85 -> 21.05 -> 19.45 ms; L1 hit rate of the EPA kernel 67 -> 80 %.  Also
+// measured, no gain, removed: the first 8-12 vertices in shared memory (the larger carve-out halves the L1), a 4-wide
+// edge search, a class scan without early exit, the face scan's vertex fetched one face ahead (profiles/README.md).
 struct EpaGenericArena {
-    vec3 P[kEpaMaxVerts];                       // stored vertices (pairs with a sphere; box pairs re-form them, epa_P)
-    __device__ __forceinline__ vec3 getP(int i) const { return P[i]; }
-    __device__ __forceinline__ void setP(int i, vec3 v) { P[i] = v; }
-    vec3 SA[kEpaMaxVerts], SB[kEpaMaxVerts];    // sphere sides only
-    uint8_t ia[kEpaMaxVerts], ib[kEpaMaxVerts]; // box sides only
-    uint8_t cid[kEpaMaxVerts];                  // lowest vertex index with an equal P (kCidNaN: equal to nothing)
-    uint32_t vw[kEpaMaxVerts];                  // NANS_EPA_PSHAPES, box pairs: ia | ib << 4 | cid << 8 | hash16(P) << 16 (replaces P, ia, ib, cid)
-    float4 fnd[kEpaMaxFaces];
-    uint32_t fidx[kEpaMaxFaces];
+    uint32_t vw[kEpaMaxVerts];                  // ia | ib << 4 | class << 8 | hash16(P) << 16
+    vec3 SA[kEpaMaxVerts], SB[kEpaMaxVerts];    // sphere sides only: the support points
+    float4 fnd[kEpaMaxFaces];                   // {n.xyz, packed indices}
     uint32_t vis[kEpaMaxFaces];                 // packed indices of the faces dissolved this iteration
-    uint32_t edge[kEpaMaxEdges];                // a | b<<8 | cid[a]<<16 | cid[b]<<24
+    uint32_t edge[kEpaMaxEdges];                // a | b<<8 | class[a]<<16 | class[b]<<24
 };
 using EpaArena = EpaGenericArena;
 constexpr int kCidNaN = 254;
 
-// The reference's edge cancels an opposite-winding edge BY VALUE of P (code/nans.h:251-254).  Float
-// equality is an equivalence on non-NaN vectors (+0 == -0 included), so every vertex gets the lowest
-// index of its class once, when it is stored, and the edge compares become one integer compare.
-// Vertex i of the polytope.  For a BOX pair the point is a pure function of two vertex indices, P = A[ia] - B[ib]
-// (CalculateSupport, :464-519: the same subtraction of the same operands), and the shapes sit in shared memory: with
-// NANS_EPA_PSHAPES the arena keeps ONE 16-bit word per vertex (ia, ib, class) instead of 15 bytes, and every use
-// re-forms P from six shared-memory loads.  The polytope arenas of the resident threads do not fit the L1 (DESIGN.md
-// 4): what the arena does not hold it cannot miss on.
-template <bool AS, bool BS> constexpr bool kPFromShapes = NANS_EPA_PSHAPES && !AS && !BS;
-
+template <bool AS, bool BS> __device__ __forceinline__ vec3 epa_sup_a(const EpaGenericArena &E, const NpShapes &S, int i)
+{
+    if constexpr (AS) return E.SA[i]; else return S.vertex(0, E.vw[i] & 15u);
+}
+template <bool AS, bool BS> __device__ __forceinline__ vec3 epa_sup_b(const EpaGenericArena &E, const NpShapes &S, int i)
+{
+    if constexpr (BS) return E.SB[i]; else return S.vertex(1, (E.vw[i] >> 4) & 15u);
+}
+// vertex i of the polytope, re-formed
 template <bool AS, bool BS>
 __device__ __forceinline__ vec3 epa_P(const EpaGenericArena &E, const NpShapes &S, int i)
 {
-    if constexpr (kPFromShapes<AS, BS>) {
-        const uint32_t w = E.vw[i];
+    if constexpr (!AS && !BS) {
+        const uint32_t w = E.vw[i];             // one load for both indices
         return S.vertex(0, w & 15u) - S.vertex(1, (w >> 4) & 15u);
     } else {
-        return E.getP(i);
+        return epa_sup_a<AS, BS>(E, S, i) - epa_sup_b<AS, BS>(E, S, i);
     }
 }
-template <bool AS, bool BS>
-__device__ __forceinline__ uint32_t epa_cid(const EpaGenericArena &E, int i)
-{
-    if constexpr (kPFromShapes<AS, BS>) return (E.vw[i] >> 8) & 255u; else return E.cid[i];
-}
+__device__ __forceinline__ uint32_t epa_cid(const EpaGenericArena &E, int i) { return (E.vw[i] >> 8) & 255u; }
 
+// equal vectors have equal hashes: x + 0 maps -0 to +0, the one pair of different bit patterns that compare equal
 __device__ __forceinline__ uint32_t epa_hash16(vec3 p)
 {
     uint32_t h = __float_as_uint(fadd(p.x, 0.0f)) ^ (__float_as_uint(fadd(p.y, 0.0f)) * 0x9E3779B1u) ^
@@ -269,48 +255,23 @@ __device__ __forceinline__ uint32_t epa_hash16(vec3 p)
 
 // The reference's edge cancels an opposite-winding edge BY VALUE of P (code/nans.h:251-254).  Float
 // equality is an equivalence on non-NaN vectors (+0 == -0 included), so every vertex gets the lowest
-// index of its class once, when it is stored, and the edge compares become one integer compare.
+// index of its class once, when it is stored, and the edge compares become one integer compare.  The stored hash
+// rules an earlier vertex out without re-forming its P.
 template <bool AS, bool BS>
 __device__ __forceinline__ void epa_store_vertex(EpaGenericArena &E, const NpShapes &S, int i, const GjkVertex<AS, BS> &v)
 {
-    if constexpr (!kPFromShapes<AS, BS>) {
-        E.setP(i, v.P);
-        if constexpr (AS) E.SA[i] = v.a.v; else E.ia[i] = (uint8_t)v.a.idx;
-        if constexpr (BS) E.SB[i] = v.b.v; else E.ib[i] = (uint8_t)v.b.idx;
-    }
+    uint32_t w = 0;
+    if constexpr (AS) E.SA[i] = v.a.v; else w |= (uint32_t)v.a.idx;
+    if constexpr (BS) E.SB[i] = v.b.v; else w |= (uint32_t)v.b.idx << 4;
+    const uint32_t h = epa_hash16(v.P);
     int c = i;
-    if constexpr (kPFromShapes<AS, BS>) {
-        // equal vectors have equal hashes (x + 0 maps -0 to +0, the one pair of different bit patterns that compare
-        // equal), so a stored 16-bit hash rules an earlier vertex out without re-forming its P
-        const uint32_t h = epa_hash16(v.P);
-        if (!equal(v.P, v.P)) {
-            c = kCidNaN;
-        } else {
-            for (int j = 0; j < i; ++j)
-                if ((E.vw[j] >> 16) == h && equal(epa_P<AS, BS>(E, S, j), v.P)) { c = j; break; }
-        }
-        E.vw[i] = (uint32_t)v.a.idx | ((uint32_t)v.b.idx << 4) | ((uint32_t)c << 8) | (h << 16);
+    if (!equal(v.P, v.P)) {
+        c = kCidNaN;
     } else {
-        if (!equal(v.P, v.P)) {
-            c = kCidNaN;
-        } else {
-            for (int j = 0; j < i; ++j)
-                if (equal(E.getP(j), v.P)) { c = j; break; }
-        }
-        E.cid[i] = (uint8_t)c;
+        for (int j = 0; j < i; ++j)
+            if ((E.vw[j] >> 16) == h && equal(epa_P<AS, BS>(E, S, j), v.P)) { c = j; break; }
     }
-}
-template <bool AS, bool BS> __device__ __forceinline__ vec3 epa_sup_a(const EpaGenericArena &E, const NpShapes &S, int i)
-{
-    if constexpr (AS) return E.SA[i];
-    else if constexpr (kPFromShapes<AS, BS>) return S.vertex(0, E.vw[i] & 15u);
-    else return S.vertex(0, E.ia[i]);
-}
-template <bool AS, bool BS> __device__ __forceinline__ vec3 epa_sup_b(const EpaGenericArena &E, const NpShapes &S, int i)
-{
-    if constexpr (BS) return E.SB[i];
-    else if constexpr (kPFromShapes<AS, BS>) return S.vertex(1, (E.vw[i] >> 4) & 15u);
-    else return S.vertex(1, E.ib[i]);
+    E.vw[i] = w | ((uint32_t)c << 8) | (h << 16);
 }
 
 // closest face = FIRST strict minimum of |d| in face order (:807-822).  The reference rescans every
@@ -327,35 +288,15 @@ __device__ __forceinline__ void epa_push_face(EpaGenericArena &E, const NpShapes
     // PushTriangle, code/nans.cpp:293-322 (flip folded into the sign of d); pa == P[a]
     const vec3 n = normalize(cross(epa_P<AS, BS>(E, S, b) - pa, epa_P<AS, BS>(E, S, c) - pa));
     const float d = dot(pa, n);
-    const uint32_t f = (uint32_t)a | ((uint32_t)b << 8) | ((uint32_t)c << 16);
-#if NANS_EPA_FACE16
-    E.fnd[nf] = make_float4(n.x, n.y, n.z, __uint_as_float(f));
-#else
-    E.fnd[nf] = make_float4(n.x, n.y, n.z, d);
-    E.fidx[nf] = f;
-#endif
+    E.fnd[nf] = make_float4(n.x, n.y, n.z, __uint_as_float((uint32_t)a | ((uint32_t)b << 8) | ((uint32_t)c << 16)));
     epa_track_min(d, nf, cur, ci);
     ++nf;
 }
-// a face's packed vertex indices and plane offset d = dot(P[a], n).  NANS_EPA_FACE16: the record holds {n, indices}
-// and d is re-formed (the same dot product of the same operands PushTriangle's flip test forms, :316-320)
-__device__ __forceinline__ uint32_t face_idx(const EpaGenericArena &E, int i, const float4 &nd)
-{
-#if NANS_EPA_FACE16
-    return __float_as_uint(nd.w);
-#else
-    return E.fidx[i];
-#endif
-}
-__device__ __forceinline__ vec3 face_normal_flipped_d(const float4 &nd, float d)
+// PushTriangle's stored N (:316-320): the unit normal, flipped by the sign of d = dot(P[a], n)
+__device__ __forceinline__ vec3 face_normal_flipped(const float4 &nd, float d)
 {
     const vec3 n = V3(nd);
     return d < 0.0f ? n * -1.0f : n;
-}
-__device__ __forceinline__ vec3 face_normal_flipped(const float4 &nd)
-{
-    const vec3 n = V3(nd);
-    return nd.w < 0.0f ? n * -1.0f : n;
 }
 
 // PushEdge, code/nans.cpp:233-266: an opposite-winding edge already in the list is erased (order of
@@ -396,15 +337,11 @@ __device__ __forceinline__ int epa_resolve(const NpShapes &S, const GjkVertex<AS
         if (it > max_iters) return kEpaOutOfBudget;
         max_faces = max(max_faces, nf);
         const float4 cnd = E.fnd[ci];
-#if NANS_EPA_FACE16
-        const vec3 N = face_normal_flipped_d(cnd, dot(epa_P<AS, BS>(E, S, __float_as_uint(cnd.w) & 255), V3(cnd)));
-#else
-        const vec3 N = face_normal_flipped(cnd);
-#endif
+        const uint32_t cf = __float_as_uint(cnd.w);
+        const vec3 N = face_normal_flipped(cnd, dot(epa_P<AS, BS>(E, S, cf & 255), V3(cnd)));
         const GjkVertex<AS, BS> ns = calc_support<AS, BS>(S, N);
         if (fsub(dot(N, ns.P), cur) < 0.001f) {   // MAX_EPA_ERROR, code/nans.h:55
-            const uint32_t f = face_idx(E, ci, cnd);
-            const int a = f & 255, b = (f >> 8) & 255, c = (f >> 16) & 255;
+            const int a = cf & 255, b = (cf >> 8) & 255, c = (cf >> 16) & 255;
             // Barycentric, code/nans.cpp:772-785
             const vec3 Pp = N * cur;
             const vec3 A0 = epa_P<AS, BS>(E, S, a);
@@ -429,7 +366,6 @@ __device__ __forceinline__ int epa_resolve(const NpShapes &S, const GjkVertex<AS
         // stays converged over the face scan.
         const int nf_old = nf;
         int keep = 0, nvis = 0;
-#if NANS_EPA_FACE16
         float4 nd_next = E.fnd[0];
         for (int i = 0; i < nf; ++i) {
             const float4 nd = nd_next;
@@ -438,7 +374,7 @@ __device__ __forceinline__ int epa_resolve(const NpShapes &S, const GjkVertex<AS
             const vec3 pa = epa_P<AS, BS>(E, S, f & 255);
             const float d = dot(pa, V3(nd));
             const vec3 tmp = ns.P - pa;
-            if (dot(face_normal_flipped_d(nd, d), tmp) > 0.0f) {
+            if (dot(face_normal_flipped(nd, d), tmp) > 0.0f) {
                 E.vis[nvis++] = f;
             } else {
                 if (keep != i) E.fnd[keep] = nd;
@@ -446,29 +382,11 @@ __device__ __forceinline__ int epa_resolve(const NpShapes &S, const GjkVertex<AS
                 ++keep;
             }
         }
-#else
-        float4 nd_next = E.fnd[0];
-        uint32_t f_next = E.fidx[0];
-        for (int i = 0; i < nf; ++i) {
-            const float4 nd = nd_next;
-            const uint32_t f = f_next;
-            if (i + 1 < nf) { nd_next = E.fnd[i + 1]; f_next = E.fidx[i + 1]; }
-            const vec3 tmp = ns.P - epa_P<AS, BS>(E, S, f & 255);
-            if (dot(face_normal_flipped(nd), tmp) > 0.0f) {
-                E.vis[nvis++] = f;
-            } else {
-                if (keep != i) { E.fnd[keep] = nd; E.fidx[keep] = f; }
-                epa_track_min(nd.w, keep, cur, ci);
-                ++keep;
-            }
-        }
-#endif
         nf = keep;
         for (int j = 0; j < nvis; ++j) {
             uint32_t f = E.vis[j];
             // the three vertices' classes, fetched once per face (every vertex is on two of its edges)
-            uint32_t cl = epa_cid<AS, BS>(E, f & 255) | (epa_cid<AS, BS>(E, (f >> 8) & 255) << 8) |
-                          (epa_cid<AS, BS>(E, (f >> 16) & 255) << 16);
+            uint32_t cl = epa_cid(E, f & 255) | (epa_cid(E, (f >> 8) & 255) << 8) | (epa_cid(E, (f >> 16) & 255) << 16);
 #pragma unroll 1
             for (int k = 0; k < 3; ++k) {           // AB, BC, CA
                 epa_push_edge(E, ne, f & 255, (f >> 8) & 255, cl & 255, (cl >> 8) & 255, ovf);
@@ -494,12 +412,7 @@ __device__ __forceinline__ int epa_resolve(const NpShapes &S, const GjkVertex<AS
         if (nf == 0 && nf_old > 0) {
             const float4 last = E.fnd[nf_old - 1];
             E.fnd[0] = last;
-#if NANS_EPA_FACE16
             cur = fabsf(dot(epa_P<AS, BS>(E, S, __float_as_uint(last.w) & 255), V3(last)));
-#else
-            E.fidx[0] = E.fidx[nf_old - 1];
-            cur = fabsf(last.w);
-#endif
             ci = 0;
         }
     }

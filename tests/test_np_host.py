@@ -30,11 +30,7 @@ def _build(name, flags):
 
 
 @pytest.fixture(scope="module", params=[("default", []), ("gjk_capped", ["-DNANS_NP_GJK_CAPPED=8"]),
-                                        ("gjk_capped1", ["-DNANS_NP_GJK_CAPPED=1"]),
-                                        # the EPA arena forms the kernels may be built with (csrc/narrowphase.cuh)
-                                        ("epa_stored", ["-DNANS_EPA_PSHAPES=0", "-DNANS_EPA_FACE16=0"]),
-                                        ("epa_face16_stored_p", ["-DNANS_EPA_PSHAPES=0", "-DNANS_EPA_FACE16=1"]),
-                                        ("epa_pshapes_face20", ["-DNANS_EPA_PSHAPES=1", "-DNANS_EPA_FACE16=0"])],
+                                        ("gjk_capped1", ["-DNANS_NP_GJK_CAPPED=1"])],
                 ids=lambda p: p[0])
 def host_np(request):
     if not os.path.exists("/usr/local/cuda/include/cuda_runtime.h"):
