@@ -80,3 +80,6 @@ extern "C" int np_host_check_collision_batch(int n, const int32_t *type, const f
     if (max_faces) *max_faces = mf;
     return ovf;
 }
+
+// the vertex hash that gates EPA's class scan: equal vectors (+0 == -0 included) must have equal hashes
+extern "C" unsigned np_host_hash16(float x, float y, float z) { return epa_hash16(V3(x, y, z)); }

@@ -143,3 +143,25 @@ def test_emptied_polytope_golden(host_np, oracle):
         h = z["ref_hit"] == 1
         for k in ("N", "PA", "PB"):
             assert np.array_equal(r[k][h].view(np.uint32), z[f"ref_{k}"][h].view(np.uint32)), f"{who}: {k}"
+
+
+def test_vertex_hash_respects_float_equality(host_np):
+    """EPA's class scan skips an earlier vertex whose stored 16-bit hash differs from the new vertex's
+    (csrc/narrowphase.cuh, epa_store_vertex): sound only if vectors that COMPARE equal hash equal.  The one case of
+    different bits comparing equal is +0 / -0 (NaN compares equal to nothing and is handled before the scan)."""
+    lib = host_np
+    lib.np_host_hash16.restype = C.c_uint
+    lib.np_host_hash16.argtypes = [C.c_float] * 3
+    rng = np.random.default_rng(3)
+    vals = [0.0, -0.0, 1.0, -1.0, 1e-45, -1e-45, 3.5, np.float32(np.inf), np.float32(-np.inf)]
+    vecs = [(a, b, c) for a in vals for b in vals for c in vals]
+    vecs += [tuple(rng.normal(0, 3, 3).astype(np.float32)) for _ in range(2000)]
+    h = {}
+    for v in vecs:
+        key = tuple(np.float32(x) + np.float32(0.0) for x in v)       # the equality class: -0 -> +0
+        got = lib.np_host_hash16(*[C.c_float(float(x)) for x in v])
+        assert 0 <= got < 65536
+        assert h.setdefault(key, got) == got, f"{v}: equal vectors, different hashes"
+    # and it does discriminate: random vectors rarely collide
+    rnd = [lib.np_host_hash16(*[C.c_float(float(x)) for x in v]) for v in vecs[-2000:]]
+    assert len(set(rnd)) > 1900
