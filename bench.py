@@ -268,7 +268,37 @@ def run_reference(args):
                              "sample": f"{what}; {n} cubes + floor, {inner * args.steps} steps, {el:.1f} s"},
             "e2e": {"value": value, "unit": "body-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "host": {"nproc": os.cpu_count()}}
+    if not args.no_subrecords and args.workload == "pile":
+        try:
+            line["same_workload_grid_port"] = cpu_same_workload(args)
+        except Exception as ex:   # an extra record must never lose the reference line
+            line["same_workload_grid_port"] = {"unavailable": f"{type(ex).__name__}: {ex}"}
     print(json.dumps(line), flush=True)
+
+
+def cpu_same_workload(args, timed_steps=3):
+    """The arm's OWN workload (the whole pile, same seed, same settle steps) on the host cores: the oracle port's
+    arithmetic behind its uniform-grid prefilter.  The reference cannot run it (16-cube cap, all-pairs loop), so this is
+    NOT the reference arm's `value`: it is the same-config CPU figure to read beside it -- a CPU given this repo's
+    candidate search.  GJK+EPA on min(nproc, 32) threads, grid / solver / integrators on one (oracle/nans_oracle.c)."""
+    from oracle import oracle as O
+    scene, layers = build_pile(args.bodies, args.side, seed=7)
+    w = O.World(scene.n_cubes, scene.n_spheres, scene.n_statics)
+    for f in scene.ARRAYS:
+        getattr(w, f)[...] = getattr(scene, f)
+    w.rebuild_vertices()
+    cap = max(8 * scene.nb, 1 << 20)
+    for _ in range(args.settle):                            # the same preparation as our arm (prepare_world)
+        w.step(DT, prefilter="grid", cap=cap)
+    t0, contacts = time.perf_counter(), 0
+    for _ in range(timed_steps):
+        contacts += len(w.step(DT, prefilter="grid", cap=cap))
+    el = time.perf_counter() - t0
+    return {"value": scene.nb * timed_steps / el, "unit": "body-steps/s", "bodies": scene.nb,
+            "shape": f"{args.side}x{layers}x{args.side}", "cores": min(os.cpu_count() or 1, 32),
+            "steps": timed_steps, "settle_steps": args.settle, "seconds_per_step": el / timed_steps,
+            "contacts_per_step": contacts / timed_steps,
+            "what": "oracle port + uniform-grid prefilter on the whole pile (not the reference's O(N^2) all-pairs loop)"}
 
 
 def _c3_pairs_torch(n, seed, dev):
@@ -537,14 +567,16 @@ def parity_in_run(world, scene, prepared):
     world.step(DT)
     gc = world.contacts()
     d = world.download(fields=FULL)
+    t_or = time.perf_counter()
     oc = w.step(DT, prefilter="grid", cap=max(8 * scene.nb, 1 << 20))
+    t_or = time.perf_counter() - t_or
     same_c = gc.tobytes() == oc.tobytes()
     bad = [f for f in ("pos", "vel", "ang", "angvel", "verts") if getattr(d, f).tobytes() != getattr(w, f).tobytes()]
     world.restore()
     return {"checked": "one step from the prepared state, GPU vs CPU oracle (oracle/nans_oracle.c, pinned to the "
                        "reference's nans.so), contact list in reference order + pos/vel/ang/angvel/verts of every body",
             "contacts": int(len(oc)), "contact_list_bit_exact": bool(same_c), "state_bit_exact": not bad,
-            "fields_differing": bad, "seconds": time.perf_counter() - t0}
+            "fields_differing": bad, "seconds": time.perf_counter() - t0, "oracle_step_seconds": t_or}
 
 
 def sub_record(scene, name, local, settle, window, steps, warmup, shard_note=None, barrier=lambda: None, reduce_max=None):
@@ -801,6 +833,15 @@ def main():
         world.download_into(sv, ("st_verts",))
         state.st_verts[...] = sv.st_verts
         cpu = cpu_port_baseline(state, args.cpu_bodies)
+        if parity and parity.get("oracle_step_seconds"):
+            # the SAME workload on the host cores: the oracle port's arithmetic behind a uniform-grid prefilter.  NOT the
+            # reference's algorithm (its all-pairs loop cannot run 10^6 bodies) -- a CPU with this repo's candidate
+            # search; GJK+EPA on min(nproc, 32) threads, grid / solver / integrators on one (oracle/nans_oracle.c)
+            cpu["same_workload_grid_port"] = {
+                "value": nb / parity["oracle_step_seconds"], "unit": "body-steps/s", "bodies": nb,
+                "cores": min(os.cpu_count() or 1, 32), "seconds_per_step": parity["oracle_step_seconds"],
+                "what": "ONE step of the headline state by the oracle port with its uniform-grid prefilter (the step "
+                        "parity_in_run checks the GPU against); not the reference's O(N^2) all-pairs loop"}
     world.close()
     del world
     torch.cuda.empty_cache()
