@@ -41,7 +41,7 @@ def _view(scene, fields) -> _lib.SceneView:
         else:
             a = np.ascontiguousarray(a, np.float32)
             setattr(v, f, _fp(a))
-        keep.append(a)
+        keep.append((f, a))
     v._keepalive = keep
     return v
 
@@ -94,6 +94,9 @@ class World:
     def download_into(self, scene, fields):
         v = _view(scene, fields)
         _lib.check(_lib.lib().nans_world_download(self._h, C.byref(v)))
+        for f, a in v._keepalive:      # a field that was not a contiguous f32 array went through a copy: hand it back
+            if a is not getattr(scene, f):
+                getattr(scene, f)[...] = a
 
     # pipelined I/O (poses one frame late): copies overlap the step on their own streams
     def upload_async(self, scene, fields=("force", "torque")):
