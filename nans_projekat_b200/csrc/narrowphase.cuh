@@ -244,6 +244,33 @@ __device__ __forceinline__ vec3 epa_P(const EpaGenericArena &E, const NpShapes &
 }
 __device__ __forceinline__ uint32_t epa_cid(const EpaGenericArena &E, int i) { return (E.vw[i] >> 8) & 255u; }
 
+#ifndef NANS_EPA_FW
+#define NANS_EPA_FW 0
+#endif
+// A face word is a | b << 8 | c << 16 | (box-support indices of vertex a: ia | ib << 4) << 24: the face scan needs P[a]
+// of every face, and with the indices in the word it re-forms it without the dependent load of vw[a]
+// (the kernel's first stall line before, profiles/README.md).
+template <bool AS, bool BS> __device__ __forceinline__ uint32_t epa_sup_byte(const GjkVertex<AS, BS> &v)
+{
+    uint32_t w = 0;
+    if constexpr (!AS) w |= (uint32_t)v.a.idx;
+    if constexpr (!BS) w |= (uint32_t)v.b.idx << 4;
+    return w;
+}
+// P of a face's first vertex (same operands as epa_P: the same bits)
+template <bool AS, bool BS>
+__device__ __forceinline__ vec3 epa_P_face(const EpaGenericArena &E, const NpShapes &S, uint32_t fw)
+{
+#if NANS_EPA_FW
+    vec3 sa, sb;
+    if constexpr (AS) sa = E.SA[fw & 255u]; else sa = S.vertex(0, (fw >> 24) & 15u);
+    if constexpr (BS) sb = E.SB[fw & 255u]; else sb = S.vertex(1, fw >> 28);
+    return sa - sb;
+#else
+    return epa_P<AS, BS>(E, S, fw & 255u);
+#endif
+}
+
 // equal vectors have equal hashes: x + 0 maps -0 to +0, the one pair of different bit patterns that compare equal
 __device__ __forceinline__ uint32_t epa_hash16(vec3 p)
 {
@@ -276,20 +303,21 @@ __device__ __forceinline__ void epa_store_vertex(EpaGenericArena &E, const NpSha
 
 // closest face = FIRST strict minimum of |d| in face order (:807-822).  The reference rescans every
 // iteration; here the minimum is carried along while the face list is rebuilt in the same order.
-__device__ __forceinline__ void epa_track_min(float d, int slot, float &cur, int &ci)
+__device__ __forceinline__ void epa_track_min(float d, int slot, float &cur, int &ci, bool &cneg)
 {
     const float dist = fabsf(d);
-    if (slot == 0 || dist < cur) { cur = dist; ci = slot; }
+    if (slot == 0 || dist < cur) { cur = dist; ci = slot; cneg = d < 0.0f; }
 }
 
 template <bool AS, bool BS>
-__device__ __forceinline__ void epa_push_face(EpaGenericArena &E, const NpShapes &S, int &nf, int a, int b, int c, vec3 pa, float &cur, int &ci)
+__device__ __forceinline__ void epa_push_face(EpaGenericArena &E, const NpShapes &S, int &nf, int a, int b, int c, vec3 pa, uint32_t sup_a,
+                                              float &cur, int &ci, bool &cneg)
 {
     // PushTriangle, code/nans.cpp:293-322 (flip folded into the sign of d); pa == P[a]
     const vec3 n = normalize(cross(epa_P<AS, BS>(E, S, b) - pa, epa_P<AS, BS>(E, S, c) - pa));
     const float d = dot(pa, n);
-    E.fnd[nf] = make_float4(n.x, n.y, n.z, __uint_as_float((uint32_t)a | ((uint32_t)b << 8) | ((uint32_t)c << 16)));
-    epa_track_min(d, nf, cur, ci);
+    E.fnd[nf] = make_float4(n.x, n.y, n.z, __uint_as_float((uint32_t)a | ((uint32_t)b << 8) | ((uint32_t)c << 16) | (sup_a << 24)));
+    epa_track_min(d, nf, cur, ci, cneg);
     ++nf;
 }
 // PushTriangle's stored N (:316-320): the unit normal, flipped by the sign of d = dot(P[a], n)
@@ -327,10 +355,12 @@ __device__ __forceinline__ int epa_resolve(const NpShapes &S, const GjkVertex<AS
     for (int k = 0; k < 4; ++k) epa_store_vertex<AS, BS>(E, S, k, s[k]);
     int nv = 4, nf = 0, ne = 0, ci = 0, it = 0;
     float cur = 0.f;
-    epa_push_face<AS, BS>(E, S, nf, 0, 1, 2, s[0].P, cur, ci);  // ABC
-    epa_push_face<AS, BS>(E, S, nf, 0, 2, 3, s[0].P, cur, ci);  // ACD
-    epa_push_face<AS, BS>(E, S, nf, 0, 3, 1, s[0].P, cur, ci);  // ADB
-    epa_push_face<AS, BS>(E, S, nf, 1, 3, 2, s[1].P, cur, ci);  // BDC
+    bool cneg = false;              // the closest face's d is negative (its stored N is -n)
+    const uint32_t sb0 = epa_sup_byte<AS, BS>(s[0]), sb1 = epa_sup_byte<AS, BS>(s[1]);
+    epa_push_face<AS, BS>(E, S, nf, 0, 1, 2, s[0].P, sb0, cur, ci, cneg);  // ABC
+    epa_push_face<AS, BS>(E, S, nf, 0, 2, 3, s[0].P, sb0, cur, ci, cneg);  // ACD
+    epa_push_face<AS, BS>(E, S, nf, 0, 3, 1, s[0].P, sb0, cur, ci, cneg);  // ADB
+    epa_push_face<AS, BS>(E, S, nf, 1, 3, 2, s[1].P, sb1, cur, ci, cneg);  // BDC
     while (it++ <= 64) {            // MAX_EPA_ITERATIONS, code/nans.h:56
         // a BUDGETED run (max_iters < 65: the multi-pass batch path) gives up before iteration max_iters + 1; the
         // caller runs the pair again, from its simplex, with a larger budget
@@ -338,13 +368,17 @@ __device__ __forceinline__ int epa_resolve(const NpShapes &S, const GjkVertex<AS
         max_faces = max(max_faces, nf);
         const float4 cnd = E.fnd[ci];
         const uint32_t cf = __float_as_uint(cnd.w);
+#if NANS_EPA_FW
+        const vec3 N = cneg ? V3(cnd) * -1.0f : V3(cnd);     // the sign of d was kept when the face became the closest
+#else
         const vec3 N = face_normal_flipped(cnd, dot(epa_P<AS, BS>(E, S, cf & 255), V3(cnd)));
+#endif
         const GjkVertex<AS, BS> ns = calc_support<AS, BS>(S, N);
         if (fsub(dot(N, ns.P), cur) < 0.001f) {   // MAX_EPA_ERROR, code/nans.h:55
             const int a = cf & 255, b = (cf >> 8) & 255, c = (cf >> 16) & 255;
             // Barycentric, code/nans.cpp:772-785
             const vec3 Pp = N * cur;
-            const vec3 A0 = epa_P<AS, BS>(E, S, a);
+            const vec3 A0 = epa_P_face<AS, BS>(E, S, cf);
             const vec3 v0 = epa_P<AS, BS>(E, S, b) - A0, v1 = epa_P<AS, BS>(E, S, c) - A0, v2 = Pp - A0;
             const float d00 = dot(v0, v0), d01 = dot(v0, v1), d11 = dot(v1, v1);
             const float d20 = dot(v2, v0), d21 = dot(v2, v1);
@@ -371,20 +405,27 @@ __device__ __forceinline__ int epa_resolve(const NpShapes &S, const GjkVertex<AS
             const float4 nd = nd_next;
             const uint32_t f = __float_as_uint(nd.w);
             if (i + 1 < nf) nd_next = E.fnd[i + 1];
-            const vec3 pa = epa_P<AS, BS>(E, S, f & 255);
+            const vec3 pa = epa_P_face<AS, BS>(E, S, f);
             const float d = dot(pa, V3(nd));
             const vec3 tmp = ns.P - pa;
-            if (dot(face_normal_flipped(nd, d), tmp) > 0.0f) {
+#if NANS_EPA_FW
+            // dot(-n, tmp) is -dot(n, tmp) bit for bit (or both are zeros), so the flipped normal is never formed
+            const float tv = dot(V3(nd), tmp);
+            const bool sees = d < 0.0f ? tv < 0.0f : tv > 0.0f;
+#else
+            const bool sees = dot(face_normal_flipped(nd, d), tmp) > 0.0f;
+#endif
+            if (sees) {
                 E.vis[nvis++] = f;
             } else {
                 if (keep != i) E.fnd[keep] = nd;
-                epa_track_min(d, keep, cur, ci);
+                epa_track_min(d, keep, cur, ci, cneg);
                 ++keep;
             }
         }
         nf = keep;
         for (int j = 0; j < nvis; ++j) {
-            uint32_t f = E.vis[j];
+            uint32_t f = E.vis[j] & 0xffffffu;      // the three vertex indices (the support byte is not rotated)
             // the three vertices' classes, fetched once per face (every vertex is on two of its edges)
             uint32_t cl = epa_cid(E, f & 255) | (epa_cid(E, (f >> 8) & 255) << 8) | (epa_cid(E, (f >> 16) & 255) << 16);
 #pragma unroll 1
@@ -396,9 +437,10 @@ __device__ __forceinline__ int epa_resolve(const NpShapes &S, const GjkVertex<AS
         }
         // one new face per horizon edge, in edge-list order (:894-901)
         if (nf + ne > kEpaMaxFaces) { ovf |= OVF_EPA_FACES; return 0; }
+        const uint32_t sbn = epa_sup_byte<AS, BS>(ns);
         for (int i = 0; i < ne; ++i) {
             const uint32_t ed = E.edge[i];
-            epa_push_face<AS, BS>(E, S, nf, nv, ed & 255, (ed >> 8) & 255, ns.P, cur, ci);
+            epa_push_face<AS, BS>(E, S, nf, nv, ed & 255, (ed >> 8) & 255, ns.P, sbn, cur, ci, cneg);
         }
         ne = 0;
         ++nv;
@@ -412,7 +454,9 @@ __device__ __forceinline__ int epa_resolve(const NpShapes &S, const GjkVertex<AS
         if (nf == 0 && nf_old > 0) {
             const float4 last = E.fnd[nf_old - 1];
             E.fnd[0] = last;
-            cur = fabsf(dot(epa_P<AS, BS>(E, S, __float_as_uint(last.w) & 255), V3(last)));
+            const float dl = dot(epa_P_face<AS, BS>(E, S, __float_as_uint(last.w)), V3(last));
+            cur = fabsf(dl);
+            cneg = dl < 0.0f;
             ci = 0;
         }
     }
