@@ -11,7 +11,8 @@
 //     arenas of the resident threads compete for the L1): a box-pair vertex is its two support
 //     indices (P = A[ia] - B[ib] is re-formed from shared memory), a face is three byte indices plus
 //     a CACHED unflipped unit normal n; the signed plane offset d = dot(n, A.P) is re-formed next to
-//     the visibility test.  The reference recomputes normalize(cross(AB,AC)) for every face twice
+//     the visibility test; the face also carries the support indices of its first vertex, so that P[a] is
+//     re-formed without a second dependent load.  The reference recomputes normalize(cross(AB,AC)) for every face twice
 //     per iteration (closest-face scan :813-821 and visibility test :873-881); it is a pure function
 //     of the face's vertices, so it is computed once at face creation: |d| is the scan distance,
 //     the flipped normal is (d < 0 ? -n : n) = PushTriangle's stored N (:316-320);
@@ -206,7 +207,7 @@ __device__ __forceinline__ int evolve_simplex(const NpShapes &S, GjkVertex<AS, B
 //     sphere side adds its support point, 12 bytes).  P itself is never stored: P = SupA - SupB (CalculateSupport,
 //     :464-519) is re-formed from the same operands wherever it is used -- for a box pair six conflict-free
 //     shared-memory loads and three subtractions (round 1 stored 15 bytes per vertex);
-//   * a face record is 16 bytes {unflipped unit normal n, packed indices a | b<<8 | c<<16}; the plane offset
+//   * a face record is 16 bytes {unflipped unit normal n, packed indices a | b<<8 | c<<16 | support indices of a << 24}; the plane offset
 //     d = dot(P[a], n) is re-formed next to the visibility test, which needs P[a] anyway (round 1: 20 bytes;
 //     carrying P[a] in the record as well was measured then: slower).
 // Measured, step by step (1 M-cube pile 100^3 / flat 250x250x16 / config C3): narrowphase stage 0.367 -> 0.355 ->
@@ -244,12 +245,12 @@ __device__ __forceinline__ vec3 epa_P(const EpaGenericArena &E, const NpShapes &
 }
 __device__ __forceinline__ uint32_t epa_cid(const EpaGenericArena &E, int i) { return (E.vw[i] >> 8) & 255u; }
 
-#ifndef NANS_EPA_FW
-#define NANS_EPA_FW 0
-#endif
 // A face word is a | b << 8 | c << 16 | (box-support indices of vertex a: ia | ib << 4) << 24: the face scan needs P[a]
-// of every face, and with the indices in the word it re-forms it without the dependent load of vw[a]
-// (the kernel's first stall line before, profiles/README.md).
+// of every face, and with the indices in the word it re-forms it without the dependent load of vw[a] (that load was
+// the kernel's first stall line: 10 % of the samples).  With it, the closest face keeps the sign of its d (no
+// re-forming of P[a] at the head of an iteration) and the visibility test takes one dot product (the flipped
+// normal is never formed).  Measured (A/B, profiles/r4_ab_*.json): narrowphase stage 0.336 -> 0.324 ms on the 100^3
+// pile, 0.647 -> 0.623 ms on the flat pile, config C3 8.39e8 -> 8.58e8 pairs/s, config C4 unchanged.
 template <bool AS, bool BS> __device__ __forceinline__ uint32_t epa_sup_byte(const GjkVertex<AS, BS> &v)
 {
     uint32_t w = 0;
@@ -261,14 +262,10 @@ template <bool AS, bool BS> __device__ __forceinline__ uint32_t epa_sup_byte(con
 template <bool AS, bool BS>
 __device__ __forceinline__ vec3 epa_P_face(const EpaGenericArena &E, const NpShapes &S, uint32_t fw)
 {
-#if NANS_EPA_FW
     vec3 sa, sb;
     if constexpr (AS) sa = E.SA[fw & 255u]; else sa = S.vertex(0, (fw >> 24) & 15u);
     if constexpr (BS) sb = E.SB[fw & 255u]; else sb = S.vertex(1, fw >> 28);
     return sa - sb;
-#else
-    return epa_P<AS, BS>(E, S, fw & 255u);
-#endif
 }
 
 // equal vectors have equal hashes: x + 0 maps -0 to +0, the one pair of different bit patterns that compare equal
@@ -320,12 +317,6 @@ __device__ __forceinline__ void epa_push_face(EpaGenericArena &E, const NpShapes
     epa_track_min(d, nf, cur, ci, cneg);
     ++nf;
 }
-// PushTriangle's stored N (:316-320): the unit normal, flipped by the sign of d = dot(P[a], n)
-__device__ __forceinline__ vec3 face_normal_flipped(const float4 &nd, float d)
-{
-    const vec3 n = V3(nd);
-    return d < 0.0f ? n * -1.0f : n;
-}
 
 // PushEdge, code/nans.cpp:233-266: an opposite-winding edge already in the list is erased (order of
 // the rest kept), otherwise the edge is appended
@@ -368,11 +359,7 @@ __device__ __forceinline__ int epa_resolve(const NpShapes &S, const GjkVertex<AS
         max_faces = max(max_faces, nf);
         const float4 cnd = E.fnd[ci];
         const uint32_t cf = __float_as_uint(cnd.w);
-#if NANS_EPA_FW
         const vec3 N = cneg ? V3(cnd) * -1.0f : V3(cnd);     // the sign of d was kept when the face became the closest
-#else
-        const vec3 N = face_normal_flipped(cnd, dot(epa_P<AS, BS>(E, S, cf & 255), V3(cnd)));
-#endif
         const GjkVertex<AS, BS> ns = calc_support<AS, BS>(S, N);
         if (fsub(dot(N, ns.P), cur) < 0.001f) {   // MAX_EPA_ERROR, code/nans.h:55
             const int a = cf & 255, b = (cf >> 8) & 255, c = (cf >> 16) & 255;
@@ -408,13 +395,9 @@ __device__ __forceinline__ int epa_resolve(const NpShapes &S, const GjkVertex<AS
             const vec3 pa = epa_P_face<AS, BS>(E, S, f);
             const float d = dot(pa, V3(nd));
             const vec3 tmp = ns.P - pa;
-#if NANS_EPA_FW
             // dot(-n, tmp) is -dot(n, tmp) bit for bit (or both are zeros), so the flipped normal is never formed
             const float tv = dot(V3(nd), tmp);
             const bool sees = d < 0.0f ? tv < 0.0f : tv > 0.0f;
-#else
-            const bool sees = dot(face_normal_flipped(nd, d), tmp) > 0.0f;
-#endif
             if (sees) {
                 E.vis[nvis++] = f;
             } else {
