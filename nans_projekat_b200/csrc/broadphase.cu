@@ -105,9 +105,25 @@ __device__ __forceinline__ float order_float(uint32_t e)
 }
 
 // AABB per body + the largest AABB extent of this step (block reduce -> one atomicMax per block).
-__global__ void __launch_bounds__(256) aabb_kernel(DeviceWorld w)
+#ifndef NANS_BP_FOLD
+#define NANS_BP_FOLD 0   // the clears of the cell table / cell sizes / pair counts ride in aabb_kernel (no memset nodes)
+#endif
+__global__ void __launch_bounds__(256) aabb_kernel(DeviceWorld w, int clear)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (clear) {
+        // what the later kernels of the stage accumulate into, cleared here: coalesced 16-byte / 4-byte stores spread
+        // over the grid instead of three memset nodes between the kernels (each a launch gap on the step's critical path)
+        const size_t nthreads = (size_t)gridDim.x * blockDim.x;
+        const size_t table = (size_t)w.cell_mask + 1;
+        for (size_t s = (size_t)i; s < table; s += nthreads) {
+            w.cell_tab[s] = make_uint4(kEmptyKey, kEmptyKey, kEmptyKey, kEmptyKey);
+            w.cell_count[s] = 0u;
+        }
+        if (i == 0) w.cell_count[table] = 0u;
+        const size_t npc = (size_t)w.n_seg * w.nb + 1;
+        for (size_t s = (size_t)i; s < npc; s += nthreads) w.pair_count[s] = 0u;
+    }
     if (i < w.n_statics) {   // statics: AABB only (tested against every body, never sorted)
         float lo[3], hi[3];
         box_aabb(w.st_verts + 6 * i, lo, hi);
@@ -498,6 +514,7 @@ __global__ void __launch_bounds__(128) pair_emit_kernel(DeviceWorld w)
         if (t == 0) {
             const uint32_t total = w.pair_count[(size_t)w.n_seg * w.nb];
             w.counters->n_pairs = (int32_t)min(total, (uint32_t)w.max_pairs);
+            w.pair_hit[min(total, (uint32_t)w.max_pairs)] = 0;    // sentinel: the scan of the hit flags yields the total
             if (total > (uint32_t)w.max_pairs) atomicOr(&w.counters->overflow, OVF_PAIRS);
         }
         return;
@@ -543,6 +560,7 @@ __global__ void __launch_bounds__(128) pair_emit_kernel(DeviceWorld w)
     if (t == 0) {
         const uint32_t total = w.pair_count[(size_t)w.n_seg * w.nb];
         w.counters->n_pairs = (int32_t)min(total, cap);
+        w.pair_hit[min(total, cap)] = 0;                          // sentinel: the scan of the hit flags yields the total
         if (total > cap) atomicOr(&w.counters->overflow, OVF_PAIRS);
     }
 }
@@ -552,7 +570,7 @@ int launch_aabb_only(World *w)
 {
     DeviceWorld &d = w->d;
     if (d.nb == 0) return NANS_OK;
-    aabb_kernel<<<div_up(max(d.nb, d.n_statics), 256), 256, 0, w->stream>>>(d);
+    aabb_kernel<<<div_up(max(d.nb, d.n_statics), 256), 256, 0, w->stream>>>(d, 0);
     NANS_LAUNCH_CHECK();
     return NANS_OK;
 }
@@ -565,15 +583,17 @@ int launch_broadphase(World *w)
     const int nb = d.nb;
     NANS_CUDA(cudaMemsetAsync(d.counters, 0, sizeof(Counters), s));
     if (nb == 0) return NANS_OK;
-    aabb_kernel<<<div_up(max(nb, d.n_statics), 256), 256, 0, s>>>(d);
+    aabb_kernel<<<div_up(max(nb, d.n_statics), 256), 256, 0, s>>>(d, NANS_BP_FOLD);
     NANS_LAUNCH_CHECK();
     key_kernel<<<div_up(nb, 256), 256, 0, s>>>(d);
     NANS_LAUNCH_CHECK();
 
     // counting sort by cell: table + cell sizes cleared, insert, scan, scatter
     const size_t table = (size_t)d.cell_mask + 1;
+#if !NANS_BP_FOLD
     NANS_CUDA(cudaMemsetAsync(d.cell_tab, 0xff, sizeof(uint4) * table, s));
     NANS_CUDA(cudaMemsetAsync(d.cell_count, 0, sizeof(uint32_t) * (table + 1), s));
+#endif
     cell_insert_kernel<<<div_up(nb, 256), 256, 0, s>>>(d);
     NANS_LAUNCH_CHECK();
     int rc = exclusive_scan_u32(d.cell_count, d.cell_count, (int)table + 1, d.scan_block, s);
@@ -581,7 +601,9 @@ int launch_broadphase(World *w)
     cell_scatter_kernel<<<div_up(nb, 256), 256, 0, s>>>(d);
     NANS_LAUNCH_CHECK();
     // counts per (type, body) are accumulated with atomics; a cube-only world only has the CC and CF segments
+#if !NANS_BP_FOLD
     NANS_CUDA(cudaMemsetAsync(d.pair_count, 0, sizeof(uint32_t) * ((size_t)d.n_seg * nb + 1), s));
+#endif
     pair_count_kernel<<<div_up(nb, 128), 128, 0, s>>>(d);
     NANS_LAUNCH_CHECK();
     rc = exclusive_scan_u32(d.pair_count, d.pair_count, d.n_seg * nb + 1, d.scan_block, s);

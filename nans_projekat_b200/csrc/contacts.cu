@@ -65,8 +65,14 @@ int launch_contacts(World *w)
     if (d.nb == 0) return NANS_OK;
     cudaStream_t s = w->stream;
     const int grid = min(div_up(d.max_pairs + 1, 256), kNumSMs * 8);
-    cs_dedup_kernel<<<grid, 256, 0, s>>>(d);
-    NANS_LAUNCH_CHECK();
+#ifndef NANS_CT_SKIP
+#define NANS_CT_SKIP 0
+#endif
+    // a world without spheres has no CS pairs to drop; the sentinel behind the hit flags is written by pair_emit_kernel
+    if (!NANS_CT_SKIP || d.n_spheres > 0) {
+        cs_dedup_kernel<<<grid, 256, 0, s>>>(d);
+        NANS_LAUNCH_CHECK();
+    }
     int rc = exclusive_scan_u32_dn((const uint32_t *)d.pair_hit, d.pair_hit_scan, d.max_pairs + 1,
                                    &d.counters->n_pairs, 1, d.scan_block, s);
     if (rc) return rc;

@@ -112,8 +112,14 @@ __global__ void __launch_bounds__(kScanThreads) scan_apply_kernel(const uint32_t
 // (Round 2 measured a FLAT look-back for scans of up to 1024 tiles -- every block sums the aggregates of all its
 // predecessors in one sweep instead of walking back 32 at a time: 0.943 vs 0.940 ms per step, no difference; the
 // ~11 us of a 2 M-element scan is not the look-back chain.  Removed.)
-constexpr int kLbThreads = 256;
-constexpr int kLbItems = 16;
+#ifndef NANS_LB_THREADS
+#define NANS_LB_THREADS 256
+#endif
+#ifndef NANS_LB_ITEMS
+#define NANS_LB_ITEMS 16
+#endif
+constexpr int kLbThreads = NANS_LB_THREADS;
+constexpr int kLbItems = NANS_LB_ITEMS;
 constexpr int kLbTile = kLbThreads * kLbItems;   // 4096
 
 __device__ __forceinline__ unsigned long long lb_pack(uint32_t epoch, uint32_t status, uint32_t value)
