@@ -5,7 +5,8 @@
 // CS (cube-major), SS (i<j) — so that compaction of the narrowphase hits yields the reference's
 // contact list with no sort of the contacts.
 //
-//   aabb_kernel          AABB per body (8 vertices / centre +- radius) + this step's largest extent
+//   aabb_kernel          AABB per body (8 vertices / centre +- radius) + this step's largest extent; also clears the
+//                        cell table, the cell sizes and the pair counts the later kernels accumulate into
 //   key_kernel           30-bit Morton key of the cell (edge = largest extent) holding the AABB centre
 //   cell_insert_kernel   counting sort, pass 1: the body's cell is found-or-inserted in the cell table (open
 //                        addressing; slot = the Morton key itself while it fits the table, so slot order IS
@@ -105,15 +106,13 @@ __device__ __forceinline__ float order_float(uint32_t e)
 }
 
 // AABB per body + the largest AABB extent of this step (block reduce -> one atomicMax per block).
-#ifndef NANS_BP_FOLD
-#define NANS_BP_FOLD 0   // the clears of the cell table / cell sizes / pair counts ride in aabb_kernel (no memset nodes)
-#endif
 __global__ void __launch_bounds__(256) aabb_kernel(DeviceWorld w, int clear)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (clear) {
         // what the later kernels of the stage accumulate into, cleared here: coalesced 16-byte / 4-byte stores spread
-        // over the grid instead of three memset nodes between the kernels (each a launch gap on the step's critical path)
+        // over the grid instead of three memset nodes between the kernels (each a launch gap on the step's critical
+        // path): broadphase stage 0.287 -> 0.275 ms on the 1 M-cube pile (profiles/r4_ab_*.json)
         const size_t nthreads = (size_t)gridDim.x * blockDim.x;
         const size_t table = (size_t)w.cell_mask + 1;
         for (size_t s = (size_t)i; s < table; s += nthreads) {
@@ -583,27 +582,21 @@ int launch_broadphase(World *w)
     const int nb = d.nb;
     NANS_CUDA(cudaMemsetAsync(d.counters, 0, sizeof(Counters), s));
     if (nb == 0) return NANS_OK;
-    aabb_kernel<<<div_up(max(nb, d.n_statics), 256), 256, 0, s>>>(d, NANS_BP_FOLD);
+    aabb_kernel<<<div_up(max(nb, d.n_statics), 256), 256, 0, s>>>(d, 1);
     NANS_LAUNCH_CHECK();
     key_kernel<<<div_up(nb, 256), 256, 0, s>>>(d);
     NANS_LAUNCH_CHECK();
 
-    // counting sort by cell: table + cell sizes cleared, insert, scan, scatter
+    // counting sort by cell (table + cell sizes were cleared by aabb_kernel): insert, scan, scatter
     const size_t table = (size_t)d.cell_mask + 1;
-#if !NANS_BP_FOLD
-    NANS_CUDA(cudaMemsetAsync(d.cell_tab, 0xff, sizeof(uint4) * table, s));
-    NANS_CUDA(cudaMemsetAsync(d.cell_count, 0, sizeof(uint32_t) * (table + 1), s));
-#endif
     cell_insert_kernel<<<div_up(nb, 256), 256, 0, s>>>(d);
     NANS_LAUNCH_CHECK();
     int rc = exclusive_scan_u32(d.cell_count, d.cell_count, (int)table + 1, d.scan_block, s);
     if (rc) return rc;
     cell_scatter_kernel<<<div_up(nb, 256), 256, 0, s>>>(d);
     NANS_LAUNCH_CHECK();
-    // counts per (type, body) are accumulated with atomics; a cube-only world only has the CC and CF segments
-#if !NANS_BP_FOLD
-    NANS_CUDA(cudaMemsetAsync(d.pair_count, 0, sizeof(uint32_t) * ((size_t)d.n_seg * nb + 1), s));
-#endif
+    // counts per (type, body) are accumulated with atomics (cleared by aabb_kernel); a cube-only world only has the CC
+    // and CF segments
     pair_count_kernel<<<div_up(nb, 128), 128, 0, s>>>(d);
     NANS_LAUNCH_CHECK();
     rc = exclusive_scan_u32(d.pair_count, d.pair_count, d.n_seg * nb + 1, d.scan_block, s);

@@ -16,7 +16,7 @@ __global__ void __launch_bounds__(256) cs_dedup_kernel(DeviceWorld w)
     const int n_pairs = w.counters->n_pairs;
     const int stride = gridDim.x * blockDim.x;
     for (int p = blockIdx.x * blockDim.x + threadIdx.x; p <= n_pairs; p += stride) {
-        if (p == n_pairs) { w.pair_hit[p] = 0; break; }   // sentinel so the scan yields the total
+        if (p == n_pairs) break;
         const int a = w.pair_a[p], b = w.pair_b[p];
         if (!(a < w.n_cubes && b >= w.n_cubes) || !w.pair_hit[p]) continue;   // hit CS pairs only
         const int cube = a, sph = b - w.n_cubes;
@@ -65,11 +65,8 @@ int launch_contacts(World *w)
     if (d.nb == 0) return NANS_OK;
     cudaStream_t s = w->stream;
     const int grid = min(div_up(d.max_pairs + 1, 256), kNumSMs * 8);
-#ifndef NANS_CT_SKIP
-#define NANS_CT_SKIP 0
-#endif
     // a world without spheres has no CS pairs to drop; the sentinel behind the hit flags is written by pair_emit_kernel
-    if (!NANS_CT_SKIP || d.n_spheres > 0) {
+    if (d.n_spheres > 0) {
         cs_dedup_kernel<<<grid, 256, 0, s>>>(d);
         NANS_LAUNCH_CHECK();
     }
