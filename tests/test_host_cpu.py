@@ -87,3 +87,21 @@ def test_headers_are_plain_c(tmp_path):
         src = tmp_path / (h + ".c")
         src.write_text(f'#include "{os.path.join(ROOT, "include", h)}"\nint main(void) {{ return 0; }}\n')
         subprocess.check_call(["gcc", "-std=c11", "-Wall", "-Werror", "-fsyntax-only", str(src)])
+
+
+def test_plugin_exports_the_reference_entry_and_fails_loudly_without_a_device(built):
+    """The drop-in plugin exports the reference's ONE entry point (code/nans.h:396-397) under its C name, and the
+    headless host + plugin abort with the CUDA layer's error text when no device is usable: no CPU fallback."""
+    host_dir = os.path.join(ROOT, "nans_projekat_b200", "host")
+    plugin = os.path.join(host_dir, "nans.so")
+    assert os.path.exists(plugin), "build() did not produce the plugin"
+    syms = subprocess.check_output(["nm", "-D", "--defined-only", plugin]).decode()
+    exported = {l.split()[-1] for l in syms.splitlines() if " T " in l}
+    assert "SimUpdateAndRender" in exported and "NansPluginPeek" in exported
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    r = subprocess.run([os.path.join(host_dir, "nans"), "--frames", "2", "--dt", "0.016666668"], cwd=host_dir,
+                       capture_output=True, text=True, timeout=60)
+    assert r.returncode != 0
+    assert "nans_world_create" in (r.stderr + r.stdout)
