@@ -1,5 +1,5 @@
-"""The ordering argument of the multi-GPU slab decomposition (csrc/slab.cu) on CPU: world_size-2
-and -3 gloo process groups, the oracle as the per-rank engine (tests/slab_protocol_model.py).  The decomposed
+"""The ordering argument of the multi-GPU slab decomposition (csrc/slab.cu) on CPU: world_size-2, -3
+and -4 gloo process groups, the oracle as the per-rank engine (tests/slab_protocol_model.py).  The decomposed
 world must stay BIT-IDENTICAL to the same world stepped as one piece.  Scene: the slab-major numbered pile the
 GPU path uses (index ranges = spatial x-slabs)."""
 import os
@@ -48,7 +48,7 @@ def _worker(rank, size, port, steps, q):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("size", [2, 3])
+@pytest.mark.parametrize("size", [2, 3, 4])
 def test_slab_protocol_is_exact(oracle, size):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
